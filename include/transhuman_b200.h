@@ -1,0 +1,224 @@
+/*
+ * transhuman_b200 -- C ABI of the B200-native TransHuman query path.
+ *
+ * Drop-in boundary for the per-ray volumetric query path of
+ * pansanity666/TransHuman (sample -> cull -> k-NN/DPaRF -> pixel-aligned
+ * gather -> per-point MLP -> alpha compositing).  The reference has no FFI:
+ * its boundary is the Python plugin surface `Renderer(net).render /
+ * render_fast` selected by the YAML keys `renderer_module` / `renderer_path`
+ * (lib/networks/renderer/make_renderer.py:4-8).  `transhuman_b200/renderer.py`
+ * implements that surface and calls the entry points below through ctypes;
+ * INTEGRATION.md shows the binding.  Each entry point cites the reference
+ * code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless its name
+ *    ends in `_host`; fp32 unless stated; all tensors contiguous;
+ *  - return 0 on success, a negative TH_E* code otherwise (never throws, never
+ *    exits); `th_last_error()` returns a thread-local message;
+ *  - asynchronous with respect to the host on `stream` unless stated; the
+ *    library allocates nothing persistent: the caller passes a workspace of
+ *    at least `th_workspace_bytes(...)` bytes (256-byte aligned);
+ *  - forward only (training keeps the reference's torch path).
+ */
+#ifndef TRANSHUMAN_B200_H
+#define TRANSHUMAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TH_OK 0
+#define TH_EINVAL (-1)     /* bad argument (null pointer, unsupported shape) */
+#define TH_EWORKSPACE (-2) /* workspace too small */
+#define TH_ECUDA (-3)      /* a CUDA call / launch failed */
+#define TH_EUNSUPPORTED (-4)
+
+#define TH_C_TOK 192 /* token feature width, cfg.embed_size (vit_tiny)            */
+#define TH_C_PIX 384 /* pixel-aligned feature width, encoder.py:133-146           */
+#define TH_C_REP 255 /* 192 + 63, cross_transformer.py:106                        */
+#define TH_C_VIEW 27 /* view-direction embedding, embedder.py (view_res = 4)      */
+#define TH_MAX_VIEWS 4
+#define TH_TRAIN_BRANCH_MAX_RAYS 2400 /* if_clight_renderer.py:551 */
+
+/* `culled` argument of th_render_rays */
+#define TH_RENDER_DENSE 0   /* Renderer.render: every sample evaluated             */
+#define TH_RENDER_MASKED 1  /* render_fast, chunked branch: only points within the
+                               cull radius are evaluated, progressive RGB          */
+#define TH_RENDER_FAST 2    /* render_fast literally: as MASKED when more than
+                               TH_TRAIN_BRANCH_MAX_RAYS rays survive the cull, else
+                               every sample of the surviving rays (the reference's
+                               un-chunked branch drops pts_mask)                    */
+#define TH_MAX_KNN 16
+
+/* Flags for ThFrame.flags / th_render_rays */
+#define TH_FLAG_WHITE_BKGD 1u /* cfg.white_bkgd, nerf_net_utils.py:56-57 */
+#define TH_FLAG_SIMT_MLP 2u   /* force the fp32 CUDA-core GEMM path (debug / parity) */
+
+/* Per-frame state: the outputs of the (out-of-scope, torch) prologue that the
+ * query path consumes.  Built once per frame by the Python Renderer. */
+typedef struct ThFrame {
+  /* tokens: ViT output `holder_completed` (if_clight_renderer.py:538) and the
+   * DPaRF parameters `obs_smpl_smplcoord`, `blend_mtx[..., :3, :3].float()`
+   * (if_clight_renderer.py:541-544, cross_transformer.py:185) */
+  const float* tok_feat; /* (V, n_tok, 192)                               */
+  const float* tok_xyz;  /* (n_tok, 3)   SMPL coordinates                 */
+  const float* tok_rot;  /* (n_tok, 3, 3) row-major                       */
+  /* cull set: batch['tar_smpl_vertice'] (if_clight_renderer.py:440)      */
+  const float* verts;    /* (n_verts, 3) world coordinates                */
+  /* encoder output `pixel_feat_map` (if_clight_renderer.py:399), stored
+   * channel-last: (V, H, W, 384).  th_nchw_to_nhwc converts.             */
+  const float* feat;
+  /* input cameras batch['input_R'|'input_T'|'input_K'][0]
+   * (if_clight_renderer.py:215-221)                                      */
+  const float* cam_R;    /* (V, 3, 3) */
+  const float* cam_T;    /* (V, 3)    */
+  const float* cam_K;    /* (V, 3, 3) */
+  /* batch['Rh'], batch['Th'] (if_clight_renderer.py:289-295, 520)        */
+  const float* Rh;       /* (3, 3)    */
+  const float* Th;       /* (3)       */
+  const void* weights;   /* blob written by th_pack_weights, uploaded by the caller */
+  int32_t n_views;       /* V: 1..TH_MAX_VIEWS                            */
+  int32_t n_tok;         /* cfg.num_class                                 */
+  int32_t n_verts;       /* 6890 for SMPL                                 */
+  int32_t feat_h, feat_w;
+  int32_t knn;           /* cfg.KNN (7), <= TH_MAX_KNN                    */
+  /* uv -> [-1,1]: `feat_scale / image_shape` evaluated in float64 on the host
+   * then cast (if_clight_renderer.py:193-197; x uses index 0, y index 1) */
+  float uv_scale_x, uv_scale_y;
+  float knn_dist_alpha;  /* cfg.KNN_DIST_ALPHA = 0.5, cross_transformer.py:154 */
+  float cull_radius;     /* 0.1, if_clight_renderer.py:442                */
+  uint32_t flags;
+} ThFrame;
+
+/* Ray bundle: batch['ray_o','ray_d','near','far'] (if_clight_renderer.py:431-434)
+ * and the S-float `torch.linspace(0,1,S)` table the reference evaluates on the
+ * CPU (if_clight_renderer.py:273) -- taken as an input so z_vals are bit-exact. */
+typedef struct ThRays {
+  const float* ray_o;  /* (N, 3) */
+  const float* ray_d;  /* (N, 3) */
+  const float* near_;  /* (N)    */
+  const float* far_;   /* (N)    */
+  const float* t_vals; /* (S)    */
+  int64_t n_rays;
+  int32_t n_samples;
+} ThRays;
+
+/* Outputs of Renderer._render (if_clight_renderer.py:599): caller-allocated. */
+typedef struct ThOut {
+  float* rgb_map;   /* (N, 3) */
+  float* acc_map;   /* (N)    */
+  float* depth_map; /* (N)    */
+  /* optional debug taps (may be NULL) */
+  float* raw;       /* (N, S, 4): (rgb raw x3, alpha raw); 0 where culled */
+  uint8_t* pts_mask; /* (N, S): cull result (1 = within cull_radius)      */
+  int64_t* counters_host; /* HOST, optional: [0] = points within the cull radius,
+                             [1] = surviving rays, [2] = points evaluated        */
+} ThOut;
+
+/* The 16 Conv1d(k=1) layers of the per-point network, HOST pointers, reference
+ * state_dict names (cross_transformer.py:97-126); weight (out, in) row-major. */
+typedef struct ThWeightsF32 {
+  const float *fc_0_w, *fc_0_b;               /* (256,255) */
+  const float *alpha_res_0_w, *alpha_res_0_b; /* (256,384) */
+  const float *skv0_key_w, *skv0_key_b;       /* spatial_key_value_0.key_embed   (128,256) */
+  const float *skv0_value_w, *skv0_value_b;   /* spatial_key_value_0.value_embed (256,256) */
+  const float *skv1_key_w, *skv1_key_b;       /* spatial_key_value_1.key_embed   (128,256) */
+  const float *skv1_value_w, *skv1_value_b;   /* spatial_key_value_1.value_embed (256,256) */
+  const float *fc_1_w, *fc_1_b;               /* (256,256) */
+  const float *fc_2_w, *fc_2_b;               /* (256,256) */
+  const float *fc_3_w, *fc_3_b;               /* (256,256) */
+  const float *alpha_fc_w, *alpha_fc_b;       /* (1,256)   */
+  const float *feature_fc_w, *feature_fc_b;   /* (256,256) */
+  const float *rgb_res_0_w, *rgb_res_0_b;     /* (256,384) */
+  const float *view_fc_w, *view_fc_b;         /* (128,283) */
+  const float *rgb_res_1_w, *rgb_res_1_b;     /* (128,384) */
+  const float *fc_4_w, *fc_4_b;               /* (128,128) */
+  const float *rgb_fc_w, *rgb_fc_b;           /* (3,128)   */
+} ThWeightsF32;
+
+/* ---- library ---------------------------------------------------------- */
+const char* th_version(void);
+const char* th_last_error(void);
+
+/* ---- weights (host side, no CUDA call): replaces load_network's role of
+ * turning a state_dict into what the kernels read (net_utils.py:361-392) ---- */
+size_t th_packed_weights_bytes(int32_t n_views);
+int th_pack_weights(const ThWeightsF32* w_host, int32_t n_views, void* packed_host, size_t bytes);
+
+/* ---- fused path --------------------------------------------------------- */
+/* Workspace needed by th_render_rays / th_query_density for up to `n_points`
+ * sample points in flight (n_rays * n_samples for rays). */
+size_t th_workspace_bytes(int64_t n_points, int32_t n_views, int32_t n_verts);
+
+/* Renderer.render (dense: every sample evaluated, pts_mask=None;
+ * if_clight_renderer.py:486-498 -> 500-605) when culled == 0, and
+ * Renderer.render_fast (K=1 cull at cull_radius, masked points give raw = 0,
+ * culled rays give 0; if_clight_renderer.py:429-484 with the chunk loop
+ * 607-656, Network.forward cross_transformer.py:207-271 and raw2outputs
+ * nerf_net_utils.py:14-59) when culled != 0 (TH_RENDER_*).  Rows a1-a11 of
+ * SURVEY 8(a).  Synchronises the stream once when culled != 0 (to read the
+ * survivor count). */
+int th_render_rays(const ThFrame* frame, const ThRays* rays, ThOut* out, int32_t culled,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Mesh renderer's grid query (if_mesh_renderer.py:46-96): cull, zero view
+ * direction, alpha_raw only.  pts (P,3) world; alpha_raw (P) gets raw[...,-1]
+ * (0 where culled); mask (P) optional.  Row a12. */
+int th_query_density(const ThFrame* frame, const float* pts, int64_t n_points, float* alpha_raw,
+                     uint8_t* mask, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- staged entry points (parity / debugging; same arithmetic as the fused
+ * path, reference tensor layouts) ------------------------------------------ */
+/* a1: Renderer.get_sampling_points (if_clight_renderer.py:271-287, no jitter):
+ * pts (N,S,3), z_vals (N,S). */
+int th_sample_points(const ThRays* rays, float* pts, float* z_vals, void* stream);
+/* a2: knn_points(pts, verts, K=1) + sqrt + `< radius` (if_clight_renderer.py:440-442,
+ * if_mesh_renderer.py:53-55).  Brute force: d2 (P) and idx (P) of the nearest
+ * vertex (lower index on ties), mask (P).  Any output may be NULL. */
+int th_cull_knn1(const float* pts, int64_t n_points, const float* verts, int32_t n_verts, float radius,
+                 float* d2, int64_t* idx, uint8_t* mask, void* stream);
+/* a2 (fast): the same mask from a uniform-grid search (exactly equal to the
+ * brute-force mask); needs a workspace of th_workspace_bytes(0, 1, n_verts). */
+int th_cull_grid(const float* pts, int64_t n_points, const float* verts, int32_t n_verts, float radius,
+                 uint8_t* mask, void* workspace, size_t workspace_bytes, void* stream);
+/* a3: Renderer.world2smpl (if_clight_renderer.py:289-295). */
+int th_world2smpl(const float* pts, int64_t n_points, const float* Rh, const float* Th, float* out,
+                  void* stream);
+/* a4: view-direction embedding (if_clight_renderer.py:525-526, embedder.py): (N,27). */
+int th_view_embed(const float* ray_d, int64_t n_rays, float* out, void* stream);
+/* a5: get_pixel_aligned_feature + sample_from_feature_map
+ * (if_clight_renderer.py:186-269): pts (P,3) world -> pixel_feat (V,384,P). */
+int th_pixel_gather(const ThFrame* frame, const float* pts, int64_t n_points, float* pixel_feat,
+                    void* stream);
+/* a8: get_human_representation (cross_transformer.py:158-205): pts (P,3) SMPL
+ * coordinates -> knn_idx (P,K) int64, knn_d2 (P,K) squared, human_rep (V,255,P).
+ * Outputs may be NULL. */
+int th_knn_dparf(const ThFrame* frame, const float* pts_smpl, int64_t n_points, int64_t* knn_idx,
+                 float* knn_d2, float* human_rep, void* stream);
+/* a9+a10: the per-point network from its reference inputs
+ * (cross_transformer.py:273-353): human_rep (V,255,P), pixel_feat (V,384,P),
+ * viewdir (P,27), pts_mask (P) or NULL -> raw (P,4).  With a mask, masked-out
+ * points get raw = 0 and rgb is 0 where alpha_raw <= 0 (the progressive
+ * variant, 291-311).  workspace >= th_workspace_bytes(P, V, 0). */
+int th_mlp_raw(const ThFrame* frame, const float* human_rep, const float* pixel_feat, const float* viewdir,
+               const uint8_t* pts_mask, int64_t n_points, float* raw, void* workspace,
+               size_t workspace_bytes, void* stream);
+/* a11: raw2outputs (nerf_net_utils.py:14-59; raw_noise_std = 0). */
+int th_integrate(const float* raw, const float* z_vals, const float* ray_d, int64_t n_rays,
+                 int32_t n_samples, int32_t white_bkgd, float* rgb_map, float* acc_map, float* depth_map,
+                 void* stream);
+/* layout helper: (V,C,H,W) -> (V,H,W,C). */
+int th_nchw_to_nhwc(const float* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
+
+/* Number of kernels this library launched on the calling thread since the last
+ * reset (bench.py reports it as gpu_launches). */
+int64_t th_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRANSHUMAN_B200_H */

@@ -1,0 +1,134 @@
+"""Host-side checks of the C ABI that need no GPU: the library loads, exports
+every symbol include/transhuman_b200.h declares, packs weights correctly, and
+the product path refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import ROOT
+from transhuman_b200 import _lib, ops, synth
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    return _lib.load()
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "transhuman_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(th_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == declared
+    assert b"sm_100a" in lib.th_version()
+
+
+def test_struct_layouts_match_header():
+    # ThFrame: 11 pointers, 6 int32, 4 float, 1 uint32 -> 88 + 44 = 132 -> padded to 136
+    assert C.sizeof(_lib.ThFrame) == 136
+    assert C.sizeof(_lib.ThRays) == 56
+    assert C.sizeof(_lib.ThOut) == 48
+    assert C.sizeof(_lib.ThWeightsF32) == 32 * 8
+
+
+def test_pack_weights_folds_layers(lib):
+    w = synth.make_weights(seed=5)
+    for V in (1, 3):
+        pw_bytes = lib.th_packed_weights_bytes(V)
+        assert pw_bytes > 3_000_000
+        wstruct = _lib.ThWeightsF32()
+        keep = []
+        for cname, rname in _lib.WEIGHT_FIELDS:
+            for suf, key in (("w", rname + ".weight"), ("b", rname + ".bias")):
+                a = np.ascontiguousarray(w[key].reshape(-1))
+                keep.append(a)
+                setattr(wstruct, f"{cname}_{suf}", a.ctypes.data)
+        blob = np.zeros(pw_bytes, dtype=np.uint8)
+        assert lib.th_pack_weights(C.byref(wstruct), V, blob.ctypes.data, pw_bytes) == 0
+        # too small a buffer -> TH_EWORKSPACE with a message
+        assert lib.th_pack_weights(C.byref(wstruct), V, blob.ctypes.data, 16) == -2
+        assert b"need" in lib.th_last_error()
+        magic, nviews, total = struct.unpack_from("<IiQ", blob, 0)
+        assert magic == 0x31574854 and nviews == V and total == pw_bytes
+        offs = struct.unpack_from("<37Q", blob, 16)
+        f32 = lambda off, n: blob[off:off + 4 * n].view(np.float32)
+        # fc_0: K padded 255 -> 256 with a zero column
+        fc0 = f32(offs[0], 256 * 256).reshape(256, 256)
+        assert np.array_equal(fc0[:, :255], w["fc_0.weight"]) and np.all(fc0[:, 255] == 0)
+        # W_v = [value_embed_1 | value_embed_0], b = b1 + b0
+        wv = f32(offs[8], 256 * 512).reshape(256, 512)
+        assert np.array_equal(wv[:, :256], w["spatial_key_value_1.value_embed.weight"])
+        assert np.array_equal(wv[:, 256:], w["spatial_key_value_0.value_embed.weight"])
+        # fc_3 with the view mean folded into K
+        w3 = f32(offs[14], 256 * 256 * V).reshape(256, 256 * V)
+        for v in range(V):
+            np.testing.assert_allclose(w3[:, 256 * v:256 * (v + 1)], w["fc_3.weight"] / V, rtol=1e-7)
+        # W_t = [fc_4/V ... | fc_4 @ rgb_res_1], b_t = fc_4 @ b_r1 + b_4
+        ld = 128 * V + 384
+        wt = f32(offs[22], 128 * ld).reshape(128, ld)
+        want = w["fc_4.weight"].astype(np.float64) @ w["rgb_res_1.weight"].astype(np.float64)
+        np.testing.assert_allclose(wt[:, 128 * V:], want, rtol=0, atol=1e-7)
+        bt = f32(offs[23], 128)
+        wantb = w["fc_4.weight"].astype(np.float64) @ w["rgb_res_1.bias"].astype(np.float64) + w["fc_4.bias"]
+        np.testing.assert_allclose(bt, wantb, rtol=0, atol=1e-7)
+        # fp16 hi/lo planes reconstruct the fp32 matrix to ~2^-22 relative
+        h_fc0 = offs[26]
+        hi = blob[h_fc0:h_fc0 + 2 * 65536].view(np.float16).astype(np.float32)
+        lo = blob[h_fc0 + 2 * 65536:h_fc0 + 4 * 65536].view(np.float16).astype(np.float32)
+        assert np.abs((hi + lo) - fc0.reshape(-1)).max() <= 2.0 ** -21 * np.abs(fc0).max()
+
+
+def test_workspace_bytes(lib):
+    a = lib.th_workspace_bytes(1000, 3, 6890)
+    b = lib.th_workspace_bytes(100000, 3, 6890)
+    c = lib.th_workspace_bytes(262144 * 64, 3, 6890)
+    assert 0 < a < b < c < 8 << 30
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are rejected; nothing in the package imports the oracle."""
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.view_embed(torch.zeros((4, 3)))
+    pkg = os.path.join(ROOT, "transhuman_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+    if not torch.cuda.is_available():
+        lib = _lib.load()
+        out = np.zeros(27, dtype=np.float32)
+        # a compute entry point without a device reports TH_ECUDA, it does not compute on the host
+        rc = lib.th_view_embed(C.c_void_p(out.ctypes.data), 1, C.c_void_p(out.ctypes.data), None)
+        assert rc == -3 and lib.th_last_error()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.TransHumanLibraryError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_synth_frame_is_deterministic():
+    a = synth.make_frame(H=8, W=8, n_class=100, V=2, feat_hw=8, seed=3)
+    b = synth.make_frame(H=8, W=8, n_class=100, V=2, feat_hw=8, seed=3)
+    for k in ("ray_o", "ray_d", "holder", "pixel_feat_map", "tar_smpl_vertice", "pc2voxel_ind"):
+        assert np.array_equal(a[k], b[k])
+    assert sorted(np.unique(a["pc2voxel_ind"])) == list(range(100))
+    v = a["tar_smpl_vertice"]
+    assert v.shape == (6890, 3) and abs(v[:, 0]).max() < 0.95 and v[:, 1].min() > -1.25

@@ -1,0 +1,351 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the
+golden fixtures generated from the genuine reference.  Needs a B200.
+
+Tolerances: k-NN indices, squared distances, sampler outputs and
+cull masks are bit-exact; rgb/acc <= 1e-4 max-abs; depth <= 1e-4 * far; staged
+float features <= a few 1e-6 (different FMA/summation order only)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import GOLDEN_CASES, load_golden
+from oracle import transhuman_oracle as orc
+from tests.gpu_util import frame_to_device
+from transhuman_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+RGB_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def small():
+    fr = synth.make_frame(H=20, W=20, n_class=300, V=3, feat_hw=28, seed=21, alpha_bias_shift=-12.0)
+    tf = orc.to_torch_frame(fr)
+    tokens = orc.build_tokens(tf)
+    frame, rays = frame_to_device(fr, tokens, DEV)
+    return fr, tf, tokens, frame, rays
+
+
+def _knife_edge_rays(raw, S, eps=1e-3):
+    """Rays whose last-sample alpha_raw is within eps of 0: dist = 1e10 makes
+    alpha_S a step function of sign(raw) (nerf_net_utils.py:31-34), so these are
+    excluded-and-counted (hard parts)."""
+    return raw.reshape(-1, S, 4)[:, -1, 3].abs() < eps
+
+
+# ---------------------------------------------------------------- staged, exact
+def test_sample_points_bit_exact(small):
+    fr, tf, tokens, frame, rays = small
+    for S in (1, 7, 64):
+        pts, z = ops.sample_points(*rays, S)
+        wp, wz = orc.get_sampling_points(tf["ray_o"][None], tf["ray_d"][None], tf["near"][None], tf["far"][None], S)
+        assert torch.equal(z.cpu(), wz[0]) and torch.equal(pts.cpu(), wp[0])
+
+
+def test_cull_knn1_and_grid_exact(small):
+    fr, tf, tokens, frame, rays = small
+    pts, _ = ops.sample_points(*rays, 24)
+    flat = pts.view(-1, 3)
+    d2, idx, mask = ops.cull_knn1(flat, frame.verts)
+    wd2, widx, _ = orc.knn_points(flat.cpu()[None], tf["tar_smpl_vertice"][None], K=1)
+    assert torch.equal(d2.cpu(), wd2[0, :, 0])
+    assert torch.equal(idx.cpu(), widx[0, :, 0])
+    wmask = orc.cull_mask(flat.cpu()[None], tf["tar_smpl_vertice"][None])[0]
+    assert torch.equal(mask.cpu().bool(), wmask)
+    assert 0 < int(wmask.sum()) < wmask.numel()
+    gmask = ops.cull_grid(flat, frame.verts)
+    assert torch.equal(gmask, mask)
+
+
+def test_cull_grid_equals_brute_on_hard_points(small):
+    """Points on and around the 0.1 m shell of random vertices, far points and
+    points outside the vertex bounding box."""
+    fr, tf, tokens, frame, rays = small
+    g = torch.Generator().manual_seed(5)
+    v = tf["tar_smpl_vertice"]
+    sel = v[torch.randint(0, v.shape[0], (20000,), generator=g)]
+    d = torch.randn((20000, 3), generator=g)
+    d = d / d.norm(dim=1, keepdim=True)
+    r = torch.cat([torch.full((10000,), 0.1), 0.1 + (torch.rand(10000, generator=g) - 0.5) * 2e-6])
+    shell = sel + d * r[:, None]
+    far = (torch.rand((5000, 3), generator=g) - 0.5) * 8.0
+    pts = torch.cat([shell, far, v[:100]]).to(DEV)
+    _, _, bm = ops.cull_knn1(pts, frame.verts)
+    gm = ops.cull_grid(pts, frame.verts)
+    assert torch.equal(bm, gm)
+    wm = orc.cull_mask(pts.cpu()[None], v[None])[0]
+    assert torch.equal(bm.cpu().bool(), wm)
+
+
+def test_knn_dparf(small):
+    fr, tf, tokens, frame, rays = small
+    pts, _ = ops.sample_points(*rays, 16)
+    ps = orc.world2smpl(pts.cpu()[None], tf["Rh"][None], tf["Th"][None]).view(-1, 3)
+    idx, d2, rep = ops.knn_dparf(frame, ps.to(DEV))
+    wrep, widx, wdist, ww, wdef = orc.human_representation(ps, tokens[0], tokens[1], tf["holder"], return_knn=True)
+    wd2, _, _ = orc.knn_points(ps[None], tokens[0][None], K=7)
+    assert torch.equal(idx.cpu(), widx)          # bit-exact index selection
+    assert torch.equal(d2.cpu(), wd2[0])         # and squared distances
+    assert (rep.cpu() - wrep).abs().max().item() <= 5e-6
+
+
+@pytest.mark.parametrize("K", [1, 3, 7, 12])
+def test_knn_other_k(small, K):
+    fr, tf, tokens, frame, rays = small
+    old = frame.c.knn
+    try:
+        frame.c.knn = K
+        g = torch.Generator().manual_seed(K)
+        ps = (torch.rand((3000, 3), generator=g) - 0.5) * torch.tensor([1.8, 1.8, 0.4]) + torch.tensor([0, -0.3, 0])
+        idx, d2, rep = ops.knn_dparf(frame, ps.to(DEV))
+        wd2, widx, _ = orc.knn_points(ps[None], tokens[0][None], K=K)
+        assert torch.equal(idx.cpu(), widx[0]) and torch.equal(d2.cpu(), wd2[0])
+        wrep = orc.human_representation(ps, tokens[0], tokens[1], tf["holder"], K=K)
+        assert (rep.cpu() - wrep).abs().max().item() <= 5e-6
+    finally:
+        frame.c.knn = old
+
+
+def test_knn_ties_lower_index_wins():
+    """Duplicate tokens: equal distances must resolve to the lower index."""
+    fr = synth.make_frame(H=4, W=4, n_class=100, V=1, feat_hw=8, seed=3)
+    tf = orc.to_torch_frame(fr)
+    tok_xyz, tok_blend = orc.build_tokens(tf)
+    tok_xyz = tok_xyz.clone()
+    tok_xyz[50:] = tok_xyz[:50]                     # every token appears twice
+    frame, rays = frame_to_device(fr, (tok_xyz, tok_blend), DEV)
+    g = torch.Generator().manual_seed(1)
+    ps = (torch.rand((4096, 3), generator=g) - 0.5) * 2.0
+    idx, d2, _ = ops.knn_dparf(frame, ps.to(DEV))
+    wd2, widx, _ = orc.knn_points(ps[None], tok_xyz[None], K=7)
+    assert torch.equal(idx.cpu(), widx[0]) and torch.equal(d2.cpu(), wd2[0])
+    assert (idx[:, 0] < 50).all() and (idx[:, 1] == idx[:, 0] + 50).all()
+
+
+def test_world2smpl_view_embed_pixel_gather(small):
+    fr, tf, tokens, frame, rays = small
+    pts, _ = ops.sample_points(*rays, 8)
+    got = ops.world2smpl(pts, frame.Rh, frame.Th)
+    want = orc.world2smpl(pts.cpu()[None], tf["Rh"][None], tf["Th"][None])[0]
+    assert torch.equal(got.cpu(), want)             # Rh = I: exact
+    fr2 = synth.make_frame(H=8, W=8, n_class=100, V=3, feat_hw=8, seed=3, rotate_rh=True, with_feature_maps=False)
+    t2 = orc.to_torch_frame(fr2)
+    got = ops.world2smpl(pts, t2["Rh"].to(DEV), t2["Th"].to(DEV).view(3))
+    want = orc.world2smpl(pts.cpu()[None], t2["Rh"][None], t2["Th"][None])[0]
+    assert (got.cpu() - want).abs().max().item() <= 5e-7
+    vd = ops.view_embed(rays[1])
+    assert (vd.cpu() - orc.view_embed(tf["ray_d"][None])[0]).abs().max().item() <= 5e-7
+    flat = pts.view(-1, 3)
+    pix = ops.pixel_gather(frame, flat)
+    wpix = orc.get_pixel_aligned_feature(flat.cpu()[None], tf["input_R"], tf["input_T"], tf["input_K"],
+                                         tf["pixel_feat_map"], tf["pixel_feat_map"].shape[-2:])
+    assert (pix.cpu() - wpix).abs().max().item() <= 2e-5
+
+
+def test_pixel_gather_out_of_image_border(small):
+    """Points projecting outside the input views: border padding clamps."""
+    fr, tf, tokens, frame, rays = small
+    g = torch.Generator().manual_seed(2)
+    pts = (torch.rand((4000, 3), generator=g) - 0.5) * 6.0
+    pts[:, 2] *= 0.2
+    pix = ops.pixel_gather(frame, pts.to(DEV))
+    wpix = orc.get_pixel_aligned_feature(pts[None], tf["input_R"], tf["input_T"], tf["input_K"],
+                                         tf["pixel_feat_map"], tf["pixel_feat_map"].shape[-2:])
+    assert (pix.cpu() - wpix).abs().max().item() <= 2e-5
+
+
+def test_integrate(small):
+    g = torch.Generator().manual_seed(3)
+    raw = torch.randn((500, 32, 4), generator=g) * 3
+    raw[:, :, 3] *= 10
+    z = torch.sort(torch.rand((500, 32), generator=g) * 2 + 1.0, dim=1)[0]
+    d = torch.randn((500, 3), generator=g)
+    for white in (False, True):
+        rgb, acc, depth = ops.integrate(raw.to(DEV), z.to(DEV), d.to(DEV), white_bkgd=white)
+        wrgb, wacc, _, wdepth = orc.raw2outputs(raw, z, d, white_bkgd=white)
+        assert (rgb.cpu() - wrgb).abs().max().item() <= 2e-6
+        assert (acc.cpu() - wacc).abs().max().item() <= 2e-6
+        assert (depth.cpu() - wdepth).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("simt", [True, False])
+def test_mlp_raw_stage(small, simt):
+    """a9 + a10 from the reference-layout inputs, dense and masked/progressive."""
+    fr, tf, tokens, frame, rays = small
+    frame.set_flag(ops.TH_FLAG_SIMT_MLP, simt)
+    try:
+        pts, _ = ops.sample_points(*rays, 8)
+        flat = pts.view(-1, 3)[:2000].cpu()
+        ps = orc.world2smpl(flat[None], tf["Rh"][None], tf["Th"][None])[0]
+        rep = orc.human_representation(ps, tokens[0], tokens[1], tf["holder"])
+        pix = orc.get_pixel_aligned_feature(flat[None], tf["input_R"], tf["input_T"], tf["input_K"],
+                                            tf["pixel_feat_map"], tf["pixel_feat_map"].shape[-2:])
+        vd = orc.view_embed(tf["ray_d"][None])[:, :, None].repeat(1, 1, 8, 1).view(1, -1, 27)[:, :2000]
+        want = orc.mlp_forward(tf["weights"], rep, pix, vd, progressive=False)[0]
+        got = ops.mlp_raw(frame, rep.to(DEV), pix.to(DEV), vd[0].to(DEV))
+        scale = want.abs().max().item()
+        assert (got.cpu() - want).abs().max().item() <= 2e-5 * max(scale, 1.0)
+        mask = torch.zeros(2000, dtype=torch.bool)
+        mask[::3] = True
+        wantm = orc.network_forward(tf["weights"], pix, vd, ps[None], tokens[0], tokens[1], tf["holder"],
+                                    pts_mask=mask[None])[0]
+        gotm = ops.mlp_raw(frame, rep.to(DEV), pix.to(DEV), vd[0].to(DEV), pts_mask=mask.to(DEV))
+        assert (gotm.cpu() - wantm).abs().max().item() <= 2e-5 * max(scale, 1.0)
+        assert torch.all(gotm.cpu()[~mask] == 0)
+    finally:
+        frame.set_flag(ops.TH_FLAG_SIMT_MLP, False)
+
+
+# ---------------------------------------------------------------- fused path
+def _compare_maps(got, want, far, name, exclude=None):
+    keep = slice(None) if exclude is None else ~exclude
+    e_rgb = (got["rgb_map"].cpu() - want["rgb_map"][0])[keep].abs().max().item()
+    e_acc = (got["acc_map"].cpu() - want["acc_map"][0])[keep].abs().max().item()
+    e_dep = (got["depth_map"].cpu() - want["depth_map"][0])[keep].abs().max().item()
+    assert e_rgb <= RGB_TOL, f"{name}: rgb {e_rgb}"
+    assert e_acc <= RGB_TOL, f"{name}: acc {e_acc}"
+    assert e_dep <= RGB_TOL * far, f"{name}: depth {e_dep}"
+
+
+@pytest.mark.parametrize("simt", [True, False])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_render_matches_reference_golden(name, simt):
+    """End to end against outputs of the reference's own Renderer.render /
+    render_fast (fixtures from oracle/make_golden.py)."""
+    kw, S, mode, g = load_golden(name)
+    fr = synth.make_frame(**kw)
+    tf = orc.to_torch_frame(fr)
+    tokens = orc.build_tokens(tf)
+    frame, rays = frame_to_device(fr, tokens, DEV, simt_mlp=simt)
+    m = ops.TH_RENDER_DENSE if mode == "dense" else ops.TH_RENDER_FAST
+    got = ops.render_rays(frame, *rays, S, mode=m, want_raw=True, want_mask=True)
+    want = {k: torch.from_numpy(g[k])[None] for k in ("rgb_map", "acc_map", "depth_map")}
+    # exclude-and-count rays sitting on the last-sample step function
+    ex = _knife_edge_rays(got["raw"].cpu(), S)
+    assert ex.float().mean().item() < 0.02
+    _compare_maps(got, want, float(fr["far"].max()), name, exclude=ex)
+    if mode != "dense":
+        mask = np.unpackbits(g["cull_mask"])[: got["pts_mask"].numel()].astype(bool)
+        assert np.array_equal(got["pts_mask"].cpu().numpy().reshape(-1).astype(bool), mask)   # exact cull
+        assert got["counters"][0] == int(g["n_cull"])
+        assert got["counters"][1] == int(g["n_rays_surviving"])
+        if got["counters"][1] <= 2400:  # reference quirk: all samples of surviving rays evaluated
+            assert got["counters"][2] == got["counters"][1] * S
+
+
+@pytest.mark.parametrize("mode", ["dense", "masked", "fast"])
+def test_render_matches_oracle(small, mode):
+    fr, tf, tokens, frame, rays = small
+    S = 24
+    if mode == "dense":
+        want = orc.render(tf, S, tokens=tokens)
+        got = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_DENSE, want_raw=True)
+    elif mode == "masked":
+        want = orc.render_fast(tf, S, tokens=tokens, train_branch_max_rays=0)
+        got = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_MASKED, want_raw=True, want_mask=True)
+    else:
+        want = orc.render_fast(tf, S, tokens=tokens)
+        got = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_FAST, want_raw=True, want_mask=True)
+    ex = _knife_edge_rays(want["raw"], S)
+    _compare_maps(got, want, float(fr["far"].max()), mode, exclude=ex)
+    raw_err = (got["raw"].cpu() - want["raw"]).abs().max().item()
+    assert raw_err <= 2e-5 * max(1.0, want["raw"].abs().max().item())
+    if mode != "dense":
+        assert torch.equal(got["pts_mask"].cpu().bool(), want["valid_pts_mask"][0])
+        assert (got["acc_map"] > 0).sum() > 0
+    if mode == "masked":
+        # culled rays are exactly zero; masked points have raw == 0 exactly
+        dead = ~want["valid_pts_mask"][0].any(dim=1)
+        assert torch.all(got["rgb_map"].cpu()[dead] == 0) and torch.all(got["acc_map"].cpu()[dead] == 0)
+        assert torch.all(got["raw"].cpu()[~want["valid_pts_mask"][0]] == 0)
+
+
+def test_rotated_rh_indices_explained(small):
+    """With a rotated Rh the SMPL-space points come from a 3x3 product whose
+    rounding is backend-defined; index mismatches against the oracle must be
+    near-ties (limits of bit-exactness)."""
+    fr = synth.make_frame(H=16, W=16, n_class=300, V=3, feat_hw=16, seed=9, rotate_rh=True, posed=True)
+    tf = orc.to_torch_frame(fr)
+    tokens = orc.build_tokens(tf)
+    frame, rays = frame_to_device(fr, tokens, DEV)
+    pts, _ = ops.sample_points(*rays, 16)
+    ps_gpu = ops.world2smpl(pts, frame.Rh, frame.Th).view(-1, 3)
+    ps_cpu = orc.world2smpl(pts.cpu()[None], tf["Rh"][None], tf["Th"][None]).view(-1, 3)
+    idx, d2, _ = ops.knn_dparf(frame, ps_gpu)
+    wd2, widx, _ = orc.knn_points(ps_cpu[None], tokens[0][None], K=8)
+    bad = (idx.cpu() != widx[0, :, :7]).any(dim=1)
+    if bad.any():
+        gap = (wd2[0, bad, 1:] - wd2[0, bad, :-1]).min(dim=1)[0] / wd2[0, bad, :].max(dim=1)[0]
+        assert (gap < 1e-5).all(), "index mismatch without a near-tie"
+    assert bad.float().mean().item() < 1e-3
+
+
+def test_white_background(small):
+    fr, tf, tokens, frame, rays = small
+    frame.set_flag(ops.TH_FLAG_WHITE_BKGD, True)
+    try:
+        got = ops.render_rays(frame, *rays, 12, mode=ops.TH_RENDER_DENSE)
+        want = orc.render(tf, 12, tokens=tokens, white_bkgd=True)
+        ex = _knife_edge_rays(want["raw"], 12)
+        _compare_maps(got, want, float(fr["far"].max()), "white", exclude=ex)
+    finally:
+        frame.set_flag(ops.TH_FLAG_WHITE_BKGD, False)
+
+
+def test_query_density(small):
+    fr, tf, tokens, frame, rays = small
+    grid = synth.make_grid_points(fr, 24).reshape(-1, 3)
+    alpha, mask = ops.query_density(frame, torch.from_numpy(grid).to(DEV))
+    walpha, wmask = orc.query_density(tf, torch.from_numpy(grid), tokens=tokens)
+    assert torch.equal(mask.cpu().bool(), wmask)
+    assert 0 < int(wmask.sum()) < wmask.numel()
+    assert (alpha.cpu() - walpha).abs().max().item() <= 2e-5 * max(1.0, walpha.abs().max().item())
+    assert torch.all(alpha.cpu()[~wmask] == 0)
+
+
+# ---------------------------------------------------------------- edge cases
+def test_empty_and_ragged_inputs(small):
+    fr, tf, tokens, frame, rays = small
+    empty = tuple(r[:0] for r in rays)
+    out = ops.render_rays(frame, *empty, 16, mode=ops.TH_RENDER_FAST)
+    assert out["rgb_map"].shape == (0, 3) and out["counters"] == (0, 0, 0)
+    # ragged: N*S not a multiple of any tile size; chunk-independent results
+    S = 13
+    full = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_DENSE)
+    part = ops.render_rays(frame, *(r[37:166] for r in rays), S, mode=ops.TH_RENDER_DENSE)
+    assert torch.equal(full["rgb_map"][37:166], part["rgb_map"])
+    assert torch.equal(full["depth_map"][37:166], part["depth_map"])
+
+
+def test_all_rays_culled(small):
+    fr, tf, tokens, frame, rays = small
+    o, d, n, f = rays
+    out = ops.render_rays(frame, o + 50.0, d, n, f, 16, mode=ops.TH_RENDER_FAST)
+    assert out["counters"] == (0, 0, 0)
+    assert torch.all(out["rgb_map"] == 0) and torch.all(out["acc_map"] == 0) and torch.all(out["depth_map"] == 0)
+
+
+def test_one_shot_single_view():
+    """V = 1 (scripts/test.sh one-shot setting): the cross-attention softmax is
+    an identity over one element."""
+    fr = synth.make_frame(H=12, W=12, n_class=300, V=1, feat_hw=16, seed=4, alpha_bias_shift=-10.0)
+    tf = orc.to_torch_frame(fr)
+    tokens = orc.build_tokens(tf)
+    frame, rays = frame_to_device(fr, tokens, DEV)
+    got = ops.render_rays(frame, *rays, 16, mode=ops.TH_RENDER_DENSE)
+    want = orc.render(tf, 16, tokens=tokens)
+    _compare_maps(got, want, float(fr["far"].max()), "V=1", exclude=_knife_edge_rays(want["raw"], 16))
+
+
+def test_bad_arguments_report_errors(small):
+    from transhuman_b200._lib import TransHumanLibraryError
+    fr, tf, tokens, frame, rays = small
+    old = frame.c.knn
+    frame.c.knn = 99
+    with pytest.raises(TransHumanLibraryError, match="knn"):
+        ops.render_rays(frame, *rays, 8)
+    frame.c.knn = old
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.render_rays(frame, *(r.cpu() for r in rays), 8)

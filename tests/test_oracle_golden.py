@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, load_golden
+from tests.conftest import GOLDEN_CASES, load_golden
 from oracle import transhuman_oracle as orc
 from transhuman_b200 import synth
 

@@ -1,0 +1,592 @@
+// C-ABI entry points (include/transhuman_b200.h): argument checking, host-side
+// weight packing, workspace planning and the kernel schedule of the fused path.
+#include <cuda_fp16.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace th {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int64_t& launch_counter() { return g_launches; }
+
+constexpr int64_t CHUNK_PTS = 128 * 1024;  // points per MLP chunk (workspace ~ 26 KiB / point)
+
+// ---------------------------------------------------------------------------
+// weight packing (host)
+// ---------------------------------------------------------------------------
+struct MatSpec {
+  uint64_t PackedHeader::*w;
+  uint64_t PackedHeader::*b;
+  uint64_t PackedHeader::*h;  // fp16 hi/lo planes (nullptr for the heads)
+  int N, K;
+};
+
+static std::vector<MatSpec> mat_specs(int V) {
+  typedef PackedHeader H;
+  return {
+      {&H::fc0_w, &H::fc0_b, &H::h_fc0, 256, 256},
+      {&H::ar0_w, &H::ar0_b, &H::h_ar0, 256, 384},
+      {&H::k0_w, &H::k0_b, &H::h_k0, 128, 256},
+      {&H::k1_w, &H::k1_b, &H::h_k1, 128, 256},
+      {&H::v_w, &H::v_b, &H::h_v, 256, 512},
+      {&H::fc1_w, &H::fc1_b, &H::h_fc1, 256, 256},
+      {&H::fc2_w, &H::fc2_b, &H::h_fc2, 256, 256},
+      {&H::fc3m_w, &H::fc3m_b, &H::h_fc3m, 256, 256 * V},
+      {&H::afc_w, &H::afc_b, nullptr, 1, 256},
+      {&H::f_w, &H::f_b, &H::h_f, 256, 640},
+      {&H::view_w, &H::view_b, &H::h_view, 128, 288},
+      {&H::t_w, &H::t_b, &H::h_t, 128, 128 * V + 384},
+      {&H::rgb_w, &H::rgb_b, nullptr, 3, 128},
+  };
+}
+
+static void layout_header(int V, PackedHeader* h) {
+  memset(h, 0, sizeof(*h));
+  h->magic = PACK_MAGIC;
+  h->n_views = V;
+  uint64_t off = align_up(sizeof(PackedHeader), 256);
+  for (const MatSpec& m : mat_specs(V)) {
+    h->*(m.w) = off;
+    off += align_up((size_t)m.N * m.K * 4, 256);
+    h->*(m.b) = off;
+    off += align_up((size_t)m.N * 4, 256);
+  }
+  for (const MatSpec& m : mat_specs(V)) {
+    if (!m.h) continue;
+    h->*(m.h) = off;
+    off += align_up((size_t)m.N * m.K * 2 * 2, 1024);
+  }
+  h->total_bytes = off;
+}
+
+// zero the raw rows of masked-out points (Network.forward scatter into zeros,
+// cross_transformer.py:229-233, 267-269)
+__global__ void k_apply_mask(float4* raw, const uint8_t* __restrict__ mask, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && !mask[i]) raw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+int launch_apply_mask(float* raw, const uint8_t* mask, int64_t n, cudaStream_t st) {
+  k_apply_mask<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(reinterpret_cast<float4*>(raw), mask, n);
+  TH_LAUNCHED();
+  return TH_OK;
+}
+
+}  // namespace th
+
+using namespace th;
+
+extern "C" {
+
+const char* th_version(void) { return "transhuman_b200 0.1 (sm_100a)"; }
+const char* th_last_error(void) { return g_err; }
+int64_t th_launch_count(int32_t reset) {
+  int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+size_t th_packed_weights_bytes(int32_t n_views) {
+  if (n_views < 1 || n_views > TH_MAX_VIEWS) return 0;
+  PackedHeader h;
+  layout_header(n_views, &h);
+  return (size_t)h.total_bytes;
+}
+
+int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t bytes) {
+  TH_CHECK_ARG(w && packed_host, "null pointer");
+  TH_CHECK_ARG(V >= 1 && V <= TH_MAX_VIEWS, "n_views out of range");
+  const float* const* fields = reinterpret_cast<const float* const*>(w);
+  for (size_t i = 0; i < sizeof(ThWeightsF32) / sizeof(float*); ++i) TH_CHECK_ARG(fields[i], "null weight pointer");
+  PackedHeader h;
+  layout_header(V, &h);
+  if (bytes < h.total_bytes) {
+    set_error("th_pack_weights: need %llu bytes, got %zu", (unsigned long long)h.total_bytes, bytes);
+    return TH_EWORKSPACE;
+  }
+  unsigned char* blob = static_cast<unsigned char*>(packed_host);
+  memset(blob, 0, h.total_bytes);
+  memcpy(blob, &h, sizeof(h));
+  auto W = [&](uint64_t off) { return reinterpret_cast<float*>(blob + off); };
+  auto copy_cols = [](float* dst, int ldd, int col0, const float* src, int N, int K, double scale) {
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) dst[(size_t)n * ldd + col0 + k] = (float)((double)src[(size_t)n * K + k] * scale);
+  };
+  // plain layers
+  copy_cols(W(h.fc0_w), 256, 0, w->fc_0_w, 256, 255, 1.0);
+  memcpy(W(h.fc0_b), w->fc_0_b, 256 * 4);
+  copy_cols(W(h.ar0_w), 384, 0, w->alpha_res_0_w, 256, 384, 1.0);
+  memcpy(W(h.ar0_b), w->alpha_res_0_b, 256 * 4);
+  copy_cols(W(h.k0_w), 256, 0, w->skv0_key_w, 128, 256, 1.0);
+  memcpy(W(h.k0_b), w->skv0_key_b, 128 * 4);
+  copy_cols(W(h.k1_w), 256, 0, w->skv1_key_w, 128, 256, 1.0);
+  memcpy(W(h.k1_b), w->skv1_key_b, 128 * 4);
+  // W_v = [value_embed_1 | value_embed_0] ; b = b1 + b0
+  copy_cols(W(h.v_w), 512, 0, w->skv1_value_w, 256, 256, 1.0);
+  copy_cols(W(h.v_w), 512, 256, w->skv0_value_w, 256, 256, 1.0);
+  for (int n = 0; n < 256; ++n) W(h.v_b)[n] = (float)((double)w->skv1_value_b[n] + (double)w->skv0_value_b[n]);
+  copy_cols(W(h.fc1_w), 256, 0, w->fc_1_w, 256, 256, 1.0);
+  memcpy(W(h.fc1_b), w->fc_1_b, 256 * 4);
+  copy_cols(W(h.fc2_w), 256, 0, w->fc_2_w, 256, 256, 1.0);
+  memcpy(W(h.fc2_b), w->fc_2_b, 256 * 4);
+  // mean over views folded into K
+  for (int v = 0; v < V; ++v) copy_cols(W(h.fc3m_w), 256 * V, 256 * v, w->fc_3_w, 256, 256, 1.0 / V);
+  memcpy(W(h.fc3m_b), w->fc_3_b, 256 * 4);
+  memcpy(W(h.afc_w), w->alpha_fc_w, 256 * 4);
+  W(h.afc_b)[0] = w->alpha_fc_b[0];
+  // W_f = [feature_fc | rgb_res_0]
+  copy_cols(W(h.f_w), 640, 0, w->feature_fc_w, 256, 256, 1.0);
+  copy_cols(W(h.f_w), 640, 256, w->rgb_res_0_w, 256, 384, 1.0);
+  for (int n = 0; n < 256; ++n) W(h.f_b)[n] = (float)((double)w->feature_fc_b[n] + (double)w->rgb_res_0_b[n]);
+  // W_view: 283 -> 288 columns (view direction padded to 32)
+  copy_cols(W(h.view_w), 288, 0, w->view_fc_w, 128, 283, 1.0);
+  memcpy(W(h.view_b), w->view_fc_b, 128 * 4);
+  // W_t = [fc_4/V x V | fc_4 @ rgb_res_1] ; b_t = fc_4 @ b_r1 + b_4
+  {
+    const int ld = 128 * V + 384;
+    for (int v = 0; v < V; ++v) copy_cols(W(h.t_w), ld, 128 * v, w->fc_4_w, 128, 128, 1.0 / V);
+    for (int n = 0; n < 128; ++n) {
+      for (int k = 0; k < 384; ++k) {
+        double s = 0.0;
+        for (int j = 0; j < 128; ++j) s += (double)w->fc_4_w[n * 128 + j] * (double)w->rgb_res_1_w[j * 384 + k];
+        W(h.t_w)[(size_t)n * ld + 128 * V + k] = (float)s;
+      }
+      double s = w->fc_4_b[n];
+      for (int j = 0; j < 128; ++j) s += (double)w->fc_4_w[n * 128 + j] * (double)w->rgb_res_1_b[j];
+      W(h.t_b)[n] = (float)s;
+    }
+  }
+  memcpy(W(h.rgb_w), w->rgb_fc_w, 3 * 128 * 4);
+  memcpy(W(h.rgb_b), w->rgb_fc_b, 3 * 4);
+  // fp16 hi/lo planes of the GEMM matrices: hi = fp16(w), lo = fp16(w - hi)
+  for (const MatSpec& m : mat_specs(V)) {
+    if (!m.h) continue;
+    const float* src = W(h.*(m.w));
+    __half* hi = reinterpret_cast<__half*>(blob + h.*(m.h));
+    __half* lo = hi + (size_t)m.N * m.K;
+    for (size_t i = 0; i < (size_t)m.N * m.K; ++i) {
+      __half a = __float2half_rn(src[i]);
+      hi[i] = a;
+      lo[i] = __float2half_rn(src[i] - __half2float(a));
+    }
+  }
+  return TH_OK;
+}
+
+// ---------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------
+struct Workspace {
+  unsigned char* grid;
+  unsigned long long* counters;  // 8 slots
+  uint8_t* ray_any;
+  uint8_t* mask;
+  int32_t* ids;
+  float* raw;
+  float* chunk;
+  int64_t chunk_pts;
+};
+
+static size_t ws_plan(int64_t n_points, int V, int n_verts, unsigned char* base, Workspace* ws) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  int64_t np = n_points > 0 ? n_points : 0;
+  unsigned char* grid = take(n_verts > 0 ? cull_grid_bytes(n_verts) : 0);
+  unsigned char* counters = take(64);
+  unsigned char* ray_any = take((size_t)np);
+  unsigned char* mask = take((size_t)np);
+  unsigned char* ids = take((size_t)np * 4);
+  unsigned char* raw = take((size_t)np * 16);
+  int64_t cp = np < CHUNK_PTS ? np : CHUNK_PTS;
+  unsigned char* chunk = take((size_t)cp * mlp_buffer_floats_per_point(V) * 4);
+  if (ws) {
+    ws->grid = grid;
+    ws->counters = reinterpret_cast<unsigned long long*>(counters);
+    ws->ray_any = ray_any;
+    ws->mask = mask;
+    ws->ids = reinterpret_cast<int32_t*>(ids);
+    ws->raw = reinterpret_cast<float*>(raw);
+    ws->chunk = reinterpret_cast<float*>(chunk);
+    ws->chunk_pts = cp;
+  }
+  return off;
+}
+
+size_t th_workspace_bytes(int64_t n_points, int32_t n_views, int32_t n_verts) {
+  if (n_views < 1) n_views = 1;
+  return ws_plan(n_points, n_views, n_verts, nullptr, nullptr);
+}
+
+static int frame_dev(const ThFrame* f, FrameDev* d, bool need_tokens, bool need_feat) {
+  TH_CHECK_ARG(f, "null frame");
+  TH_CHECK_ARG(f->n_views >= 1 && f->n_views <= TH_MAX_VIEWS, "n_views out of range");
+  if (need_tokens) {
+    TH_CHECK_ARG(f->tok_feat && f->tok_xyz && f->tok_rot, "null token pointer");
+    TH_CHECK_ARG(f->knn >= 1 && f->knn <= TH_MAX_KNN && f->knn <= f->n_tok, "knn out of range");
+    TH_CHECK_ARG(f->knn_dist_alpha > 0.f, "knn_dist_alpha must be positive");
+  }
+  if (need_feat) {
+    TH_CHECK_ARG(f->feat && f->cam_R && f->cam_T && f->cam_K, "null feature-map / camera pointer");
+    TH_CHECK_ARG(f->feat_h >= 1 && f->feat_w >= 1, "bad feature-map size");
+  }
+  d->tok_feat = f->tok_feat;
+  d->tok_xyz = f->tok_xyz;
+  d->tok_rot = f->tok_rot;
+  d->feat = f->feat;
+  d->cam_R = f->cam_R;
+  d->cam_T = f->cam_T;
+  d->cam_K = f->cam_K;
+  d->Rh = f->Rh;
+  d->Th = f->Th;
+  d->V = f->n_views;
+  d->n_tok = f->n_tok;
+  d->H = f->feat_h;
+  d->W = f->feat_w;
+  d->K = f->knn;
+  d->sx = f->uv_scale_x;
+  d->sy = f->uv_scale_y;
+  d->knn_alpha = f->knn_dist_alpha;
+  return TH_OK;
+}
+
+static int read_header(const ThFrame* f, PackedHeader* h, cudaStream_t st) {
+  TH_CHECK_ARG(f->weights, "null weights blob");
+  TH_CUDA(cudaMemcpyAsync(h, f->weights, sizeof(PackedHeader), cudaMemcpyDeviceToHost, st));
+  TH_CUDA(cudaStreamSynchronize(st));
+  if (h->magic != PACK_MAGIC || h->n_views != f->n_views) {
+    set_error("weights blob: bad magic or packed for %d views (frame has %d)", h->n_views, f->n_views);
+    return TH_EINVAL;
+  }
+  return TH_OK;
+}
+
+// host copy of the header, cached per blob pointer (the header never changes
+// for a given upload; avoids a device round trip per call)
+static int cached_header(const ThFrame* f, PackedHeader* h, cudaStream_t st) {
+  static thread_local const void* key = nullptr;
+  static thread_local PackedHeader cache;
+  if (key != f->weights || cache.n_views != f->n_views) {
+    int rc = read_header(f, &cache, st);
+    if (rc) {
+      key = nullptr;
+      return rc;
+    }
+    key = f->weights;
+  }
+  *h = cache;
+  return TH_OK;
+}
+
+// feature kernel + MLP over a list of points, in chunks
+static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& hdr, PointSource src,
+                      const int32_t* ids, int64_t n_list, const Workspace& ws, float* raw, float* alpha_out,
+                      int alpha_only, int zero_rgb, cudaStream_t st) {
+  const int V = fr.V;
+  for (int64_t first = 0; first < n_list; first += ws.chunk_pts) {
+    int64_t P = n_list - first < ws.chunk_pts ? n_list - first : ws.chunk_pts;
+    MlpBuffers b;
+    mlp_carve(ws.chunk, P, V, &b);
+    FeatOut fo{};
+    fo.rep = b.rep;
+    fo.rep_sv = P * REP_LD;
+    fo.rep_sp = REP_LD;
+    fo.rep_sc = 1;
+    fo.pix = b.pix;
+    fo.pix_sv = P * PIX_LD;
+    fo.pix_sp = PIX_LD;
+    fo.pix_sc = 1;
+    fo.pix_mean = alpha_only ? nullptr : b.pix_mean;
+    fo.vd = b.vd;
+    fo.do_rep = 1;
+    fo.do_pix = 1;
+    fo.do_vd = alpha_only ? 0 : 1;
+    fo.rep_pad = 1;
+    src.ids = ids;
+    src.first = first;
+    int rc = launch_features(fr, src, P, fo, st);
+    if (rc) return rc;
+    MlpRun run{};
+    run.weights = static_cast<const unsigned char*>(f->weights);
+    run.P = P;
+    run.V = V;
+    run.dst_ids = ids;
+    run.first = first;
+    run.raw = raw;
+    run.alpha_out = alpha_out;
+    run.alpha_only = alpha_only;
+    run.zero_rgb_if_transparent = zero_rgb;
+    run.use_tensor_cores = (f->flags & TH_FLAG_SIMT_MLP) ? 0 : 1;
+    rc = mlp_forward(run, b, hdr, st);
+    if (rc) return rc;
+  }
+  return TH_OK;
+}
+
+int th_render_rays(const ThFrame* f, const ThRays* r, ThOut* o, int32_t culled, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TH_CHECK_ARG(f && r && o, "null argument");
+  TH_CHECK_ARG(r->ray_o && r->ray_d && r->near_ && r->far_ && r->t_vals, "null ray pointer");
+  TH_CHECK_ARG(r->n_rays >= 0 && r->n_samples >= 1, "bad ray counts");
+  TH_CHECK_ARG(o->rgb_map && o->acc_map && o->depth_map, "null output pointer");
+  TH_CHECK_ARG(culled >= 0 && culled <= 2, "bad render mode");
+  const int64_t N = r->n_rays;
+  const int S = r->n_samples;
+  const int64_t NP = N * S;
+  TH_CHECK_ARG(NP < (1LL << 31), "more than 2^31 sample points in one call");
+  if (o->counters_host) o->counters_host[0] = o->counters_host[1] = o->counters_host[2] = 0;
+  if (N == 0) return TH_OK;
+  FrameDev fr;
+  int rc = frame_dev(f, &fr, true, true);
+  if (rc) return rc;
+  TH_CHECK_ARG(f->Rh && f->Th, "null Rh/Th");
+  if (culled) TH_CHECK_ARG(f->verts && f->n_verts > 0, "culled mode needs the cull vertices");
+  Workspace ws;
+  size_t need = ws_plan(NP, fr.V, culled ? f->n_verts : 0, static_cast<unsigned char*>(workspace), &ws);
+  if (!workspace || workspace_bytes < need) {
+    set_error("th_render_rays: workspace %zu < %zu bytes", workspace_bytes, need);
+    return TH_EWORKSPACE;
+  }
+  PackedHeader hdr;
+  if ((rc = cached_header(f, &hdr, st))) return rc;
+
+  PointSource src{};
+  src.ray_o = r->ray_o;
+  src.ray_d = r->ray_d;
+  src.near_ = r->near_;
+  src.far_ = r->far_;
+  src.t_vals = r->t_vals;
+  src.n_samples = S;
+  float* raw = o->raw ? o->raw : ws.raw;
+  const uint8_t* mask = nullptr;
+  const int white = (f->flags & TH_FLAG_WHITE_BKGD) ? 1 : 0;
+
+  if (!culled) {
+    if ((rc = run_points(f, fr, hdr, src, nullptr, NP, ws, raw, nullptr, 0, 0, st))) return rc;
+    if (o->counters_host) {
+      o->counters_host[0] = NP;
+      o->counters_host[1] = N;
+      o->counters_host[2] = NP;
+    }
+  } else {
+    uint8_t* m = o->pts_mask ? o->pts_mask : ws.mask;
+    TH_CUDA(cudaMemsetAsync(ws.counters, 0, 64, st));
+    TH_CUDA(cudaMemsetAsync(ws.ray_any, 0, (size_t)N, st));
+    if ((rc = launch_grid_build(f->verts, f->n_verts, f->cull_radius, ws.grid, st))) return rc;
+    if ((rc = launch_cull_grid(src, NP, ws.grid, f->cull_radius, m, ws.ids, ws.ray_any, ws.counters, st))) return rc;
+    if ((rc = launch_count_nonzero(ws.ray_any, N, ws.counters + 1, st))) return rc;
+    unsigned long long cnt[3] = {0, 0, 0};
+    TH_CUDA(cudaMemcpyAsync(cnt, ws.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    TH_CUDA(cudaStreamSynchronize(st));
+    int64_t n_eval = (int64_t)cnt[0];
+    int zero_rgb = 1;
+    const uint8_t* integ_mask = m;
+    if (culled == TH_RENDER_FAST && (int64_t)cnt[1] <= TH_TRAIN_BRANCH_MAX_RAYS && cnt[1] > 0) {
+      // reference quirk: <= 2400 surviving rays -> un-chunked branch without pts_mask
+      if ((rc = launch_expand_rays(ws.ray_any, NP, S, ws.mask, ws.ids, ws.counters + 2, st))) return rc;
+      TH_CUDA(cudaMemcpyAsync(cnt + 2, ws.counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      TH_CUDA(cudaStreamSynchronize(st));
+      n_eval = (int64_t)cnt[2];
+      zero_rgb = 0;
+      integ_mask = ws.mask;
+    }
+    if (o->counters_host) {
+      o->counters_host[0] = (int64_t)cnt[0];
+      o->counters_host[1] = (int64_t)cnt[1];
+      o->counters_host[2] = n_eval;
+    }
+    if (o->raw) TH_CUDA(cudaMemsetAsync(o->raw, 0, (size_t)NP * 16, st));
+    if ((rc = run_points(f, fr, hdr, src, ws.ids, n_eval, ws, raw, nullptr, 0, zero_rgb, st))) return rc;
+    mask = integ_mask;
+  }
+  return launch_integrate(raw, mask, src, nullptr, r->ray_d, N, S, white, o->rgb_map, o->acc_map, o->depth_map, st);
+}
+
+int th_query_density(const ThFrame* f, const float* pts, int64_t n_points, float* alpha_raw, uint8_t* mask_out,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TH_CHECK_ARG(f && pts && alpha_raw, "null argument");
+  TH_CHECK_ARG(n_points >= 0 && n_points < (1LL << 31), "bad point count");
+  if (n_points == 0) return TH_OK;
+  FrameDev fr;
+  int rc = frame_dev(f, &fr, true, true);
+  if (rc) return rc;
+  TH_CHECK_ARG(f->Rh && f->Th && f->verts && f->n_verts > 0, "null Rh/Th/verts");
+  Workspace ws;
+  size_t need = ws_plan(n_points, fr.V, f->n_verts, static_cast<unsigned char*>(workspace), &ws);
+  if (!workspace || workspace_bytes < need) {
+    set_error("th_query_density: workspace %zu < %zu bytes", workspace_bytes, need);
+    return TH_EWORKSPACE;
+  }
+  PackedHeader hdr;
+  if ((rc = cached_header(f, &hdr, st))) return rc;
+  PointSource src{};
+  src.pts = pts;
+  src.n_samples = 1;
+  uint8_t* m = mask_out ? mask_out : ws.mask;
+  TH_CUDA(cudaMemsetAsync(ws.counters, 0, 64, st));
+  TH_CUDA(cudaMemsetAsync(alpha_raw, 0, (size_t)n_points * 4, st));
+  if ((rc = launch_grid_build(f->verts, f->n_verts, f->cull_radius, ws.grid, st))) return rc;
+  if ((rc = launch_cull_grid(src, n_points, ws.grid, f->cull_radius, m, ws.ids, nullptr, ws.counters, st))) return rc;
+  unsigned long long cnt = 0;
+  TH_CUDA(cudaMemcpyAsync(&cnt, ws.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  TH_CUDA(cudaStreamSynchronize(st));
+  return run_points(f, fr, hdr, src, ws.ids, (int64_t)cnt, ws, nullptr, alpha_raw, 1, 0, st);
+}
+
+// ---------------------------------------------------------------------------
+// staged entry points
+// ---------------------------------------------------------------------------
+int th_sample_points(const ThRays* r, float* pts, float* z_vals, void* stream) {
+  TH_CHECK_ARG(r && r->ray_o && r->ray_d && r->near_ && r->far_ && r->t_vals, "null ray pointer");
+  TH_CHECK_ARG(r->n_rays >= 0 && r->n_samples >= 1, "bad ray counts");
+  PointSource src{};
+  src.ray_o = r->ray_o;
+  src.ray_d = r->ray_d;
+  src.near_ = r->near_;
+  src.far_ = r->far_;
+  src.t_vals = r->t_vals;
+  src.n_samples = r->n_samples;
+  return launch_sample_points(src, r->n_rays * r->n_samples, pts, z_vals, static_cast<cudaStream_t>(stream));
+}
+
+int th_cull_knn1(const float* pts, int64_t n_points, const float* verts, int32_t n_verts, float radius, float* d2,
+                 int64_t* idx, uint8_t* mask, void* stream) {
+  TH_CHECK_ARG(pts && verts, "null pointer");
+  TH_CHECK_ARG(n_points >= 0 && n_verts >= 1, "bad counts");
+  PointSource src{};
+  src.pts = pts;
+  src.n_samples = 1;
+  return launch_cull_brute(src, n_points, verts, n_verts, radius, d2, idx, mask, static_cast<cudaStream_t>(stream));
+}
+
+int th_cull_grid(const float* pts, int64_t n_points, const float* verts, int32_t n_verts, float radius,
+                 uint8_t* mask, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TH_CHECK_ARG(pts && verts && mask, "null pointer");
+  TH_CHECK_ARG(n_points >= 0 && n_verts >= 1, "bad counts");
+  if (!workspace || workspace_bytes < cull_grid_bytes(n_verts)) {
+    set_error("th_cull_grid: workspace %zu < %zu bytes", workspace_bytes, cull_grid_bytes(n_verts));
+    return TH_EWORKSPACE;
+  }
+  PointSource src{};
+  src.pts = pts;
+  src.n_samples = 1;
+  int rc = launch_grid_build(verts, n_verts, radius, workspace, st);
+  if (rc) return rc;
+  return launch_cull_grid(src, n_points, workspace, radius, mask, nullptr, nullptr, nullptr, st);
+}
+
+int th_world2smpl(const float* pts, int64_t n_points, const float* Rh, const float* Th, float* out, void* stream) {
+  TH_CHECK_ARG(pts && Rh && Th && out, "null pointer");
+  return launch_world2smpl(pts, n_points, Rh, Th, out, static_cast<cudaStream_t>(stream));
+}
+
+int th_view_embed(const float* ray_d, int64_t n_rays, float* out, void* stream) {
+  TH_CHECK_ARG(ray_d && out, "null pointer");
+  return launch_view_embed(ray_d, n_rays, out, static_cast<cudaStream_t>(stream));
+}
+
+int th_pixel_gather(const ThFrame* f, const float* pts, int64_t n_points, float* pixel_feat, void* stream) {
+  TH_CHECK_ARG(pts && pixel_feat, "null pointer");
+  FrameDev fr;
+  int rc = frame_dev(f, &fr, false, true);
+  if (rc) return rc;
+  fr.n_tok = 0;
+  PointSource src{};
+  src.pts = pts;
+  src.n_samples = 1;
+  FeatOut fo{};
+  fo.pix = pixel_feat;
+  fo.pix_sv = (int64_t)TH_C_PIX * n_points;
+  fo.pix_sp = 1;
+  fo.pix_sc = n_points;
+  fo.do_pix = 1;
+  return launch_features(fr, src, n_points, fo, static_cast<cudaStream_t>(stream));
+}
+
+int th_knn_dparf(const ThFrame* f, const float* pts_smpl, int64_t n_points, int64_t* knn_idx, float* knn_d2,
+                 float* human_rep, void* stream) {
+  TH_CHECK_ARG(pts_smpl, "null pointer");
+  FrameDev fr;
+  int rc = frame_dev(f, &fr, true, false);
+  if (rc) return rc;
+  PointSource src{};
+  src.pts = pts_smpl;
+  src.n_samples = 1;
+  FeatOut fo{};
+  fo.rep = human_rep;
+  fo.rep_sv = (int64_t)TH_C_REP * n_points;
+  fo.rep_sp = 1;
+  fo.rep_sc = n_points;
+  fo.knn_idx = knn_idx;
+  fo.knn_d2 = knn_d2;
+  fo.do_rep = 1;
+  fo.pts_are_smpl = 1;
+  return launch_features(fr, src, n_points, fo, static_cast<cudaStream_t>(stream));
+}
+
+int th_mlp_raw(const ThFrame* f, const float* human_rep, const float* pixel_feat, const float* viewdir,
+               const uint8_t* pts_mask, int64_t n_points, float* raw, void* workspace, size_t workspace_bytes,
+               void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TH_CHECK_ARG(f && human_rep && pixel_feat && viewdir && raw, "null pointer");
+  TH_CHECK_ARG(f->n_views >= 1 && f->n_views <= TH_MAX_VIEWS, "n_views out of range");
+  if (n_points <= 0) return TH_OK;
+  const int V = f->n_views;
+  size_t need = align_up((size_t)n_points * mlp_buffer_floats_per_point(V) * 4, 256);
+  if (!workspace || workspace_bytes < need) {
+    set_error("th_mlp_raw: workspace %zu < %zu bytes", workspace_bytes, need);
+    return TH_EWORKSPACE;
+  }
+  PackedHeader hdr;
+  int rc = cached_header(f, &hdr, st);
+  if (rc) return rc;
+  MlpBuffers b;
+  mlp_carve(static_cast<float*>(workspace), n_points, V, &b);
+  if ((rc = launch_pack_inputs(human_rep, pixel_feat, viewdir, n_points, V, b, st))) return rc;
+  MlpRun run{};
+  run.weights = static_cast<const unsigned char*>(f->weights);
+  run.P = n_points;
+  run.V = V;
+  run.raw = raw;
+  run.zero_rgb_if_transparent = pts_mask ? 1 : 0;
+  run.use_tensor_cores = (f->flags & TH_FLAG_SIMT_MLP) ? 0 : 1;
+  if ((rc = mlp_forward(run, b, hdr, st))) return rc;
+  if (pts_mask) {
+    if ((rc = launch_apply_mask(raw, pts_mask, n_points, st))) return rc;
+  }
+  return TH_OK;
+}
+
+int th_integrate(const float* raw, const float* z_vals, const float* ray_d, int64_t n_rays, int32_t n_samples,
+                 int32_t white_bkgd, float* rgb_map, float* acc_map, float* depth_map, void* stream) {
+  TH_CHECK_ARG(raw && z_vals && ray_d && rgb_map && acc_map && depth_map, "null pointer");
+  TH_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "bad counts");
+  PointSource src{};
+  return launch_integrate(raw, nullptr, src, z_vals, ray_d, n_rays, n_samples, white_bkgd, rgb_map, acc_map,
+                          depth_map, static_cast<cudaStream_t>(stream));
+}
+
+int th_nchw_to_nhwc(const float* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w, void* stream) {
+  TH_CHECK_ARG(src && dst && n >= 1 && c >= 1 && h >= 1 && w >= 1, "bad argument");
+  return launch_nchw_to_nhwc(src, dst, n, c, h, w, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+

@@ -1,0 +1,154 @@
+// Internal declarations shared by geometry.cu, mlp_simt.cu, mlp_tc.cu and api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace th {
+
+// Frame parameters as the kernels see them (by value).
+struct FrameDev {
+  const float *tok_feat, *tok_xyz, *tok_rot, *feat, *cam_R, *cam_T, *cam_K, *Rh, *Th;
+  int V, n_tok, H, W, K;
+  float sx, sy, knn_alpha;
+};
+
+// Output description of k_features.  Element (v, p, c) of the DPaRF
+// representation goes to rep[v*rep_sv + p*rep_sp + c*rep_sc]; same for the
+// pixel-aligned features.  GEMM layout: sv = P*ld, sp = ld, sc = 1.  Reference
+// layout (V,C,P): sv = C*P, sp = 1, sc = P.
+struct FeatOut {
+  float* rep;
+  int64_t rep_sv, rep_sp, rep_sc;
+  float* pix;
+  int64_t pix_sv, pix_sp, pix_sc;
+  float* pix_mean;   // (P, 384) mean over views, GEMM layout only (or nullptr)
+  float* vd;         // (P, 32) view-direction embedding, zero padded (or nullptr)
+  int64_t* knn_idx;  // (P, K) or nullptr
+  float* knn_d2;     // (P, K) or nullptr
+  int do_rep, do_pix, do_vd;
+  int rep_pad;       // write channel 255 = 0 (GEMM layout)
+  int pts_are_smpl;  // explicit points are already in SMPL coordinates (staged a8)
+};
+
+// Uniform grid over the cull vertices (device memory, built per frame).
+struct CullGrid {
+  static constexpr int MAX_DIM = 64;
+  float ox, oy, oz, inv_h;
+  int nx, ny, nz, ncell;
+  int* cell_start;   // (ncell + 1)
+  int* cursor;       // (ncell) build scratch
+  float4* sorted;    // (n_verts) vertices grouped by cell
+};
+inline size_t cull_grid_bytes(int n_verts) {
+  size_t cells = (size_t)CullGrid::MAX_DIM * CullGrid::MAX_DIM * CullGrid::MAX_DIM;
+  return align_up(sizeof(CullGrid), 256) + align_up((cells + 1) * 4, 256) + align_up(cells * 4, 256) +
+         align_up((size_t)n_verts * 16, 256);
+}
+
+// ---- geometry.cu -------------------------------------------------------------
+int launch_sample_points(const PointSource& src, int64_t n_points, float* pts, float* z, cudaStream_t st);
+int launch_cull_brute(const PointSource& src, int64_t n_points, const float* verts, int n_verts, float radius,
+                      float* d2, int64_t* idx, uint8_t* mask, cudaStream_t st);
+int launch_grid_build(const float* verts, int n_verts, float radius, void* grid_mem, cudaStream_t st);
+int launch_cull_grid(const PointSource& src, int64_t n_points, const void* grid_mem, float radius, uint8_t* mask,
+                     int32_t* ids, uint8_t* ray_any, unsigned long long* counters, cudaStream_t st);
+int launch_count_nonzero(const uint8_t* flags, int64_t n, unsigned long long* out, cudaStream_t st);
+int launch_expand_rays(const uint8_t* ray_any, int64_t n_points, int S, uint8_t* mask, int32_t* ids,
+                       unsigned long long* counter, cudaStream_t st);
+int launch_world2smpl(const float* pts, int64_t n, const float* Rh, const float* Th, float* out, cudaStream_t st);
+int launch_view_embed(const float* ray_d, int64_t n_rays, float* out, cudaStream_t st);
+int launch_features(const FrameDev& fr, const PointSource& src, int64_t n_points, const FeatOut& out,
+                    cudaStream_t st);
+int launch_integrate(const float* raw, const uint8_t* mask, const PointSource& src, const float* z_vals,
+                     const float* ray_d, int64_t n_rays, int S, int white_bkgd, float* rgb, float* acc,
+                     float* depth, cudaStream_t st);
+int launch_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, cudaStream_t st);
+
+// ---- packed weights (api.cu writes, mlp_*.cu read) --------------------------------
+// Offsets (in floats) into the fp32 section of the blob.  Folded matrices are
+// built in float64 by th_pack_weights:
+//   W_v    = [value_embed_1 | value_embed_0]            b_v = b_v1 + b_v0
+//   W_fc3m = [fc_3/V | ... | fc_3/V]   (mean over views folded into K)
+//   W_f    = [feature_fc | rgb_res_0]                   b_f = b_ff + b_r0
+//   W_view = [view_fc[:, :256] | view_fc[:, 256:283] | 0(5)]
+//   W_t    = [fc_4/V | ... | fc_4/V | fc_4 @ rgb_res_1] b_t = fc_4 @ b_r1 + b_4
+struct PackedHeader {
+  uint32_t magic;      // 'THW1'
+  int32_t n_views;
+  uint64_t total_bytes;
+  // fp32 matrices, row-major (N, K) with K contiguous; offsets in bytes from blob start
+  uint64_t fc0_w, fc0_b;        // (256,256)  K = 255 + 1 zero
+  uint64_t ar0_w, ar0_b;        // (256,384)
+  uint64_t k0_w, k0_b;          // (128,256)
+  uint64_t k1_w, k1_b;          // (128,256)
+  uint64_t v_w, v_b;            // (256,512)
+  uint64_t fc1_w, fc1_b;        // (256,256)
+  uint64_t fc2_w, fc2_b;        // (256,256)
+  uint64_t fc3m_w, fc3m_b;      // (256,256*V)
+  uint64_t afc_w, afc_b;        // (256), (1)
+  uint64_t f_w, f_b;            // (256,640)
+  uint64_t view_w, view_b;      // (128,288)
+  uint64_t t_w, t_b;            // (128,128*V+384)
+  uint64_t rgb_w, rgb_b;        // (3,128), (3)
+  // fp16 hi/lo planes for the tensor-core path: per matrix, (N, K) fp16 hi then lo
+  uint64_t h_fc0, h_ar0, h_k0, h_k1, h_v, h_fc1, h_fc2, h_fc3m, h_f, h_view, h_t;
+};
+constexpr uint32_t PACK_MAGIC = 0x31574854u;
+
+// ---- per-point network on GEMM-layout activations (mlp_simt.cu / mlp_tc.cu) ----
+// Activation buffers of one chunk (all fp32, row-major, rows = view-major (v*P + p)).
+struct MlpBuffers {
+  float *rep;      // (V*P, 256)
+  float *pix;      // (V*P, 384)
+  float *pix_mean; // (P, 384)
+  float *vd;       // (P, 32)
+  float *s, *x;    // (V*P, 256) each
+  float *kp, *ks;  // (V*P, 128) each
+  float *xt;       // (V*P, 256)
+  float *net;      // (V*P, 256)
+};
+size_t mlp_buffer_floats_per_point(int V);
+void mlp_carve(float* base, int64_t P, int V, MlpBuffers* b);
+
+// Runs fc_0 ... rgb_fc for P points whose inputs sit in `b`; writes raw rows
+// (rgb x3, alpha) to raw[dst_ids ? dst_ids[first + i] : first + i].  alpha_only
+// skips the colour branch (a12).  zero_rgb_if_transparent reproduces the
+// progressive variant's output (rgb = 0 where alpha_raw <= 0).
+struct MlpRun {
+  const unsigned char* weights;  // device blob
+  int64_t P;
+  int V;
+  const int32_t* dst_ids;
+  int64_t first;
+  float* raw;         // (.., 4) or nullptr
+  float* alpha_out;   // (..) or nullptr (density query)
+  int alpha_only;
+  int zero_rgb_if_transparent;
+  int use_tensor_cores;
+};
+int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& hdr_host, cudaStream_t st);
+
+// mlp_simt.cu: C[M,N] = act(sum_seg A_seg[M,K_seg] W[:, koff:koff+K_seg]^T + bias)
+struct GemmSeg {
+  const float* ptr;
+  int ld;       // row stride in floats
+  int K;        // multiple of 16
+  int64_t row_mod;  // rows wrap modulo this (0 = no wrap)
+};
+struct GemmArgs {
+  GemmSeg seg[TH_MAX_VIEWS + 1];
+  int nseg;
+  const float* W;  // (N, Ktot) row-major
+  int ldw;
+  const float* bias;
+  float* C;
+  int ldc;
+  int64_t M;
+  int N;  // multiple of 128
+  int relu;
+};
+int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
+int launch_gemm_tc(const GemmArgs& a, const void* w_hi_lo, cudaStream_t st);
+int launch_pack_inputs(const float* human_rep, const float* pixel_feat, const float* viewdir, int64_t P, int V,
+                       const MlpBuffers& b, cudaStream_t st);
+
+}  // namespace th

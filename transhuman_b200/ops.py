@@ -1,0 +1,312 @@
+"""Torch-tensor front end of the C ABI.
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every
+computation happens in ``libtranshuman_b200.so``.  All tensors must be CUDA,
+contiguous, fp32 unless stated.  No function here has a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Mapping
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (TH_FLAG_SIMT_MLP, TH_FLAG_WHITE_BKGD, TH_RENDER_DENSE, TH_RENDER_FAST, TH_RENDER_MASKED,
+                   ThFrame, ThOut, ThRays, ThWeightsF32)
+
+__all__ = ["PackedWeights", "Frame", "render_rays", "query_density", "sample_points", "cull_knn1", "cull_grid",
+           "world2smpl", "view_embed", "pixel_gather", "knn_dparf", "mlp_raw", "integrate", "nchw_to_nhwc",
+           "launch_count", "TH_RENDER_DENSE", "TH_RENDER_MASKED", "TH_RENDER_FAST"]
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (the query path has no CPU implementation)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+_workspaces: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces[key] = None
+        ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def release_workspaces():
+    _workspaces.clear()
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(_lib.load().th_launch_count(1 if reset else 0))
+
+
+class PackedWeights:
+    """The per-point network's 16 Conv1d layers packed for the kernels
+    (``th_pack_weights``).  ``state`` maps reference state_dict names
+    (``fc_0.weight`` ... ``rgb_fc.bias``, cross_transformer.py:97-126) to arrays
+    or tensors; extra keys (encoder, ViT, the dead ``xyzc_net``) are ignored."""
+
+    def __init__(self, state: Mapping, n_views: int, device="cuda"):
+        lib = _lib.load()
+        self.n_views = int(n_views)
+        keep = []
+        w = ThWeightsF32()
+        for cname, rname in _lib.WEIGHT_FIELDS:
+            for suf, key in (("w", rname + ".weight"), ("b", rname + ".bias")):
+                if key not in state:
+                    raise KeyError(f"state dict lacks {key}")
+                a = state[key]
+                if isinstance(a, torch.Tensor):
+                    a = a.detach().cpu().numpy()
+                a = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))
+                keep.append(a)
+                setattr(w, f"{cname}_{suf}", a.ctypes.data)
+        nbytes = lib.th_packed_weights_bytes(self.n_views)
+        if nbytes == 0:
+            raise ValueError(f"unsupported view count {n_views}")
+        host = np.zeros(nbytes, dtype=np.uint8)
+        _lib.check(lib.th_pack_weights(C.byref(w), self.n_views, host.ctypes.data, nbytes), "th_pack_weights")
+        self.host = host
+        self.blob = torch.from_numpy(host).to(device)
+
+
+class Frame:
+    """Per-frame state of the query path (``ThFrame``): what the torch prologue
+    (encoder, painting, grouping, ViT -- out of scope) hands to the kernels."""
+
+    def __init__(self, *, holder, tok_xyz, tok_rot, verts, feat_nhwc, cam_R, cam_T, cam_K, Rh, Th,
+                 weights: PackedWeights, uv_scale, knn: int = 7, knn_dist_alpha: float = 0.5,
+                 cull_radius: float = 0.1, white_bkgd: bool = False, simt_mlp: bool = False):
+        self.holder = _f32(holder, "holder")
+        V, n_tok, c = self.holder.shape
+        assert c == 192, "token width must be 192"
+        self.tok_xyz = _f32(tok_xyz, "tok_xyz").view(n_tok, 3)
+        self.tok_rot = _f32(tok_rot, "tok_rot").view(n_tok, 3, 3)
+        self.verts = _f32(verts, "verts").view(-1, 3)
+        self.feat = _f32(feat_nhwc, "feat_nhwc")
+        assert self.feat.dim() == 4 and self.feat.shape[0] == V and self.feat.shape[3] == 384, \
+            "feature maps must be (V,H,W,384) channel-last"
+        self.cam_R = _f32(cam_R, "cam_R").view(V, 3, 3)
+        self.cam_T = _f32(cam_T, "cam_T").view(V, 3)
+        self.cam_K = _f32(cam_K, "cam_K").view(V, 3, 3)
+        self.Rh = _f32(Rh, "Rh").view(3, 3)
+        self.Th = _f32(Th, "Th").view(3)
+        assert weights.n_views == V, "weights were packed for a different view count"
+        self.weights = weights
+        self.V, self.n_tok = V, n_tok
+        f = ThFrame()
+        f.tok_feat, f.tok_xyz, f.tok_rot = self.holder.data_ptr(), self.tok_xyz.data_ptr(), self.tok_rot.data_ptr()
+        f.verts, f.feat = self.verts.data_ptr(), self.feat.data_ptr()
+        f.cam_R, f.cam_T, f.cam_K = self.cam_R.data_ptr(), self.cam_T.data_ptr(), self.cam_K.data_ptr()
+        f.Rh, f.Th = self.Rh.data_ptr(), self.Th.data_ptr()
+        f.weights = weights.blob.data_ptr()
+        f.n_views, f.n_tok, f.n_verts = V, n_tok, self.verts.shape[0]
+        f.feat_h, f.feat_w = self.feat.shape[1], self.feat.shape[2]
+        f.knn = knn
+        f.uv_scale_x, f.uv_scale_y = float(uv_scale[0]), float(uv_scale[1])
+        f.knn_dist_alpha, f.cull_radius = knn_dist_alpha, cull_radius
+        f.flags = (TH_FLAG_WHITE_BKGD if white_bkgd else 0) | (TH_FLAG_SIMT_MLP if simt_mlp else 0)
+        self.c = f
+
+    @property
+    def device(self):
+        return self.holder.device
+
+    def set_flag(self, flag: int, on: bool):
+        self.c.flags = (self.c.flags | flag) if on else (self.c.flags & ~flag)
+
+
+def uv_scale_for(feat_h: int, feat_w: int, image_h: int, image_w: int):
+    """``feat_scale / image_shape`` of the reference, evaluated in float64
+    (encoder.py:149-150, if_clight_renderer.py:193): x is scaled by index 0 =
+    (W/(W-1)*2)/H_img and y by index 1 = (H/(H-1)*2)/W_img."""
+    fs = np.array([feat_w, feat_h]) / (np.array([feat_w, feat_h]) - 1) * 2.0
+    sc = fs / np.array([image_h, image_w])
+    return np.float32(sc[0]), np.float32(sc[1])
+
+
+def t_vals_for(S: int, device) -> torch.Tensor:
+    """``torch.linspace(0., 1., steps=S)`` evaluated on the CPU like the
+    reference (if_clight_renderer.py:273), then moved to the device."""
+    return torch.linspace(0., 1., steps=S).to(device)
+
+
+def _rays(ray_o, ray_d, near, far, S, t_vals=None):
+    ray_o = _f32(ray_o, "ray_o").view(-1, 3)
+    ray_d = _f32(ray_d, "ray_d").view(-1, 3)
+    near = _f32(near, "near").view(-1)
+    far = _f32(far, "far").view(-1)
+    N = ray_o.shape[0]
+    assert ray_d.shape[0] == N and near.shape[0] == N and far.shape[0] == N
+    t = t_vals_for(S, ray_o.device) if t_vals is None else _f32(t_vals, "t_vals")
+    r = ThRays()
+    r.ray_o, r.ray_d, r.near_, r.far_, r.t_vals = (x.data_ptr() for x in (ray_o, ray_d, near, far, t))
+    r.n_rays, r.n_samples = N, S
+    return r, (ray_o, ray_d, near, far, t)
+
+
+def render_rays(frame: Frame, ray_o, ray_d, near, far, S: int, mode: int = TH_RENDER_DENSE, want_raw: bool = False,
+                want_mask: bool = False, t_vals=None) -> dict:
+    """Fused a1-a11.  Returns ``rgb_map (N,3)``, ``acc_map (N)``, ``depth_map
+    (N)`` and ``counters`` (points in radius, surviving rays, points evaluated)."""
+    lib = _lib.load()
+    r, keep = _rays(ray_o, ray_d, near, far, S, t_vals)
+    N, dev = r.n_rays, keep[0].device
+    out = {"rgb_map": torch.empty((N, 3), device=dev), "acc_map": torch.empty((N,), device=dev),
+           "depth_map": torch.empty((N,), device=dev)}
+    o = ThOut()
+    o.rgb_map, o.acc_map, o.depth_map = (out[k].data_ptr() for k in ("rgb_map", "acc_map", "depth_map"))
+    if want_raw:
+        out["raw"] = torch.empty((N, S, 4), device=dev)
+        o.raw = out["raw"].data_ptr()
+    if want_mask and mode != TH_RENDER_DENSE:
+        out["pts_mask"] = torch.empty((N, S), dtype=torch.uint8, device=dev)
+        o.pts_mask = out["pts_mask"].data_ptr()
+    counters = (C.c_int64 * 3)()
+    o.counters_host = counters
+    nbytes = lib.th_workspace_bytes(N * S, frame.V, frame.verts.shape[0])
+    ws = _workspace(nbytes, dev)
+    _lib.check(lib.th_render_rays(C.byref(frame.c), C.byref(r), C.byref(o), mode, _ptr(ws), ws.numel(), _stream()),
+               "th_render_rays")
+    out["counters"] = tuple(int(c) for c in counters)
+    return out
+
+
+def query_density(frame: Frame, pts):
+    """a12: alpha_raw (P) (0 where culled) and the cull mask (P) uint8."""
+    lib = _lib.load()
+    pts = _f32(pts, "pts").view(-1, 3)
+    P = pts.shape[0]
+    alpha = torch.empty((P,), device=pts.device)
+    mask = torch.empty((P,), dtype=torch.uint8, device=pts.device)
+    nbytes = lib.th_workspace_bytes(P, frame.V, frame.verts.shape[0])
+    ws = _workspace(nbytes, pts.device)
+    _lib.check(lib.th_query_density(C.byref(frame.c), _ptr(pts), P, _ptr(alpha), _ptr(mask), _ptr(ws), ws.numel(),
+                                    _stream()), "th_query_density")
+    return alpha, mask
+
+
+# ---- staged entry points (reference tensor layouts) --------------------------------------
+def sample_points(ray_o, ray_d, near, far, S: int, t_vals=None):
+    lib = _lib.load()
+    r, keep = _rays(ray_o, ray_d, near, far, S, t_vals)
+    pts = torch.empty((r.n_rays, S, 3), device=keep[0].device)
+    z = torch.empty((r.n_rays, S), device=keep[0].device)
+    _lib.check(lib.th_sample_points(C.byref(r), _ptr(pts), _ptr(z), _stream()), "th_sample_points")
+    return pts, z
+
+
+def cull_knn1(pts, verts, radius: float = 0.1):
+    lib = _lib.load()
+    pts, verts = _f32(pts, "pts").view(-1, 3), _f32(verts, "verts").view(-1, 3)
+    P = pts.shape[0]
+    d2 = torch.empty((P,), device=pts.device)
+    idx = torch.empty((P,), dtype=torch.int64, device=pts.device)
+    mask = torch.empty((P,), dtype=torch.uint8, device=pts.device)
+    _lib.check(lib.th_cull_knn1(_ptr(pts), P, _ptr(verts), verts.shape[0], radius, _ptr(d2), _ptr(idx), _ptr(mask),
+                                _stream()), "th_cull_knn1")
+    return d2, idx, mask
+
+
+def cull_grid(pts, verts, radius: float = 0.1):
+    lib = _lib.load()
+    pts, verts = _f32(pts, "pts").view(-1, 3), _f32(verts, "verts").view(-1, 3)
+    P = pts.shape[0]
+    mask = torch.empty((P,), dtype=torch.uint8, device=pts.device)
+    ws = _workspace(lib.th_workspace_bytes(0, 1, verts.shape[0]), pts.device)
+    _lib.check(lib.th_cull_grid(_ptr(pts), P, _ptr(verts), verts.shape[0], radius, _ptr(mask), _ptr(ws), ws.numel(),
+                                _stream()), "th_cull_grid")
+    return mask
+
+
+def world2smpl(pts, Rh, Th):
+    lib = _lib.load()
+    pts = _f32(pts, "pts")
+    Rh, Th = _f32(Rh, "Rh").view(3, 3), _f32(Th, "Th").view(3)
+    out = torch.empty_like(pts)
+    _lib.check(lib.th_world2smpl(_ptr(pts), pts.numel() // 3, _ptr(Rh), _ptr(Th), _ptr(out), _stream()),
+               "th_world2smpl")
+    return out
+
+
+def view_embed(ray_d):
+    lib = _lib.load()
+    ray_d = _f32(ray_d, "ray_d").view(-1, 3)
+    out = torch.empty((ray_d.shape[0], 27), device=ray_d.device)
+    _lib.check(lib.th_view_embed(_ptr(ray_d), ray_d.shape[0], _ptr(out), _stream()), "th_view_embed")
+    return out
+
+
+def pixel_gather(frame: Frame, pts_world):
+    lib = _lib.load()
+    pts = _f32(pts_world, "pts").view(-1, 3)
+    out = torch.empty((frame.V, 384, pts.shape[0]), device=pts.device)
+    _lib.check(lib.th_pixel_gather(C.byref(frame.c), _ptr(pts), pts.shape[0], _ptr(out), _stream()),
+               "th_pixel_gather")
+    return out
+
+
+def knn_dparf(frame: Frame, pts_smpl):
+    lib = _lib.load()
+    pts = _f32(pts_smpl, "pts").view(-1, 3)
+    P, K = pts.shape[0], frame.c.knn
+    idx = torch.empty((P, K), dtype=torch.int64, device=pts.device)
+    d2 = torch.empty((P, K), device=pts.device)
+    rep = torch.empty((frame.V, 255, P), device=pts.device)
+    _lib.check(lib.th_knn_dparf(C.byref(frame.c), _ptr(pts), P, _ptr(idx), _ptr(d2), _ptr(rep), _stream()),
+               "th_knn_dparf")
+    return idx, d2, rep
+
+
+def mlp_raw(frame: Frame, human_rep, pixel_feat, viewdir, pts_mask=None):
+    lib = _lib.load()
+    human_rep, pixel_feat = _f32(human_rep, "human_rep"), _f32(pixel_feat, "pixel_feat")
+    viewdir = _f32(viewdir, "viewdir").view(-1, 27)
+    P = viewdir.shape[0]
+    assert human_rep.shape == (frame.V, 255, P) and pixel_feat.shape == (frame.V, 384, P)
+    m = None if pts_mask is None else pts_mask.to(torch.uint8).contiguous().view(-1)
+    raw = torch.empty((P, 4), device=viewdir.device)
+    ws = _workspace(lib.th_workspace_bytes(P, frame.V, 0), viewdir.device)
+    _lib.check(lib.th_mlp_raw(C.byref(frame.c), _ptr(human_rep), _ptr(pixel_feat), _ptr(viewdir), _ptr(m), P,
+                              _ptr(raw), _ptr(ws), ws.numel(), _stream()), "th_mlp_raw")
+    return raw
+
+
+def integrate(raw, z_vals, ray_d, white_bkgd: bool = False):
+    lib = _lib.load()
+    raw, z_vals, ray_d = _f32(raw, "raw"), _f32(z_vals, "z_vals"), _f32(ray_d, "ray_d").view(-1, 3)
+    N, S = z_vals.shape
+    assert raw.shape == (N, S, 4)
+    rgb = torch.empty((N, 3), device=raw.device)
+    acc = torch.empty((N,), device=raw.device)
+    depth = torch.empty((N,), device=raw.device)
+    _lib.check(lib.th_integrate(_ptr(raw), _ptr(z_vals), _ptr(ray_d), N, S, 1 if white_bkgd else 0, _ptr(rgb),
+                                _ptr(acc), _ptr(depth), _stream()), "th_integrate")
+    return rgb, acc, depth
+
+
+def nchw_to_nhwc(x):
+    lib = _lib.load()
+    x = _f32(x, "x")
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, c), device=x.device)
+    _lib.check(lib.th_nchw_to_nhwc(_ptr(x), _ptr(out), n, c, h, w, _stream()), "th_nchw_to_nhwc")
+    return out

@@ -1,0 +1,187 @@
+"""Drop-in ``Renderer`` for the reference's plugin surface.
+
+Select it from the reference's YAML (no reference file edited)::
+
+    renderer_module: 'transhuman_b200.renderer'
+    renderer_path: '<repo>/transhuman_b200/renderer.py'
+
+``make_renderer`` (lib/networks/renderer/make_renderer.py:4-8) then calls
+``Renderer(network)``; ``run.py:52,109`` call ``render_fast(batch)`` and
+``if_nerf_clight.py:45`` calls ``render(batch)``.  Same names, arguments,
+return dict (``rgb_map (1,N,3)``, ``acc_map (1,N)``, ``depth_map (1,N)``) and
+batch keys as ``lib/networks/renderer/if_clight_renderer.py``.
+
+The per-frame prologue (image encoder, SMPL painting, cluster grouping, ViT)
+stays in torch exactly as SURVEY.md section 8 scopes it -- only its Python loops
+over clusters are replaced by a segment mean (8f-1).  Everything per sample
+point runs in ``libtranshuman_b200.so`` through :mod:`transhuman_b200.ops`.
+Forward only: training (autograd + stratified jitter) keeps the reference path.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+N_VERTS = 6890
+
+
+class _DefaultCfg:
+    """The hot-path knobs with the values of configs/train_or_eval.yaml:20-67."""
+    N_samples = 64
+    num_class = 300
+    KNN = 7
+    KNN_DIST_ALPHA = 0.5
+    white_bkgd = False
+    perturb = 0.
+    rasterize = True
+    time_steps = 1
+    raw_noise_std = 0
+    use_truncation = False
+    embed_size = 192
+
+
+def _resolve_cfg(cfg):
+    if cfg is not None:
+        return cfg
+    try:  # running inside the reference tree as its plugin
+        from lib.config import cfg as ref_cfg  # type: ignore
+        return ref_cfg
+    except Exception:
+        return _DefaultCfg()
+
+
+def segment_mean(x: torch.Tensor, pc2voxel: torch.Tensor, n_class: int) -> torch.Tensor:
+    """Per-cluster mean over dim 0 -- the vectorised form of the reference's
+    ``voxelization`` loop (if_clight_renderer.py:356-371; the dict keys are
+    exactly ``arange(n_class)``).  Accumulated in float64."""
+    flat = x.reshape(x.shape[0], -1).to(torch.float64)
+    acc = torch.zeros((n_class, flat.shape[1]), dtype=torch.float64, device=x.device)
+    acc.index_add_(0, pc2voxel, flat)
+    cnt = torch.bincount(pc2voxel, minlength=n_class).to(torch.float64)
+    return (acc / cnt[:, None]).reshape((n_class,) + tuple(x.shape[1:]))
+
+
+class Renderer:
+    """Same surface as ``if_clight_renderer.Renderer`` (39, 429, 486)."""
+
+    def __init__(self, net, cfg=None, pc2voxel_ind=None, vertex_can=None):
+        self.net = net
+        self.cfg = _resolve_cfg(cfg)
+        if vertex_can is None:
+            # if_clight_renderer.py:43-48
+            with open('./data/smplx/smpl/SMPL_NEUTRAL.pkl', 'rb') as f:
+                vertex_can = pickle.load(f, encoding='latin1')['v_template']
+        self.vertex_can = torch.as_tensor(np.asarray(vertex_can)).contiguous()
+        self.CR = torch.tensor([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
+        num_voxel = int(self.cfg.num_class)
+        if pc2voxel_ind is None:
+            # if_clight_renderer.py:55
+            d = np.load(f'./kmeans_dict/kmeans_dict_{num_voxel}.npy', allow_pickle=True).item()
+            pc2voxel_ind = d['pc2voxel_ind']
+        self.pc2voxel_ind = torch.as_tensor(np.asarray(pc2voxel_ind)).to(torch.int64)
+        self.num_class = num_voxel
+        assert int(self.pc2voxel_ind.max()) + 1 == num_voxel and len(torch.unique(self.pc2voxel_ind)) == num_voxel, \
+            "cluster ids must be exactly arange(num_class)"
+        self.voxel_PE_can = segment_mean(self.vertex_can.to(torch.float64), self.pc2voxel_ind, num_voxel)
+        self._weights = None
+        self._weights_key = None
+        self.last_counters = None
+
+    # ---- prologue (torch; out of scope of the CUDA path) ---------------------------------
+    def normalize_PE(self, PE):
+        # if_clight_renderer.py:373-383
+        lo, hi = self.CR[:3][None, None].to(PE.device), self.CR[3:][None, None].to(PE.device)
+        return ((((PE - lo) / (hi - lo)) - 0.5) * 2).type(torch.float32)
+
+    @staticmethod
+    def _sample_from_feature_map(feat_map, feat_scale, image_shape, uv):
+        # if_clight_renderer.py:186-208
+        scale = torch.tensor(feat_scale / np.array(image_shape)).to(dtype=torch.float32, device=feat_map.device)
+        uv = (uv * scale - 1.0).unsqueeze(2)
+        return F.grid_sample(feat_map, uv, align_corners=True, mode="bilinear", padding_mode="border")[:, :, :, 0]
+
+    def _paint(self, batch, holder_feat_map, holder_feat_scale):
+        # paint_neural_human, if_clight_renderer.py:95-184 (t = 0)
+        smpl_vertice = batch['input_smpl_vertice'][0]
+        image_shape = batch['input_imgs'][0].shape[-2:]
+        R = batch['input_R'][0].reshape(-1, 3, 3)
+        T = batch['input_T'][0].reshape(-1, 3, 1)
+        K = batch['input_K'][0].reshape(-1, 3, 3)
+        v = torch.matmul(R[:, None], smpl_vertice.unsqueeze(-1))[..., 0] + T[:, None, :3, 0]
+        v = torch.matmul(K[:, None], v.unsqueeze(-1))[..., 0]
+        uv = v[:, :, :2] / v[:, :, 2:]
+        latent = self._sample_from_feature_map(holder_feat_map, holder_feat_scale, image_shape, uv).permute(0, 2, 1)
+        if getattr(self.cfg, 'rasterize', True) and 'input_vizmaps' in batch:
+            viz = batch['input_vizmaps'][0][0].to(torch.bool)
+            latent = torch.where(viz[..., None], latent, torch.zeros_like(latent))
+        return latent
+
+    def _packed_weights(self, V, device):
+        key = (V, str(device))
+        if self._weights is None or self._weights_key != key:
+            self._weights = ops.PackedWeights(self.net.state_dict(), V, device=device)
+            self._weights_key = key
+        return self._weights
+
+    def refresh_weights(self):
+        """Call after loading a new checkpoint into ``net``."""
+        self._weights = None
+
+    def prepare_frame(self, batch) -> ops.Frame:
+        """encoder -> paint -> group -> ViT -> tokens (if_clight_renderer.py:531-547)."""
+        assert int(getattr(self.cfg, 'time_steps', 1)) == 1
+        dev = batch['ray_o'].device
+        images = batch['input_imgs'][0].reshape(-1, *batch['input_imgs'][0].shape[2:])
+        holder_map, holder_scale, pixel_map, pixel_scale = self.net.encoder(images)
+        V = pixel_map.shape[0]
+        painted = self._paint(batch, holder_map, holder_scale)                       # (V, 6890, 192)
+        pc2 = self.pc2voxel_ind.to(dev)
+        grouped = segment_mean(painted.permute(1, 0, 2), pc2, self.num_class).permute(1, 0, 2).float()
+        pe = self.voxel_PE_can.to(dev).unsqueeze(0).repeat(V, 1, 1)
+        holder = self.net.ViT(grouped.contiguous(), self.normalize_PE(pe), mask=None)
+        tok_xyz = segment_mean(batch['tar_smpl_vertice_smplcoord'][0], pc2, self.num_class).float()
+        tok_rot = segment_mean(batch['blend_mtx'][0], pc2, self.num_class)[:, :3, :3].float()
+        image_shape = batch['input_imgs'][0].shape[-2:]
+        fs = np.asarray(pixel_scale, dtype=np.float64)
+        sc = fs / np.array(image_shape)
+        return ops.Frame(
+            holder=holder, tok_xyz=tok_xyz, tok_rot=tok_rot, verts=batch['tar_smpl_vertice'][0],
+            feat_nhwc=ops.nchw_to_nhwc(pixel_map), cam_R=batch['input_R'][0].reshape(-1, 3, 3),
+            cam_T=batch['input_T'][0].reshape(-1, 3), cam_K=batch['input_K'][0].reshape(-1, 3, 3),
+            Rh=batch['Rh'][0], Th=batch['Th'][0].reshape(3), weights=self._packed_weights(V, dev),
+            uv_scale=(np.float32(sc[0]), np.float32(sc[1])), knn=int(self.cfg.KNN),
+            knn_dist_alpha=float(self.cfg.KNN_DIST_ALPHA), white_bkgd=bool(self.cfg.white_bkgd))
+
+    # ---- the reference's two entry points ------------------------------------------------
+    def _check_forward_only(self):
+        if float(getattr(self.cfg, 'perturb', 0.)) > 0. and getattr(self.net, 'training', False) \
+                and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "transhuman_b200.Renderer is forward-only: training (stratified jitter + autograd, "
+                "if_clight_renderer.py:276-283) keeps the reference renderer")
+
+    def _run(self, batch, mode):
+        self._check_forward_only()
+        with torch.no_grad():
+            frame = self.prepare_frame(batch)
+            out = ops.render_rays(frame, batch['ray_o'][0], batch['ray_d'][0], batch['near'][0], batch['far'][0],
+                                  int(self.cfg.N_samples), mode=mode)
+        self.last_counters = out["counters"]
+        return {'rgb_map': out['rgb_map'][None], 'acc_map': out['acc_map'][None],
+                'depth_map': out['depth_map'][None]}
+
+    def render(self, batch, is_train=True):
+        """if_clight_renderer.py:486-498 (every sample evaluated)."""
+        return self._run(batch, ops.TH_RENDER_DENSE)
+
+    def render_fast(self, batch, is_train=True):
+        """if_clight_renderer.py:429-484.  Unlike the reference this does not
+        overwrite batch['ray_o','ray_d','near','far'] with their compacted
+        versions (459-462); nothing downstream reads them."""
+        return self._run(batch, ops.TH_RENDER_FAST)
