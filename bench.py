@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the TransHuman query path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path (sample -> k-NN/DPaRF -> pixel gather ->
+per-point MLP -> integrate) over one synthetic 512x512 frame at 64 samples/ray,
+300 tokens, K=7, V=3 -- BASELINE.json configs[1] -- in DENSE mode (every sample
+evaluated, `Renderer.render` semantics; data independent).  With N > 1 ranks
+(torchrun), every rank renders its own 512x512 target view of the same frame
+state and the images are gathered with one NCCL all_gather (configs[3]); the
+value is the rays all ranks rendered / max-over-ranks device time ("weak").
+
+`--impl reference` times the oracle port of the reference's PyTorch CPU path
+(oracle/transhuman_oracle.py) on the host cores, on a bounded ray sample of the
+same workload per step.  Rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_PER_POINT_V3 = 4_615_038          # reference Network.forward FLOPs per sample point, V = 3
+BYTES_PER_RAY = 4_675               # algorithmic HBM bytes per ray @ 512x512x64 dense
+
+
+def flops_per_point(V: int) -> int:
+    return 2 * (740_480 * V + 384 * V * V + 82_560) + 126
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json (bf16 sustained, kernel timed inside a long step)"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+def build_workload(args, rank: int, device):
+    """Synthetic frame state on the device + this rank's ray bundle."""
+    from transhuman_b200 import ops, synth
+    from transhuman_b200.renderer import segment_mean
+    H = args.size
+    fr = synth.make_frame(H=H, W=H, n_class=args.tokens, V=args.views, feat_hw=H, seed=0,
+                          target_azimuth=1.0 + rank * 2.0 * math.pi / 8.0, with_feature_maps=False)
+
+    def t(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+    g = torch.Generator(device=device).manual_seed(1234)
+    feat = torch.randn((args.views, H, H, 384), generator=g, device=device)          # NHWC, 1.2 GB at 512^2
+    pc2 = t(fr["pc2voxel_ind"]).long()
+    tok_xyz = segment_mean(t(fr["tar_smpl_vertice_smplcoord"]), pc2, args.tokens).float()
+    tok_rot = segment_mean(t(fr["blend_mtx"]), pc2, args.tokens)[:, :3, :3].float().contiguous()
+    weights = ops.PackedWeights(fr["weights"], args.views, device=device)
+    frame = ops.Frame(holder=t(fr["holder"]), tok_xyz=tok_xyz, tok_rot=tok_rot, verts=t(fr["tar_smpl_vertice"]),
+                      feat_nhwc=feat, cam_R=t(fr["input_R"]), cam_T=t(fr["input_T"]).reshape(args.views, 3),
+                      cam_K=t(fr["input_K"]), Rh=t(fr["Rh"]), Th=t(fr["Th"]).reshape(3), weights=weights,
+                      uv_scale=ops.uv_scale_for(H, H, H, H), simt_mlp=args.simt)
+    host_rays = tuple(torch.from_numpy(fr[k]).pin_memory() for k in ("ray_o", "ray_d", "near", "far"))
+    return fr, frame, host_rays
+
+
+def cpu_reference_leg(args, n_rays: int, steps: int, warmup: int):
+    """The oracle port of the reference's PyTorch CPU path on a bounded ray
+    sample of the same workload.  Returns (rays/s, cores, seconds/step, sample)."""
+    from oracle import transhuman_oracle as orc
+    from transhuman_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    H = args.size
+    fr = synth.make_frame(H=H, W=H, n_class=args.tokens, V=args.views, feat_hw=H, seed=0, with_feature_maps=False)
+    g = torch.Generator().manual_seed(1234)
+    fr_t = orc.to_torch_frame(fr)
+    fr_t["pixel_feat_map"] = torch.randn((args.views, 384, H, H), generator=g)
+    tokens = orc.build_tokens(fr_t)
+    # a block of rays around the image centre (dense mode: cost is data independent)
+    start = (H // 2) * H + max(0, H // 2 - n_rays // 2) if n_rays < H else (H // 2 - n_rays // (2 * H)) * H
+    sel = slice(start, start + n_rays)
+    sub = dict(fr_t)
+    for k in ("ray_o", "ray_d", "near", "far"):
+        sub[k] = fr_t[k][sel]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = orc.render(sub, args.samples, tokens=tokens)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    assert torch.isfinite(out["rgb_map"]).all()
+    sec = float(np.mean(times))
+    sample = (f"{n_rays} rays x {args.samples} samples around the image centre of the {H}x{H} frame, dense, "
+              f"oracle port of Renderer.render (torch CPU fp32)")
+    return n_rays / sec, torch.get_num_threads(), sec, sample
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--samples", type=int, default=64)
+    ap.add_argument("--tokens", type=int, default=300)
+    ap.add_argument("--views", type=int, default=3)
+    ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core GEMM path")
+    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-culled", action="store_true", help="skip the extra culled-mode measurement")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    N_rays = args.size * args.size
+    workload = (f"configs[1]: {args.size}x{args.size} render, {args.samples} samples/ray, {args.tokens} tokens, "
+                f"k=7, V={args.views}, dense (every sample evaluated)")
+    metric = f"rays/sec at {args.size}x{args.size}x{args.samples} samples"
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        val, cores, sec, sample = cpu_reference_leg(args, args.cpu_rays, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload},
+                "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import __graft_entry__ as entry
+    entry.build()
+    from transhuman_b200 import ops
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    fr, frame, host_rays = build_workload(args, rank, device)
+    dev_rays = tuple(r.to(device) for r in host_rays)
+    S = args.samples
+    gathered = torch.empty((world, N_rays, 5), device=device) if world > 1 else None
+
+    def step(rays, mode=ops.TH_RENDER_DENSE):
+        out = ops.render_rays(frame, *rays, S, mode=mode)
+        img = torch.cat([out["rgb_map"], out["acc_map"][:, None], out["depth_map"][:, None]], dim=1)
+        if world > 1:  # the final image gather over NVLink
+            dist.all_gather_into_tensor(gathered, img)
+        return img, out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps
+
+    # ---- device-resident timing (value) with live per-kernel-category timing
+    for _ in range(args.warmup):
+        step(dev_rays)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ops.launch_count(reset=True)
+    ops.profile_start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        img, last = step(dev_rays)
+    e1.record()
+    barrier()
+    prof = ops.profile_stop()
+    launches = ops.launch_count()
+    clk = clocks.stop()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_step = ms_t.item() / args.steps
+    value = world * N_rays / (ms_step * 1e-3)
+    assert torch.isfinite(img).all()
+
+    # ---- end to end: pinned host rays in, image out, every step
+    pinned_out = torch.empty((N_rays, 5)).pin_memory()
+
+    def e2e_step():
+        rays = tuple(r.to(device, non_blocking=True) for r in host_rays)
+        im, _ = step(rays)
+        pinned_out.copy_(im, non_blocking=True)
+
+    ms_e2e = timed(e2e_step, args.steps, 1)
+    h2d = sum(r.numel() * 4 for r in host_rays)
+    d2h = pinned_out.numel() * 4
+
+    # ---- roofline of the dominant kernel family (the GEMM layers)
+    peaks = measured_peaks()
+    P_step = N_rays * S
+    gemm_ms, gemm_launches = prof["gemm"]
+    gemm_ms_step = gemm_ms / args.steps
+    flops_step = flops_per_point(args.views) * P_step
+    achieved = flops_step / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("gemm_dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+                "kernel": "k_gemm_simt (fp32 CUDA cores)" if args.simt else "k_gemm_tc (tcgen05, fp16x3 split)",
+                "launches_per_step": gemm_launches // args.steps, "gemm_ms_per_step": gemm_ms_step,
+                "share_of_step": gemm_ms_step / ms_step, "peak_source": peaks["source"],
+                "flops_per_point": flops_per_point(args.views),
+                "hbm_algorithmic_gbs": BYTES_PER_RAY * N_rays / (ms_step * 1e-3) / 1e9,
+                "hbm_peak_gbs": peaks["hbm_gbs"]}
+    breakdown = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
+
+    extra = {}
+    if not args.no_culled and world == 1:
+        # render_fast semantics (what run.py executes): cull at 0.1 m + progressive RGB
+        ms_c = timed(lambda: step(dev_rays, ops.TH_RENDER_MASKED), max(1, args.steps), 1)
+        _, oc = step(dev_rays, ops.TH_RENDER_MASKED)
+        extra["culled"] = {"rays_per_s": N_rays / (ms_c * 1e-3), "ms_per_step": ms_c,
+                           "points_in_radius": oc["counters"][0], "rays_surviving": oc["counters"][1],
+                           "point_fraction": oc["counters"][0] / P_step}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            val, cores, sec, sample = cpu_reference_leg(args, args.cpu_rays, 1, 0)
+            cpu = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+        line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "l2": "inputs larger than L2 (1.2 GB feature maps per frame)",
+                           "sharding": "one 512x512 target view per rank, NCCL all_gather of the images",
+                           "mlp": "fp32 CUDA cores" if args.simt else "tcgen05 fp16x3 split, fp32 accumulate"},
+                "clocks": clk,
+                "e2e": {"value": world * N_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "ms_per_step_by_category": breakdown, **extra}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -214,6 +214,15 @@ int th_integrate(const float* raw, const float* z_vals, const float* ray_d, int6
 /* layout helper: (V,C,H,W) -> (V,H,W,C). */
 int th_nchw_to_nhwc(const float* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
 
+/* Optional device-time profile: between start and stop every kernel launch is
+ * bracketed by CUDA events on its stream; stop synchronises the device and
+ * returns, per category, the summed elapsed milliseconds and launch counts.
+ * Categories: 0 cull, 1 features (sampler + k-NN/DPaRF + pixel gather),
+ * 2 GEMM layers, 3 point-wise (attention mix, heads), 4 integration. */
+#define TH_PROF_NCAT 5
+int th_profile_start(void);
+int th_profile_stop(double* ms_per_category_host, int64_t* launches_per_category_host, int32_t n);
+
 /* Number of kernels this library launched on the calling thread since the last
  * reset (bench.py reports it as gpu_launches). */
 int64_t th_launch_count(int32_t reset);

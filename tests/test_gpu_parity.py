@@ -32,7 +32,8 @@ def _knife_edge_rays(raw, S, eps=1e-3):
     """Rays whose last-sample alpha_raw is within eps of 0: dist = 1e10 makes
     alpha_S a step function of sign(raw) (nerf_net_utils.py:31-34), so these are
     excluded-and-counted (hard parts)."""
-    return raw.reshape(-1, S, 4)[:, -1, 3].abs() < eps
+    a = raw.reshape(-1, S, 4)[:, -1, 3]
+    return (a.abs() < eps) & (a != 0)     # raw == 0 exactly is a masked-out sample, not an edge
 
 
 # ---------------------------------------------------------------- staged, exact

@@ -67,6 +67,8 @@ SIGNATURES = {
     "th_version": (C.c_char_p, []),
     "th_last_error": (C.c_char_p, []),
     "th_launch_count": (C.c_int64, [C.c_int32]),
+    "th_profile_start": (C.c_int, []),
+    "th_profile_stop": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "th_packed_weights_bytes": (C.c_size_t, [C.c_int32]),
     "th_pack_weights": (C.c_int, [C.POINTER(ThWeightsF32), C.c_int32, _fp, C.c_size_t]),
     "th_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),

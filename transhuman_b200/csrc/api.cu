@@ -21,6 +21,38 @@ void set_error(const char* fmt, ...) {
 }
 int64_t& launch_counter() { return g_launches; }
 
+// ---- profiler: CUDA events around every launch of a category, summed at stop ----
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev[PROF_NCAT];  // start/stop pairs
+  std::vector<cudaEvent_t> pool;
+  int launches[PROF_NCAT] = {0};
+};
+static thread_local ProfState g_prof;
+static cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof.pool.empty()) {
+    e = g_prof.pool.back();
+    g_prof.pool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+void prof_begin(int cat, cudaStream_t st) {
+  if (!g_prof.on) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, st);
+  g_prof.ev[cat].push_back(e);
+}
+void prof_end(int cat, cudaStream_t st) {
+  if (!g_prof.on) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, st);
+  g_prof.ev[cat].push_back(e);
+  ++g_prof.launches[cat];
+}
+
 constexpr int64_t CHUNK_PTS = 128 * 1024;  // points per MLP chunk (workspace ~ 26 KiB / point)
 
 // ---------------------------------------------------------------------------
@@ -95,6 +127,34 @@ int64_t th_launch_count(int32_t reset) {
   int64_t v = g_launches;
   if (reset) g_launches = 0;
   return v;
+}
+
+int th_profile_start(void) {
+  for (int c = 0; c < PROF_NCAT; ++c) {
+    for (cudaEvent_t e : g_prof.ev[c]) g_prof.pool.push_back(e);
+    g_prof.ev[c].clear();
+    g_prof.launches[c] = 0;
+  }
+  g_prof.on = true;
+  return TH_OK;
+}
+
+int th_profile_stop(double* ms_per_category, int64_t* launches_per_category, int32_t n) {
+  g_prof.on = false;
+  TH_CUDA(cudaDeviceSynchronize());
+  for (int c = 0; c < PROF_NCAT; ++c) {
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < g_prof.ev[c].size(); i += 2) {
+      float ms = 0.f;
+      TH_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[c][i], g_prof.ev[c][i + 1]));
+      total += ms;
+    }
+    if (c < n) {
+      if (ms_per_category) ms_per_category[c] = total;
+      if (launches_per_category) launches_per_category[c] = g_prof.launches[c];
+    }
+  }
+  return TH_OK;
 }
 
 size_t th_packed_weights_bytes(int32_t n_views) {

@@ -40,6 +40,17 @@ int64_t& launch_counter();
     }                                                                      \
   } while (0)
 
+// ---- optional per-category device timing (th_profile_start/stop) -------------
+enum ProfCat { PROF_CULL = 0, PROF_FEATURES = 1, PROF_GEMM = 2, PROF_POINTWISE = 3, PROF_INTEGRATE = 4, PROF_NCAT = 5 };
+void prof_begin(int cat, cudaStream_t st);
+void prof_end(int cat, cudaStream_t st);
+struct ProfScope {
+  int cat;
+  cudaStream_t st;
+  ProfScope(int c, cudaStream_t s) : cat(c), st(s) { prof_begin(cat, st); }
+  ~ProfScope() { prof_end(cat, st); }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm_simt(GemmArgs a) {
 }
 
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
+  ProfScope prof_(PROF_GEMM, st);
   if (a.M <= 0) return TH_OK;
   if (a.N % GBN != 0) {
     set_error("gemm_simt: N=%d not a multiple of %d", a.N, GBN);
@@ -381,7 +382,10 @@ int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& h, c
   // keys
   if ((rc = one(b.x, 256, 256, wf(run, h.k0_w), wf(run, h.k0_b), b.kp, 128, R, 0, h.h_k0))) return rc;
   if ((rc = one(b.s, 256, 256, wf(run, h.k1_w), wf(run, h.k1_b), b.ks, 128, R, 0, h.h_k1))) return rc;
-  k_attn_mix<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(b.kp, b.ks, b.x, b.xt, P, V);
+  {
+    ProfScope prof_(PROF_POINTWISE, st);
+    k_attn_mix<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(b.kp, b.ks, b.x, b.xt, P, V);
+  }
   TH_LAUNCHED();
   {  // NET = [S | XT] W_v^T
     GemmArgs g{};
@@ -416,7 +420,10 @@ int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& h, c
     g.relu = 1;
     if ((rc = gemm(g, h.h_fc3m))) return rc;
   }
-  k_alpha_head<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(o, wf(run, h.afc_w), wf(run, h.afc_b), alpha, P);
+  {
+    ProfScope prof_(PROF_POINTWISE, st);
+    k_alpha_head<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(o, wf(run, h.afc_w), wf(run, h.afc_b), alpha, P);
+  }
   TH_LAUNCHED();
   if (run.alpha_only) {
     k_write_alpha<<<(unsigned)cdiv(P, 256), 256, 0, st>>>(alpha, run.dst_ids, run.first, P, run.alpha_out, run.raw);
@@ -470,8 +477,11 @@ int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& h, c
     g.relu = 1;
     if ((rc = gemm(g, h.h_t))) return rc;
   }
-  k_rgb_head<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(t, wf(run, h.rgb_w), wf(run, h.rgb_b), alpha, run.dst_ids,
+  {
+    ProfScope prof_(PROF_POINTWISE, st);
+    k_rgb_head<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(t, wf(run, h.rgb_w), wf(run, h.rgb_b), alpha, run.dst_ids,
                                                    run.first, P, run.zero_rgb_if_transparent, run.raw);
+  }
   TH_LAUNCHED();
   return TH_OK;
 }

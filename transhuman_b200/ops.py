@@ -58,6 +58,21 @@ def launch_count(reset: bool = False) -> int:
     return int(_lib.load().th_launch_count(1 if reset else 0))
 
 
+PROFILE_CATEGORIES = ("cull", "features", "gemm", "pointwise", "integrate")
+
+
+def profile_start():
+    _lib.check(_lib.load().th_profile_start(), "th_profile_start")
+
+
+def profile_stop() -> dict:
+    """-> {category: (milliseconds, launches)} summed since profile_start()."""
+    ms = (C.c_double * 5)()
+    n = (C.c_int64 * 5)()
+    _lib.check(_lib.load().th_profile_stop(ms, n, 5), "th_profile_stop")
+    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(PROFILE_CATEGORIES)}
+
+
 class PackedWeights:
     """The per-point network's 16 Conv1d layers packed for the kernels
     (``th_pack_weights``).  ``state`` maps reference state_dict names
