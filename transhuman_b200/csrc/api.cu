@@ -401,10 +401,14 @@ int th_render_rays(const ThFrame* f, const ThRays* r, ThOut* o, int32_t culled, 
                    size_t workspace_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TH_CHECK_ARG(f && r && o, "null argument");
-  TH_CHECK_ARG(r->ray_o && r->ray_d && r->near_ && r->far_ && r->t_vals, "null ray pointer");
   TH_CHECK_ARG(r->n_rays >= 0 && r->n_samples >= 1, "bad ray counts");
-  TH_CHECK_ARG(o->rgb_map && o->acc_map && o->depth_map, "null output pointer");
   TH_CHECK_ARG(culled >= 0 && culled <= 2, "bad render mode");
+  if (r->n_rays == 0) {  // empty bundle: nothing to read or write
+    if (o->counters_host) o->counters_host[0] = o->counters_host[1] = o->counters_host[2] = 0;
+    return TH_OK;
+  }
+  TH_CHECK_ARG(r->ray_o && r->ray_d && r->near_ && r->far_ && r->t_vals, "null ray pointer");
+  TH_CHECK_ARG(o->rgb_map && o->acc_map && o->depth_map, "null output pointer");
   const int64_t N = r->n_rays;
   const int S = r->n_samples;
   const int64_t NP = N * S;
