@@ -85,11 +85,15 @@ def test_pack_weights_folds_layers(lib):
         bt = f32(offs[23], 128)
         wantb = w["fc_4.weight"].astype(np.float64) @ w["rgb_res_1.bias"].astype(np.float64) + w["fc_4.bias"]
         np.testing.assert_allclose(bt, wantb, rtol=0, atol=1e-7)
-        # fp16 hi/lo planes reconstruct the fp32 matrix to ~2^-22 relative
+        # fp16 hi/lo tile images (128B-swizzled, per 64-wide k-block) reconstruct fc_0 to ~2^-22
         h_fc0 = offs[26]
-        hi = blob[h_fc0:h_fc0 + 2 * 65536].view(np.float16).astype(np.float32)
-        lo = blob[h_fc0 + 2 * 65536:h_fc0 + 4 * 65536].view(np.float16).astype(np.float32)
-        assert np.abs((hi + lo) - fc0.reshape(-1)).max() <= 2.0 ** -21 * np.abs(fc0).max()
+        img = blob[h_fc0:h_fc0 + 4 * 65536].view(np.float16).astype(np.float32).reshape(4, 2, 256, 64)
+        n = np.arange(256)[:, None]
+        kk = np.arange(64)[None, :]
+        col = (((kk >> 3) ^ (n & 7)) << 3) + (kk & 7)          # position of element kk inside the swizzled row
+        rec = np.concatenate([np.take_along_axis(img[kb, 0], col, 1) + np.take_along_axis(img[kb, 1], col, 1)
+                              for kb in range(4)], axis=1)
+        assert np.abs(rec - fc0).max() <= 2.0 ** -21 * np.abs(fc0).max()
 
 
 def test_workspace_bytes(lib):

@@ -78,7 +78,7 @@ static std::vector<MatSpec> mat_specs(int V) {
       {&H::fc3m_w, &H::fc3m_b, &H::h_fc3m, 256, 256 * V},
       {&H::afc_w, &H::afc_b, nullptr, 1, 256},
       {&H::f_w, &H::f_b, &H::h_f, 256, 640},
-      {&H::view_w, &H::view_b, &H::h_view, 128, 288},
+      {&H::view_w, &H::view_b, &H::h_view, 128, 320},
       {&H::t_w, &H::t_b, &H::h_t, 128, 128 * V + 384},
       {&H::rgb_w, &H::rgb_b, nullptr, 3, 128},
   };
@@ -209,8 +209,8 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
   copy_cols(W(h.f_w), 640, 0, w->feature_fc_w, 256, 256, 1.0);
   copy_cols(W(h.f_w), 640, 256, w->rgb_res_0_w, 256, 384, 1.0);
   for (int n = 0; n < 256; ++n) W(h.f_b)[n] = (float)((double)w->feature_fc_b[n] + (double)w->rgb_res_0_b[n]);
-  // W_view: 283 -> 288 columns (view direction padded to 32)
-  copy_cols(W(h.view_w), 288, 0, w->view_fc_w, 128, 283, 1.0);
+  // W_view: 283 -> 320 columns (view direction padded to 32, then to a whole 64-wide k-block)
+  copy_cols(W(h.view_w), 320, 0, w->view_fc_w, 128, 283, 1.0);
   memcpy(W(h.view_b), w->view_fc_b, 128 * 4);
   // W_t = [fc_4/V x V | fc_4 @ rgb_res_1] ; b_t = fc_4 @ b_r1 + b_4
   {
@@ -229,17 +229,24 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
   }
   memcpy(W(h.rgb_w), w->rgb_fc_w, 3 * 128 * 4);
   memcpy(W(h.rgb_b), w->rgb_fc_b, 3 * 4);
-  // fp16 hi/lo planes of the GEMM matrices: hi = fp16(w), lo = fp16(w - hi)
+  // fp16 hi/lo split of the GEMM matrices, stored as shared-memory tile images for
+  // the tensor-core path: per 64-wide k-block, [hi image | lo image], each N rows
+  // of 128 bytes, K-major with the 128-byte swizzle (16-byte chunk ^= row & 7).
   for (const MatSpec& m : mat_specs(V)) {
     if (!m.h) continue;
     const float* src = W(h.*(m.w));
-    __half* hi = reinterpret_cast<__half*>(blob + h.*(m.h));
-    __half* lo = hi + (size_t)m.N * m.K;
-    for (size_t i = 0; i < (size_t)m.N * m.K; ++i) {
-      __half a = __float2half_rn(src[i]);
-      hi[i] = a;
-      lo[i] = __float2half_rn(src[i] - __half2float(a));
-    }
+    unsigned char* img = blob + h.*(m.h);
+    for (int kb = 0; kb < m.K / 64; ++kb)
+      for (int n = 0; n < m.N; ++n)
+        for (int kk = 0; kk < 64; ++kk) {
+          const float x = src[(size_t)n * m.K + kb * 64 + kk];
+          const __half a = __float2half_rn(x);
+          const __half b = __float2half_rn(x - __half2float(a));
+          const size_t off = (size_t)n * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+          unsigned char* tile = img + (size_t)kb * (2 * m.N * 128);
+          memcpy(tile + off, &a, 2);
+          memcpy(tile + (size_t)m.N * 128 + off, &b, 2);
+        }
   }
   return TH_OK;
 }

@@ -69,7 +69,7 @@ int launch_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w
 //   W_v    = [value_embed_1 | value_embed_0]            b_v = b_v1 + b_v0
 //   W_fc3m = [fc_3/V | ... | fc_3/V]   (mean over views folded into K)
 //   W_f    = [feature_fc | rgb_res_0]                   b_f = b_ff + b_r0
-//   W_view = [view_fc[:, :256] | view_fc[:, 256:283] | 0(5)]
+//   W_view = [view_fc[:, :256] | view_fc[:, 256:283] | 0(37)]   (K = 320)
 //   W_t    = [fc_4/V | ... | fc_4/V | fc_4 @ rgb_res_1] b_t = fc_4 @ b_r1 + b_4
 struct PackedHeader {
   uint32_t magic;      // 'THW1'
@@ -86,10 +86,10 @@ struct PackedHeader {
   uint64_t fc3m_w, fc3m_b;      // (256,256*V)
   uint64_t afc_w, afc_b;        // (256), (1)
   uint64_t f_w, f_b;            // (256,640)
-  uint64_t view_w, view_b;      // (128,288)
+  uint64_t view_w, view_b;      // (128,320)
   uint64_t t_w, t_b;            // (128,128*V+384)
   uint64_t rgb_w, rgb_b;        // (3,128), (3)
-  // fp16 hi/lo planes for the tensor-core path: per matrix, (N, K) fp16 hi then lo
+  // fp16 hi/lo tile images for the tensor-core path (see th_pack_weights)
   uint64_t h_fc0, h_ar0, h_k0, h_k1, h_v, h_fc1, h_fc2, h_fc3m, h_f, h_view, h_t;
 };
 constexpr uint32_t PACK_MAGIC = 0x31574854u;

@@ -453,7 +453,7 @@ int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& h, c
     g.seg[1] = {b.vd, VD_LD, VD_LD, P};
     g.nseg = 2;
     g.W = wf(run, h.view_w);
-    g.ldw = 288;
+    g.ldw = 320;
     g.bias = wf(run, h.view_b);
     g.C = gbuf;
     g.ldc = 128;

@@ -1,8 +1,382 @@
-// tcgen05 split-fp16 GEMM (placeholder until the tensor-core kernel lands).
+// tcgen05 GEMM for the per-point network's layers (rows a9/a10), sm_100a.
+//
+//   C[M,N] = act( sum_seg A_seg[M,K_seg] . W[:, seg]^T + bias ),  fp32 in / fp32 out
+//
+// Precision: a single-pass TF32/BF16 product misses the <= 1e-4 RGB bar
+// (SURVEY finding 2), so every operand is split into two fp16 terms,
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (22 significant bits), and
+// three tensor-core products are accumulated in fp32 in TMEM:
+//     D += A_hi B_hi ;  D += A_lo B_hi ;  D += A_hi B_lo        (lo*lo ~ 2^-22 dropped)
+// Weights are split once on the host (th_pack_weights) and stored as ready-made
+// shared-memory tile images (128B-swizzled, K-major), so a k-block of B is one
+// cp.async.bulk; activations are split on the fly by the producer warps.
+//
+// Persistent, warp-specialised CTA (one per SM), BM = 128 rows, BN = N (128 or
+// 256: A is read once), BK = 64:
+//   warps 0-3  A producers: coalesced fp32 loads -> hi/lo fp16 -> swizzled smem
+//   warp  4    B loader:    cp.async.bulk of the packed weight tile images
+//   warp  5    MMA issuer:  one thread issues tcgen05.mma (kind::f16, M=128)
+//   warps 6-9  epilogue:    tcgen05.ld -> bias/ReLU -> global; overlaps the next
+//                           tile's mainloop through a double-buffered accumulator
+// Pipelines: smem full/empty mbarriers per stage, TMEM full/empty per buffer.
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
+
 namespace th {
-int launch_gemm_tc(const GemmArgs& a, const void* w_hi_lo, cudaStream_t st) {
-  (void)w_hi_lo;
-  return launch_gemm_simt(a, st);
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                         // fp16 elements per k-block = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = BM * BK * 2;      // 16 KiB (one of hi / lo)
+constexpr int NUM_THREADS = 320;
+constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {  // turn a deadlock into an error instead of a hang
+      printf("k_gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+             bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms of 1024 B
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format F16 (0), K-major
+// A and B, n_dim = N>>3 [17,23), m_dim = M>>4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// split two floats into packed fp16 hi and lo pairs
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __half2 h = __floats2half2_rn(x, y);
+  float2 hf = __half22float2(h);
+  __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+struct TcArgs {
+  GemmArgs g;
+  const unsigned char* wimg;  // per k-block: [hi tile image (N x 128 B) | lo tile image]
+  int nkb;                    // k-blocks over all segments (each segment rounded up to 64)
+  int num_tiles;
+};
+
+template <int N>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
+  constexpr int B_TILE_BYTES = N * BK * 2;                      // one of hi / lo
+  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  constexpr int NSTAGE = N == 256 ? 2 : 3;
+  constexpr int TMEM_COLS = 2 * N;                              // double-buffered fp32 accumulator
+
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  // control block after the stages
+  const uint32_t ctrl = base + NSTAGE * STAGE_BYTES;
+  const uint32_t bar_full = ctrl, bar_empty = ctrl + 8 * NSTAGE, bar_tfull = ctrl + 16 * NSTAGE,
+                 bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + NSTAGE * STAGE_BYTES + 16 * NSTAGE + 32);
+  float* s_bias = reinterpret_cast<float*>(base_ptr + NSTAGE * STAGE_BYTES + 16 * NSTAGE + 64);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bar_full + 8 * s, 128 + 1);  // 128 A-producer threads + the B loader's expect_tx arrive
+      mbar_init(bar_empty + 8 * s, 1);       // tcgen05.commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);       // tcgen05.commit
+      mbar_init(bar_tempty + 8 * b, 128);    // epilogue threads
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < N; i += NUM_THREADS) s_bias[i] = a.g.bias ? a.g.bias[i] : 0.f;
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t M = a.g.M;
+
+  if (warp < 4) {
+    // ===================== A producers =====================
+    int kcount = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int64_t m0 = (int64_t)tile * BM;
+      for (int sgi = 0; sgi < a.g.nseg; ++sgi) {
+        const GemmSeg sg = a.g.seg[sgi];
+        for (int kin = 0; kin < sg.K; kin += BK, ++kcount) {
+          const int s = kcount % NSTAGE;
+          const uint32_t ph = (kcount / NSTAGE) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          unsigned char* a_hi = base_ptr + s * STAGE_BYTES;
+          unsigned char* a_lo = a_hi + A_TILE_BYTES;
+          // 4 passes of 32 rows; a warp covers 8 rows x 64 columns per pass:
+          // lane -> row (lane>>2), 4 float4 loads at columns 16*i + 4*(lane&3)
+          float4 v[4][4];
+#pragma unroll
+          for (int pass = 0; pass < 4; ++pass) {
+            const int r = pass * 32 + warp * 8 + (lane >> 2);
+            const int64_t m = m0 + r;
+            const bool row_ok = m < M;
+            const int64_t row = sg.row_mod ? m % sg.row_mod : m;
+            const float* src = sg.ptr + row * sg.ld + kin;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int col = 16 * i + 4 * (lane & 3);
+              v[pass][i] = (row_ok && kin + col < sg.K) ? __ldg(reinterpret_cast<const float4*>(src + col))
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int pass = 0; pass < 4; ++pass) {
+            const int r = pass * 32 + warp * 8 + (lane >> 2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint2 hi, lo;
+              split2(v[pass][i].x, v[pass][i].y, hi.x, lo.x);
+              split2(v[pass][i].z, v[pass][i].w, hi.y, lo.y);
+              // byte offset of columns [col, col+4) in the 128B row: 32*i + 8*(lane&3)
+              const int chunk = 2 * i + ((lane & 3) >> 1);
+              const int off = r * 128 + ((chunk ^ (r & 7)) << 4) + ((lane & 1) << 3);
+              *reinterpret_cast<uint2*>(a_hi + off) = hi;
+              *reinterpret_cast<uint2*>(a_lo + off) = lo;
+            }
+          }
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          mbar_arrive(bar_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== B loader =====================
+    if (lane == 0) {
+      int kcount = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < a.nkb; ++kb, ++kcount) {
+          const int s = kcount % NSTAGE;
+          const uint32_t ph = (kcount / NSTAGE) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, 2 * B_TILE_BYTES);
+          bulk_g2s(base + s * STAGE_BYTES + 2 * A_TILE_BYTES, a.wimg + (size_t)kb * (2 * B_TILE_BYTES),
+                   2 * B_TILE_BYTES, bar_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(N);
+      int kcount = 0, it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        const int ab = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * ab, aph ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * N;
+        for (int kb = 0; kb < a.nkb; ++kb, ++kcount) {
+          const int s = kcount % NSTAGE;
+          const uint32_t ph = (kcount / NSTAGE) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * STAGE_BYTES;
+          const uint64_t d_ahi = umma_desc(sa), d_alo = umma_desc(sa + A_TILE_BYTES);
+          const uint64_t d_bhi = umma_desc(sa + 2 * A_TILE_BYTES),
+                         d_blo = umma_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 32) >> 4);  // 16 fp16 = 32 bytes along K inside the swizzle row
+            umma_f16(d_tmem, d_ahi + adv, d_bhi + adv, idesc, (kb | ks) ? 1u : 0u);
+            umma_f16(d_tmem, d_alo + adv, d_bhi + adv, idesc, 1u);
+            umma_f16(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+          }
+          umma_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs have read it
+        }
+        umma_commit(bar_tfull + 8 * ab);   // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * ab, aph);
+      tc_fence_after();
+      const int64_t m = (int64_t)tile * BM + r;
+      float* crow = a.g.C + m * a.g.ldc;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (m < M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[j + 0]) + s_bias[c0 + j + 0];
+            o.y = __uint_as_float(v[j + 1]) + s_bias[c0 + j + 1];
+            o.z = __uint_as_float(v[j + 2]) + s_bias[c0 + j + 2];
+            o.w = __uint_as_float(v[j + 3]) + s_bias[c0 + j + 3];
+            if (a.g.relu) {
+              o.x = fmaxf(o.x, 0.f);
+              o.y = fmaxf(o.y, 0.f);
+              o.z = fmaxf(o.z, 0.f);
+              o.w = fmaxf(o.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(crow + c0 + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * ab);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <int N>
+static size_t smem_bytes() {
+  constexpr int NSTAGE = N == 256 ? 2 : 3;
+  return 1024 + (size_t)NSTAGE * (2 * A_TILE_BYTES + 2 * N * BK * 2) + 16 * NSTAGE + 64 + N * 4 + 64;
+}
+
+}  // namespace tc
+
+int tc_image_kblocks(const GemmArgs& a) {
+  int n = 0;
+  for (int s = 0; s < a.nseg; ++s) n += (a.seg[s].K + tc::BK - 1) / tc::BK;
+  return n;
+}
+
+int launch_gemm_tc(const GemmArgs& a, const void* w_image, cudaStream_t st) {
+  ProfScope prof_(PROF_GEMM, st);
+  if (a.M <= 0) return TH_OK;
+  if (a.N != 128 && a.N != 256) {
+    set_error("gemm_tc: N=%d unsupported (128 or 256)", a.N);
+    return TH_EINVAL;
+  }
+  for (int s = 0; s < a.nseg; ++s)
+    if (a.seg[s].K % 16 != 0 || a.seg[s].ld % 4 != 0 || (reinterpret_cast<uintptr_t>(a.seg[s].ptr) & 15)) {
+      set_error("gemm_tc: segment %d K=%d ld=%d unsupported", s, a.seg[s].K, a.seg[s].ld);
+      return TH_EINVAL;
+    }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    TH_CUDA(cudaGetDevice(&dev));
+    TH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  tc::TcArgs t;
+  t.g = a;
+  t.wimg = static_cast<const unsigned char*>(w_image);
+  t.nkb = tc_image_kblocks(a);
+  t.num_tiles = (int)cdiv(a.M, tc::BM);
+  const int grid = t.num_tiles < num_sms ? t.num_tiles : num_sms;
+  if (a.N == 256) {
+    static bool cfg = false;
+    const size_t smem = tc::smem_bytes<256>();
+    if (!cfg) {
+      TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cfg = true;
+    }
+    tc::k_gemm_tc<256><<<grid, tc::NUM_THREADS, smem, st>>>(t);
+  } else {
+    static bool cfg = false;
+    const size_t smem = tc::smem_bytes<128>();
+    if (!cfg) {
+      TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cfg = true;
+    }
+    tc::k_gemm_tc<128><<<grid, tc::NUM_THREADS, smem, st>>>(t);
+  }
+  TH_LAUNCHED();
+  return TH_OK;
+}
+
 }  // namespace th
