@@ -159,6 +159,8 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-culled", action="store_true", help="skip the extra culled-mode measurement")
+    ap.add_argument("--profile-run", action="store_true",
+                    help="one untimed dense step and exit (for ncu; prints nothing)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -228,6 +230,11 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / steps
+
+    if args.profile_run:
+        step(dev_rays)
+        barrier()
+        return
 
     # ---- device-resident timing (value) with live per-kernel-category timing
     for _ in range(args.warmup):
