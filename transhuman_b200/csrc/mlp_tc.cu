@@ -30,6 +30,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;                         // fp16 elements per k-block = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 2;      // 16 KiB (one of hi / lo)
 constexpr int NUM_THREADS = 320;
+constexpr int EPI_LD = 36;                     // staging row stride in floats (16 B aligned, conflict-free float4)
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
                  bar_tempty = bar_tfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + NSTAGE * STAGE_BYTES + 16 * NSTAGE + 32);
   float* s_bias = reinterpret_cast<float*>(base_ptr + NSTAGE * STAGE_BYTES + 16 * NSTAGE + 64);
+  float* s_stage = s_bias + N;  // 4 epilogue warps x 32 rows x EPI_LD floats
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -175,53 +177,67 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
 
   if (warp < 4) {
     // ===================== A producers =====================
-    int kcount = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    // Software pipelined: the global loads of k-block i+1 are issued right after
+    // k-block i has been written to shared memory, so their latency overlaps the
+    // wait for the next free stage.
+    // 4 passes of 32 rows; a warp covers 8 rows x 64 columns per pass:
+    // lane -> row (lane>>2), 4 float4 loads at columns 16*i + 4*(lane&3)
+    float4 v[4][4];
+    auto load_block = [&](int tile, int sgi, int kin) {
+      const GemmSeg sg = a.g.seg[sgi];
       const int64_t m0 = (int64_t)tile * BM;
-      for (int sgi = 0; sgi < a.g.nseg; ++sgi) {
-        const GemmSeg sg = a.g.seg[sgi];
-        for (int kin = 0; kin < sg.K; kin += BK, ++kcount) {
-          const int s = kcount % NSTAGE;
-          const uint32_t ph = (kcount / NSTAGE) & 1;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          unsigned char* a_hi = base_ptr + s * STAGE_BYTES;
-          unsigned char* a_lo = a_hi + A_TILE_BYTES;
-          // 4 passes of 32 rows; a warp covers 8 rows x 64 columns per pass:
-          // lane -> row (lane>>2), 4 float4 loads at columns 16*i + 4*(lane&3)
-          float4 v[4][4];
 #pragma unroll
-          for (int pass = 0; pass < 4; ++pass) {
-            const int r = pass * 32 + warp * 8 + (lane >> 2);
-            const int64_t m = m0 + r;
-            const bool row_ok = m < M;
-            const int64_t row = sg.row_mod ? m % sg.row_mod : m;
-            const float* src = sg.ptr + row * sg.ld + kin;
+      for (int pass = 0; pass < 4; ++pass) {
+        const int r = pass * 32 + warp * 8 + (lane >> 2);
+        const int64_t m = m0 + r;
+        const bool row_ok = m < M;
+        const int64_t row = sg.row_mod ? m % sg.row_mod : m;
+        const float* src = sg.ptr + row * sg.ld + kin;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int col = 16 * i + 4 * (lane & 3);
-              v[pass][i] = (row_ok && kin + col < sg.K) ? __ldg(reinterpret_cast<const float4*>(src + col))
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-#pragma unroll
-          for (int pass = 0; pass < 4; ++pass) {
-            const int r = pass * 32 + warp * 8 + (lane >> 2);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint2 hi, lo;
-              split2(v[pass][i].x, v[pass][i].y, hi.x, lo.x);
-              split2(v[pass][i].z, v[pass][i].w, hi.y, lo.y);
-              // byte offset of columns [col, col+4) in the 128B row: 32*i + 8*(lane&3)
-              const int chunk = 2 * i + ((lane & 3) >> 1);
-              const int off = r * 128 + ((chunk ^ (r & 7)) << 4) + ((lane & 1) << 3);
-              *reinterpret_cast<uint2*>(a_hi + off) = hi;
-              *reinterpret_cast<uint2*>(a_lo + off) = lo;
-            }
-          }
-          fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-          mbar_arrive(bar_full + 8 * s);
+        for (int i = 0; i < 4; ++i) {
+          const int col = 16 * i + 4 * (lane & 3);
+          v[pass][i] = (row_ok && kin + col < sg.K) ? __ldg(reinterpret_cast<const float4*>(src + col))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+    };
+    int kcount = 0;
+    int tile = blockIdx.x, sgi = 0, kin = 0;
+    if (tile < a.num_tiles) load_block(tile, 0, 0);
+    while (tile < a.num_tiles) {
+      const int s = kcount % NSTAGE;
+      const uint32_t ph = (kcount / NSTAGE) & 1;
+      ++kcount;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      unsigned char* a_hi = base_ptr + s * STAGE_BYTES;
+      unsigned char* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int r = pass * 32 + warp * 8 + (lane >> 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint2 hi, lo;
+          split2(v[pass][i].x, v[pass][i].y, hi.x, lo.x);
+          split2(v[pass][i].z, v[pass][i].w, hi.y, lo.y);
+          // byte offset of columns [col, col+4) in the 128B row: 32*i + 8*(lane&3)
+          const int chunk = 2 * i + ((lane & 3) >> 1);
+          const int off = r * 128 + ((chunk ^ (r & 7)) << 4) + ((lane & 1) << 3);
+          *reinterpret_cast<uint2*>(a_hi + off) = hi;
+          *reinterpret_cast<uint2*>(a_lo + off) = lo;
+        }
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(bar_full + 8 * s);
+      // advance to the next k-block (segment-major inside a tile) and prefetch it
+      kin += BK;
+      if (kin >= a.g.seg[sgi].K) {
+        kin = 0;
+        if (++sgi == a.g.nseg) {
+          sgi = 0;
+          tile += gridDim.x;
+        }
+      }
+      if (tile < a.num_tiles) load_block(tile, sgi, kin);
     }
   } else if (warp == 4) {
     // ===================== B loader =====================
@@ -272,39 +288,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
     }
   } else {
     // ===================== epilogue =====================
+    // TMEM -> registers (one row per thread) -> bias/ReLU -> per-warp 32x32 staging
+    // tile in shared memory -> global stores in which 8 lanes cover one full
+    // 128-byte line of a row (row-strided 16-byte stores would cost 32 L2 write
+    // requests per instruction).
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int r = q * 32 + lane;
+    float* stage = s_stage + q * (32 * EPI_LD);
     int it = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(bar_tfull + 8 * ab, aph);
       tc_fence_after();
-      const int64_t m = (int64_t)tile * BM + r;
-      float* crow = a.g.C + m * a.g.ldc;
+      const int64_t mbase = (int64_t)tile * BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * N;
 #pragma unroll 1
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m < M) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = __uint_as_float(v[j + 0]) + s_bias[c0 + j + 0];
-            o.y = __uint_as_float(v[j + 1]) + s_bias[c0 + j + 1];
-            o.z = __uint_as_float(v[j + 2]) + s_bias[c0 + j + 2];
-            o.w = __uint_as_float(v[j + 3]) + s_bias[c0 + j + 3];
-            if (a.g.relu) {
-              o.x = fmaxf(o.x, 0.f);
-              o.y = fmaxf(o.y, 0.f);
-              o.z = fmaxf(o.z, 0.f);
-              o.w = fmaxf(o.w, 0.f);
-            }
-            *reinterpret_cast<float4*>(crow + c0 + j) = o;
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          o.x = __uint_as_float(v[j + 0]) + s_bias[c0 + j + 0];
+          o.y = __uint_as_float(v[j + 1]) + s_bias[c0 + j + 1];
+          o.z = __uint_as_float(v[j + 2]) + s_bias[c0 + j + 2];
+          o.w = __uint_as_float(v[j + 3]) + s_bias[c0 + j + 3];
+          if (a.g.relu) {
+            o.x = fmaxf(o.x, 0.f);
+            o.y = fmaxf(o.y, 0.f);
+            o.z = fmaxf(o.z, 0.f);
+            o.w = fmaxf(o.w, 0.f);
           }
+          *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = o;
         }
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int row = rr + (lane >> 3);
+          const int64_t m = mbase + row;
+          const float4 o = *reinterpret_cast<const float4*>(stage + row * EPI_LD + (lane & 7) * 4);
+          if (m < M) *reinterpret_cast<float4*>(a.g.C + m * a.g.ldc + c0 + (lane & 7) * 4) = o;
+        }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * ab);
@@ -323,7 +349,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
 template <int N>
 static size_t smem_bytes() {
   constexpr int NSTAGE = N == 256 ? 2 : 3;
-  return 1024 + (size_t)NSTAGE * (2 * A_TILE_BYTES + 2 * N * BK * 2) + 16 * NSTAGE + 64 + N * 4 + 64;
+  return 1024 + (size_t)NSTAGE * (2 * A_TILE_BYTES + 2 * N * BK * 2) + 16 * NSTAGE + 64 + N * 4 +
+         4 * 32 * EPI_LD * 4 + 64;
 }
 
 }  // namespace tc
