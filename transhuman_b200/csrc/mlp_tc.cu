@@ -13,11 +13,13 @@
 //
 // Persistent, warp-specialised CTA (one per SM), BM = 128 rows, BN = N (128 or
 // 256: A is read once), BK = 64:
-//   warps 0-3  A producers: coalesced fp32 loads -> hi/lo fp16 -> swizzled smem
-//   warp  4    B loader:    cp.async.bulk of the packed weight tile images
-//   warp  5    MMA issuer:  one thread issues tcgen05.mma (kind::f16, M=128)
-//   warps 6-9  epilogue:    tcgen05.ld -> bias/ReLU -> global; overlaps the next
-//                           tile's mainloop through a double-buffered accumulator
+//   warps 0-7   A producers: coalesced fp32 loads -> hi/lo fp16 -> swizzled smem
+//                            (two groups alternating k-blocks, register prefetched)
+//   warp  8     B loader:    cp.async.bulk of the packed weight tile images
+//   warp  9     MMA issuer:  one thread issues tcgen05.mma (kind::f16, M=128)
+//   warps 10-13 epilogue:    tcgen05.ld -> bias/ReLU -> smem staging -> full-line
+//                            stores; overlaps the next tile's mainloop through a
+//                            double-buffered accumulator
 // Pipelines: smem full/empty mbarriers per stage, TMEM full/empty per buffer.
 #include <cuda_fp16.h>
 
@@ -29,7 +31,7 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;                         // fp16 elements per k-block = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 2;      // 16 KiB (one of hi / lo)
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 448;                // 8 producer + 1 loader + 1 MMA + 4 epilogue warps
 constexpr int EPI_LD = 36;                     // staging row stride in floats (16 B aligned, conflict-free float4)
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;
 
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < N; i += NUM_THREADS) s_bias[i] = a.g.bias ? a.g.bias[i] : 0.f;
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)TMEM_COLS)
                  : "memory");
@@ -175,60 +177,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
 
   const int64_t M = a.g.M;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===================== A producers =====================
-    // Software pipelined: the global loads of k-block i+1 are issued right after
-    // k-block i has been written to shared memory, so their latency overlaps the
-    // wait for the next free stage.
-    // 4 passes of 32 rows; a warp covers 8 rows x 64 columns per pass:
-    // lane -> row (lane>>2), 4 float4 loads at columns 16*i + 4*(lane&3)
-    float4 v[4][4];
+    // Two groups of 4 warps alternate k-blocks (group g takes k-blocks g, g+2, ...),
+    // each software pipelined: the global loads of a group's next k-block are issued
+    // right after the current one has been written to shared memory, so 2 x 32 KB of
+    // loads are in flight per SM while the producers wait for free stages.
+    // Lane mapping per pass (16 rows x 64 columns per warp): row = lane>>1, 8 float4
+    // loads at columns 8*i + 4*(lane&1): 16 full 32-byte sectors per load instruction,
+    // and the 8-byte swizzled stores of a half-warp hit 8 distinct 16-byte chunks.
+    const int grp = warp >> 2, wq = warp & 3;
+    float4 v[2][8];
     auto load_block = [&](int tile, int sgi, int kin) {
       const GemmSeg sg = a.g.seg[sgi];
       const int64_t m0 = (int64_t)tile * BM;
 #pragma unroll
-      for (int pass = 0; pass < 4; ++pass) {
-        const int r = pass * 32 + warp * 8 + (lane >> 2);
+      for (int pass = 0; pass < 2; ++pass) {
+        const int r = pass * 64 + wq * 16 + (lane >> 1);
         const int64_t m = m0 + r;
         const bool row_ok = m < M;
         const int64_t row = sg.row_mod ? m % sg.row_mod : m;
-        const float* src = sg.ptr + row * sg.ld + kin;
+        const float* src = sg.ptr + row * sg.ld + kin + 4 * (lane & 1);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int col = 16 * i + 4 * (lane & 3);
-          v[pass][i] = (row_ok && kin + col < sg.K) ? __ldg(reinterpret_cast<const float4*>(src + col))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < 8; ++i)
+          v[pass][i] = (row_ok && kin + 8 * i + 4 * (lane & 1) < sg.K)
+                           ? __ldg(reinterpret_cast<const float4*>(src + 8 * i))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    int kcount = 0;
+    // k-block cursor (tile, segment, offset); advance() moves it by one k-block
     int tile = blockIdx.x, sgi = 0, kin = 0;
-    if (tile < a.num_tiles) load_block(tile, 0, 0);
-    while (tile < a.num_tiles) {
-      const int s = kcount % NSTAGE;
-      const uint32_t ph = (kcount / NSTAGE) & 1;
-      ++kcount;
-      mbar_wait(bar_empty + 8 * s, ph ^ 1);
-      unsigned char* a_hi = base_ptr + s * STAGE_BYTES;
-      unsigned char* a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll
-      for (int pass = 0; pass < 4; ++pass) {
-        const int r = pass * 32 + warp * 8 + (lane >> 2);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint2 hi, lo;
-          split2(v[pass][i].x, v[pass][i].y, hi.x, lo.x);
-          split2(v[pass][i].z, v[pass][i].w, hi.y, lo.y);
-          // byte offset of columns [col, col+4) in the 128B row: 32*i + 8*(lane&3)
-          const int chunk = 2 * i + ((lane & 3) >> 1);
-          const int off = r * 128 + ((chunk ^ (r & 7)) << 4) + ((lane & 1) << 3);
-          *reinterpret_cast<uint2*>(a_hi + off) = hi;
-          *reinterpret_cast<uint2*>(a_lo + off) = lo;
-        }
-      }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(bar_full + 8 * s);
-      // advance to the next k-block (segment-major inside a tile) and prefetch it
+    auto advance = [&]() {
       kin += BK;
       if (kin >= a.g.seg[sgi].K) {
         kin = 0;
@@ -237,9 +216,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
           tile += gridDim.x;
         }
       }
+    };
+    int kcount = 0;
+    if (grp == 1 && tile < a.num_tiles) {
+      advance();
+      kcount = 1;
+    }
+    if (tile < a.num_tiles) load_block(tile, sgi, kin);
+    while (tile < a.num_tiles) {
+      const int s = kcount % NSTAGE;
+      const uint32_t ph = (kcount / NSTAGE) & 1;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      unsigned char* a_hi = base_ptr + s * STAGE_BYTES;
+      unsigned char* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int r = pass * 64 + wq * 16 + (lane >> 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint2 hi, lo;
+          split2(v[pass][i].x, v[pass][i].y, hi.x, lo.x);
+          split2(v[pass][i].z, v[pass][i].w, hi.y, lo.y);
+          // columns [8i + 4*(lane&1), +4): 16-byte chunk i of the 128-byte row, 8-byte half (lane&1)
+          const int off = r * 128 + ((i ^ (r & 7)) << 4) + ((lane & 1) << 3);
+          *reinterpret_cast<uint2*>(a_hi + off) = hi;
+          *reinterpret_cast<uint2*>(a_lo + off) = lo;
+        }
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(bar_full + 8 * s);
+      advance();
+      if (tile < a.num_tiles) advance();
+      kcount += 2;
       if (tile < a.num_tiles) load_block(tile, sgi, kin);
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ===================== B loader =====================
     if (lane == 0) {
       int kcount = 0;
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(N);
@@ -339,7 +350,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
