@@ -22,6 +22,7 @@
 //                            double-buffered accumulator
 // Pipelines: smem full/empty mbarriers per stage, TMEM full/empty per buffer.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -357,6 +358,301 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
   }
 }
 
+// ===========================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs (one TPC) works on a
+// 256-row super-tile.  Each CTA stages its own 128 rows of A and HALF of the
+// weight tile (N/2 rows); the leader CTA issues tcgen05.mma.cta_group::2 (M=256),
+// whose operand fetch reads both halves, so every SM reads and loads only half of
+// B: shared-memory operand traffic per SM drops from 96 to 64 B/clk, weight L2
+// traffic halves, and a stage shrinks to 64 KB (3 stages).  D stays per CTA
+// (128 rows x N columns of its own TMEM), so the epilogue is unchanged.
+// Cross-CTA synchronisation:
+//   full   : per-CTA barrier (producers + B bytes); the peer's MMA-warp lane 0
+//            relays each completed phase to the leader's `pfull` barrier
+//   empty  : tcgen05.commit multicast (mask 0b11) arrives in both CTAs
+//   tfull  : same multicast commit
+//   tempty : leader's epilogue threads arrive locally, the peer's remotely
+// ===========================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+template <int N>
+struct Cfg2 {
+  static constexpr int HALF_BYTES = (N / 2) * BK * 2;           // this CTA's half of one weight plane
+  static constexpr int PLANE_BYTES = N * BK * 2;                // a full hi (or lo) plane in the image
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * HALF_BYTES;
+  static constexpr int NSTAGE = N == 256 ? 3 : 4;
+  static constexpr int CTRL_BYTES = 256;
+  static constexpr size_t SMEM = 1024 + (size_t)NSTAGE * STAGE_BYTES + CTRL_BYTES + N * 4 + 4 * 32 * EPI_LD * 4 + 64;
+};
+
+template <int N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_gemm_tc2(const TcArgs a) {
+  using C = Cfg2<N>;
+  constexpr int NSTAGE = C::NSTAGE;
+  constexpr int STAGE_BYTES = C::STAGE_BYTES;
+  constexpr int TMEM_COLS = 2 * N;
+
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t ctrl = base + NSTAGE * STAGE_BYTES;
+  const uint32_t bar_full = ctrl, bar_empty = ctrl + 32, bar_pfull = ctrl + 64, bar_tfull = ctrl + 96,
+                 bar_tempty = ctrl + 112, bar_ptempty = ctrl + 128;
+  unsigned char* ctrl_ptr = base_ptr + NSTAGE * STAGE_BYTES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl_ptr + 160);
+  float* s_bias = reinterpret_cast<float*>(ctrl_ptr + C::CTRL_BYTES);
+  float* s_stage = s_bias + N;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int num_super = (a.num_tiles + 1) >> 1;  // 256-row super-tiles
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bar_full + 8 * s, 128 + 1);
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_pfull + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 128);
+      mbar_init(bar_ptempty + 8 * b, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < N; i += NUM_THREADS) s_bias[i] = a.g.bias ? a.g.bias[i] : 0.f;
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t M = a.g.M;
+
+  if (warp < 8) {
+    // ===================== A producers (as in the 1-CTA kernel) =====================
+    const int grp = warp >> 2, wq = warp & 3;
+    float4 v[2][8];
+    auto load_block = [&](int st, int sgi, int kin) {
+      const GemmSeg sg = a.g.seg[sgi];
+      const int64_t m0 = (int64_t)st * (2 * BM) + rank * BM;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int r = pass * 64 + wq * 16 + (lane >> 1);
+        const int64_t m = m0 + r;
+        const bool row_ok = m < M;
+        const int64_t row = sg.row_mod ? m % sg.row_mod : m;
+        const float* src = sg.ptr + row * sg.ld + kin + 4 * (lane & 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          v[pass][i] = (row_ok && kin + 8 * i + 4 * (lane & 1) < sg.K)
+                           ? __ldg(reinterpret_cast<const float4*>(src + 8 * i))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    int st = cluster_id, sgi = 0, kin = 0;
+    auto advance = [&]() {
+      kin += BK;
+      if (kin >= a.g.seg[sgi].K) {
+        kin = 0;
+        if (++sgi == a.g.nseg) {
+          sgi = 0;
+          st += nclusters;
+        }
+      }
+    };
+    int kcount = 0;
+    if (grp == 1 && st < num_super) {
+      advance();
+      kcount = 1;
+    }
+    if (st < num_super) load_block(st, sgi, kin);
+    while (st < num_super) {
+      const int s = kcount % NSTAGE;
+      const uint32_t ph = (kcount / NSTAGE) & 1;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      unsigned char* a_hi = base_ptr + s * STAGE_BYTES;
+      unsigned char* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int r = pass * 64 + wq * 16 + (lane >> 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint2 hi, lo;
+          split2(v[pass][i].x, v[pass][i].y, hi.x, lo.x);
+          split2(v[pass][i].z, v[pass][i].w, hi.y, lo.y);
+          const int off = r * 128 + ((i ^ (r & 7)) << 4) + ((lane & 1) << 3);
+          *reinterpret_cast<uint2*>(a_hi + off) = hi;
+          *reinterpret_cast<uint2*>(a_lo + off) = lo;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * s);
+      advance();
+      if (st < num_super) advance();
+      kcount += 2;
+      if (st < num_super) load_block(st, sgi, kin);
+    }
+  } else if (warp == 8) {
+    // ===================== B loader: this CTA's half of every weight plane =====================
+    if (lane == 0) {
+      int kcount = 0;
+      for (int st = cluster_id; st < num_super; st += nclusters) {
+        for (int kb = 0; kb < a.nkb; ++kb, ++kcount) {
+          const int s = kcount % NSTAGE;
+          const uint32_t ph = (kcount / NSTAGE) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, 2 * C::HALF_BYTES);
+          const unsigned char* src = a.wimg + (size_t)kb * (2 * C::PLANE_BYTES) + (size_t)rank * C::HALF_BYTES;
+          const uint32_t dst = base + s * STAGE_BYTES + 2 * A_TILE_BYTES;
+          bulk_g2s(dst, src, C::HALF_BYTES, bar_full + 8 * s);
+          bulk_g2s(dst + C::HALF_BYTES, src + C::PLANE_BYTES, C::HALF_BYTES, bar_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      if (rank == 0) {
+        // ===================== MMA issuer (leader CTA) =====================
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+        int kcount = 0, it = 0;
+        for (int st = cluster_id; st < num_super; st += nclusters, ++it) {
+          const int ab = it & 1;
+          const uint32_t aph = (it >> 1) & 1;
+          mbar_wait(bar_tempty + 8 * ab, aph ^ 1);   // both epilogues have drained this accumulator
+          mbar_wait(bar_ptempty + 8 * ab, aph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + ab * N;
+          for (int kb = 0; kb < a.nkb; ++kb, ++kcount) {
+            const int s = kcount % NSTAGE;
+            const uint32_t ph = (kcount / NSTAGE) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            mbar_wait(bar_pfull + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t sa = base + s * STAGE_BYTES;
+            const uint64_t d_ahi = umma_desc(sa), d_alo = umma_desc(sa + A_TILE_BYTES);
+            const uint64_t d_bhi = umma_desc(sa + 2 * A_TILE_BYTES),
+                           d_blo = umma_desc(sa + 2 * A_TILE_BYTES + C::HALF_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+              umma_f16_2cta(d_tmem, d_ahi + adv, d_bhi + adv, idesc, (kb | ks) ? 1u : 0u);
+              umma_f16_2cta(d_tmem, d_alo + adv, d_bhi + adv, idesc, 1u);
+              umma_f16_2cta(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+            }
+            umma_commit_2cta(bar_empty + 8 * s);
+          }
+          umma_commit_2cta(bar_tfull + 8 * ab);
+        }
+      } else {
+        // ===================== relay (peer CTA): forward "stage full" to the leader =====================
+        int kcount = 0;
+        for (int st = cluster_id; st < num_super; st += nclusters) {
+          for (int kb = 0; kb < a.nkb; ++kb, ++kcount) {
+            const int s = kcount % NSTAGE;
+            const uint32_t ph = (kcount / NSTAGE) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            mbar_arrive_remote(bar_pfull + 8 * s, 0);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    float* stage = s_stage + q * (32 * EPI_LD);
+    int it = 0;
+    for (int st = cluster_id; st < num_super; st += nclusters, ++it) {
+      const int ab = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * ab, aph);
+      tc_fence_after();
+      const int64_t mbase = (int64_t)st * (2 * BM) + rank * BM + q * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          o.x = __uint_as_float(v[j + 0]) + s_bias[c0 + j + 0];
+          o.y = __uint_as_float(v[j + 1]) + s_bias[c0 + j + 1];
+          o.z = __uint_as_float(v[j + 2]) + s_bias[c0 + j + 2];
+          o.w = __uint_as_float(v[j + 3]) + s_bias[c0 + j + 3];
+          if (a.g.relu) {
+            o.x = fmaxf(o.x, 0.f);
+            o.y = fmaxf(o.y, 0.f);
+            o.z = fmaxf(o.z, 0.f);
+            o.w = fmaxf(o.w, 0.f);
+          }
+          *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int row = rr + (lane >> 3);
+          const int64_t m = mbase + row;
+          const float4 o = *reinterpret_cast<const float4*>(stage + row * EPI_LD + (lane & 7) * 4);
+          if (m < M) *reinterpret_cast<float4*>(a.g.C + m * a.g.ldc + c0 + (lane & 7) * 4) = o;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      if (rank == 0)
+        mbar_arrive(bar_tempty + 8 * ab);
+      else
+        mbar_arrive_remote(bar_ptempty + 8 * ab, 0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be reading this CTA's smem / signalling its barriers
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
 template <int N>
 static size_t smem_bytes() {
   constexpr int NSTAGE = N == 256 ? 2 : 3;
@@ -396,7 +692,32 @@ int launch_gemm_tc(const GemmArgs& a, const void* w_image, cudaStream_t st) {
   t.nkb = tc_image_kblocks(a);
   t.num_tiles = (int)cdiv(a.M, tc::BM);
   const int grid = t.num_tiles < num_sms ? t.num_tiles : num_sms;
-  if (a.N == 256) {
+  static int use_1cta = -1;
+  if (use_1cta < 0) {
+    const char* e = getenv("TH_GEMM_1CTA");
+    use_1cta = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!use_1cta) {
+    const int num_super = (t.num_tiles + 1) / 2;
+    const int nclusters = num_super < num_sms / 2 ? num_super : num_sms / 2;
+    if (a.N == 256) {
+      static bool cfg = false;
+      if (!cfg) {
+        TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tc::Cfg2<256>::SMEM));
+        cfg = true;
+      }
+      tc::k_gemm_tc2<256><<<2 * nclusters, tc::NUM_THREADS, tc::Cfg2<256>::SMEM, st>>>(t);
+    } else {
+      static bool cfg = false;
+      if (!cfg) {
+        TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tc::Cfg2<128>::SMEM));
+        cfg = true;
+      }
+      tc::k_gemm_tc2<128><<<2 * nclusters, tc::NUM_THREADS, tc::Cfg2<128>::SMEM, st>>>(t);
+    }
+  } else if (a.N == 256) {
     static bool cfg = false;
     const size_t smem = tc::smem_bytes<256>();
     if (!cfg) {
