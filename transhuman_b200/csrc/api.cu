@@ -2,6 +2,7 @@
 // weight packing, workspace planning and the kernel schedule of the fused path.
 #include <cuda_fp16.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -53,7 +54,18 @@ void prof_end(int cat, cudaStream_t st) {
   ++g_prof.launches[cat];
 }
 
-constexpr int64_t CHUNK_PTS = 128 * 1024;  // points per MLP chunk (workspace ~ 26 KiB / point)
+// points per MLP chunk (workspace ~ 26 KiB / point: 7 GB at the default; fewer, larger launches
+// measured faster than L2-sized chunks); TH_CHUNK_PTS overrides (multiple of 256)
+static int64_t chunk_pts() {
+  static int64_t v = 0;
+  if (!v) {
+    const char* e = getenv("TH_CHUNK_PTS");
+    v = e ? atoll(e) : 256 * 1024;
+    if (v < 256) v = 256;
+    v = v / 256 * 256;
+  }
+  return v;
+}
 
 // ---------------------------------------------------------------------------
 // weight packing (host)
@@ -279,7 +291,7 @@ static size_t ws_plan(int64_t n_points, int V, int n_verts, unsigned char* base,
   unsigned char* mask = take((size_t)np);
   unsigned char* ids = take((size_t)np * 4);
   unsigned char* raw = take((size_t)np * 16);
-  int64_t cp = np < CHUNK_PTS ? np : CHUNK_PTS;
+  int64_t cp = np < chunk_pts() ? np : chunk_pts();
   unsigned char* chunk = take((size_t)cp * mlp_buffer_floats_per_point(V) * 4);
   if (ws) {
     ws->grid = grid;
