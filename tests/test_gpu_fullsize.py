@@ -42,8 +42,9 @@ def test_config_512_sampled_parity(n_class, S):
     got = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_MASKED, want_mask=True)
     n_in, n_rays, n_eval = got["counters"]
     assert 0.005 < n_in / (N * S) < 0.2 and n_eval == n_in
-    alive = torch.nonzero(got["pts_mask"].any(dim=1))[:, 0].cpu()
-    dead = torch.nonzero(~got["pts_mask"].any(dim=1))[:, 0]
+    pm = got["pts_mask"].bool()                      # uint8.any() stays uint8 and ~ would be a bitwise not
+    alive = torch.nonzero(pm.any(dim=1))[:, 0].cpu()
+    dead = torch.nonzero(~pm.any(dim=1))[:, 0]
     assert len(alive) == n_rays
     assert torch.all(got["rgb_map"][dead] == 0) and torch.all(got["acc_map"][dead] == 0)
     g = torch.Generator().manual_seed(0)
@@ -89,12 +90,13 @@ def test_config_grid_6000_tokens_density():
     fr, tf, tokens, frame, rays = _frame(6000, 64, 64, seed=1, shift=0.0)
     grid = torch.from_numpy(synth.make_grid_points(fr, 96).reshape(-1, 3))
     alpha, mask = ops.query_density(frame, grid.to(DEV))
+    mask = mask.bool()
     assert 0.01 < mask.float().mean().item() < 0.6
-    assert torch.all(alpha[mask == 0] == 0)
+    assert torch.all(alpha[~mask] == 0)
     inside = torch.nonzero(mask.cpu())[:, 0]
     g = torch.Generator().manual_seed(3)
     sel = inside[torch.randperm(len(inside), generator=g)[:512]]
-    far = torch.nonzero(~mask.cpu().bool())[:, 0][:512]
+    far = torch.nonzero(~mask.cpu())[:, 0][:512]
     pts = torch.cat([grid[sel], grid[far]])
     walpha, wmask = orc.query_density(tf, pts, tokens=tokens)
     assert torch.equal(wmask, torch.cat([torch.ones(512, dtype=torch.bool), torch.zeros(512, dtype=torch.bool)]))
