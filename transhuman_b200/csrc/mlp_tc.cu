@@ -71,13 +71,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-// shared -> global bulk store (TMA engine, async proxy); completion tracked per thread by bulk groups
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -341,11 +334,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
           }
           *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = o;
         }
-        // each lane stores its own row's 128 bytes with one bulk copy (shared -> global)
-        fence_proxy_async();
-        if (mbase + lane < M) bulk_s2g(a.g.C + (mbase + lane) * a.g.ldc + c0, smem_u32(stage + lane * EPI_LD), 128);
-        bulk_commit();
-        bulk_wait_read0();  // the staging row may be overwritten once the copy has read it
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int row = rr + (lane >> 3);
+          const int64_t m = mbase + row;
+          const float4 o = *reinterpret_cast<const float4*>(stage + row * EPI_LD + (lane & 7) * 4);
+          if (m < M) *reinterpret_cast<float4*>(a.g.C + m * a.g.ldc + c0 + (lane & 7) * 4) = o;
+        }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * ab);
@@ -628,11 +625,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
           }
           *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = o;
         }
-        // each lane stores its own row's 128 bytes with one bulk copy (shared -> global)
-        fence_proxy_async();
-        if (mbase + lane < M) bulk_s2g(a.g.C + (mbase + lane) * a.g.ldc + c0, smem_u32(stage + lane * EPI_LD), 128);
-        bulk_commit();
-        bulk_wait_read0();  // the staging row may be overwritten once the copy has read it
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int row = rr + (lane >> 3);
+          const int64_t m = mbase + row;
+          const float4 o = *reinterpret_cast<const float4*>(stage + row * EPI_LD + (lane & 7) * 4);
+          if (m < M) *reinterpret_cast<float4*>(a.g.C + m * a.g.ldc + c0 + (lane & 7) * 4) = o;
+        }
+        __syncwarp();
       }
       tc_fence_before();
       if (rank == 0)
