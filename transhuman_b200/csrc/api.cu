@@ -292,7 +292,7 @@ static size_t ws_plan(int64_t n_points, int V, int n_verts, unsigned char* base,
   unsigned char* ids = take((size_t)np * 4);
   unsigned char* raw = take((size_t)np * 16);
   int64_t cp = np < chunk_pts() ? np : chunk_pts();
-  unsigned char* chunk = take((size_t)cp * mlp_buffer_floats_per_point(V) * 4);
+  unsigned char* chunk = take((size_t)pad_points(cp) * mlp_buffer_floats_per_point(V) * 4 + 1024);
   if (ws) {
     ws->grid = grid;
     ws->counters = reinterpret_cast<unsigned long long*>(counters);
@@ -380,13 +380,14 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
     int64_t P = n_list - first < ws.chunk_pts ? n_list - first : ws.chunk_pts;
     MlpBuffers b;
     mlp_carve(ws.chunk, P, V, &b);
+    const int64_t Pp = pad_points(P);
     FeatOut fo{};
     fo.rep = b.rep;
-    fo.rep_sv = P * REP_LD;
+    fo.rep_sv = Pp * REP_LD;
     fo.rep_sp = REP_LD;
     fo.rep_sc = 1;
     fo.pix = b.pix;
-    fo.pix_sv = P * PIX_LD;
+    fo.pix_sv = Pp * PIX_LD;
     fo.pix_sp = PIX_LD;
     fo.pix_sc = 1;
     fo.pix_mean = alpha_only ? nullptr : b.pix_mean;
@@ -632,7 +633,7 @@ int th_mlp_raw(const ThFrame* f, const float* human_rep, const float* pixel_feat
   TH_CHECK_ARG(f->n_views >= 1 && f->n_views <= TH_MAX_VIEWS, "n_views out of range");
   if (n_points <= 0) return TH_OK;
   const int V = f->n_views;
-  size_t need = align_up((size_t)n_points * mlp_buffer_floats_per_point(V) * 4, 256);
+  size_t need = align_up((size_t)pad_points(n_points) * mlp_buffer_floats_per_point(V) * 4 + 1024, 256);
   if (!workspace || workspace_bytes < need) {
     set_error("th_mlp_raw: workspace %zu < %zu bytes", workspace_bytes, need);
     return TH_EWORKSPACE;

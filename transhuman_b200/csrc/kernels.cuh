@@ -95,7 +95,10 @@ struct PackedHeader {
 constexpr uint32_t PACK_MAGIC = 0x31574854u;
 
 // ---- per-point network on GEMM-layout activations (mlp_simt.cu / mlp_tc.cu) ----
-// Activation buffers of one chunk (all fp32, row-major, rows = view-major (v*P + p)).
+// Activation buffers of one chunk (fp32, row-major, rows = view-major (v*Pp + p)
+// with Pp = P rounded up to 256 so that every view starts on a 2-CTA super-tile;
+// on the tensor-core path S, NET, N1, INTER, F, G hold tile images instead).
+inline int64_t pad_points(int64_t P) { return (P + 255) / 256 * 256; }
 struct MlpBuffers {
   float *rep;      // (V*P, 256)
   float *pix;      // (V*P, 384)
@@ -125,14 +128,21 @@ struct MlpRun {
   int zero_rgb_if_transparent;
   int use_tensor_cores;
 };
+// Pp = pad_points(P): view stride of every buffer in `b`.
 int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& hdr_host, cudaStream_t st);
 
 // mlp_simt.cu: C[M,N] = act(sum_seg A_seg[M,K_seg] W[:, koff:koff+K_seg]^T + bias)
+// One K-segment of the A operand.  Either fp32 rows (`ptr`, `ld`), converted to
+// fp16 hi/lo on the fly, or -- tensor-core path only -- an activation already in
+// operand TILE-IMAGE format (`img`): per 128-row tile and 64-wide k-block a
+// 32 KB block [hi 128x128B | lo 128x128B], K-major, 128-byte swizzled, tiles
+// row-major over (row tile, k-block); `K` must then be a multiple of 64.
 struct GemmSeg {
   const float* ptr;
   int ld;       // row stride in floats
   int K;        // multiple of 16
   int64_t row_mod;  // rows wrap modulo this (0 = no wrap)
+  const unsigned char* img;
 };
 struct GemmArgs {
   GemmSeg seg[TH_MAX_VIEWS + 1];
@@ -140,8 +150,9 @@ struct GemmArgs {
   const float* W;  // (N, Ktot) row-major
   int ldw;
   const float* bias;
-  float* C;
+  float* C;            // fp32 output (M, ldc) or nullptr
   int ldc;
+  unsigned char* C_img;  // tile-image output (tensor-core path) or nullptr
   int64_t M;
   int N;  // multiple of 128
   int relu;

@@ -17,6 +17,8 @@
 //   G   = relu([F | viewdir] view_fc^T)                  (V*P,128) <- K 288
 //   T   = relu([G_0|..|G_{V-1}| mean_v pix] [fc_4/V ...| fc_4 rgb_res_1]^T)
 //   rgb = T rgb_fc^T
+#include <initializer_list>
+
 #include "kernels.cuh"
 
 namespace th {
@@ -148,7 +150,7 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_attn_mix(const float* __restrict__ kp, const float* __restrict__ ks,
                                                   const float* __restrict__ x, float* __restrict__ xt, int64_t P,
-                                                  int V) {
+                                                  int64_t Pp, int V) {
   const int lane = threadIdx.x & 31;
   const int64_t p = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (p >= P) return;
@@ -156,8 +158,8 @@ __global__ void __launch_bounds__(256) k_attn_mix(const float* __restrict__ kp, 
 #pragma unroll
   for (int v = 0; v < TH_MAX_VIEWS; ++v)
     if (v < V) {
-      kpv[v] = *reinterpret_cast<const float4*>(kp + (v * P + p) * 128 + lane * 4);
-      ksv[v] = *reinterpret_cast<const float4*>(ks + (v * P + p) * 128 + lane * 4);
+      kpv[v] = *reinterpret_cast<const float4*>(kp + (v * Pp + p) * 128 + lane * 4);
+      ksv[v] = *reinterpret_cast<const float4*>(ks + (v * Pp + p) * 128 + lane * 4);
     }
   float A[TH_MAX_VIEWS][TH_MAX_VIEWS];
 #pragma unroll
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(256) k_attn_mix(const float* __restrict__ kp, 
     float4 xv[TH_MAX_VIEWS];
 #pragma unroll
     for (int i = 0; i < TH_MAX_VIEWS; ++i)
-      if (i < V) xv[i] = *reinterpret_cast<const float4*>(x + (i * P + p) * 256 + c);
+      if (i < V) xv[i] = *reinterpret_cast<const float4*>(x + (i * Pp + p) * 256 + c);
 #pragma unroll
     for (int j = 0; j < TH_MAX_VIEWS; ++j)
       if (j < V) {
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(256) k_attn_mix(const float* __restrict__ kp, 
             o.z = fmaf(A[i][j], xv[i].z, o.z);
             o.w = fmaf(A[i][j], xv[i].w, o.w);
           }
-        *reinterpret_cast<float4*>(xt + (j * P + p) * 256 + c) = o;
+        *reinterpret_cast<float4*>(xt + (j * Pp + p) * 256 + c) = o;
       }
   }
 }
@@ -266,8 +268,9 @@ __global__ void __launch_bounds__(256) k_rgb_head(const float* __restrict__ t, c
 // staged a9/a10 input packing: reference layouts (V,255,P), (V,384,P), (P,27)
 // -> GEMM layout rows.
 // ---------------------------------------------------------------------------
-__global__ void k_pack_cmajor(const float* __restrict__ src, int C, int64_t P, float* __restrict__ dst, int ld) {
-  // src (V, C, P) -> dst (V*P, ld), zero padded; 32x32 tile transpose
+__global__ void k_pack_cmajor(const float* __restrict__ src, int C, int64_t P, int64_t Pp, float* __restrict__ dst,
+                              int ld) {
+  // src (V, C, P) -> dst (V*Pp, ld), zero padded; 32x32 tile transpose
   __shared__ float tile[32][33];
   const int64_t v = blockIdx.z;
   const int64_t p0 = blockIdx.x * 32LL;
@@ -281,12 +284,12 @@ __global__ void k_pack_cmajor(const float* __restrict__ src, int C, int64_t P, f
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int64_t p = p0 + i;
     int c = c0 + threadIdx.x;
-    if (p < P && c < ld) dst[(v * P + p) * ld + c] = tile[threadIdx.x][i];
+    if (p < P && c < ld) dst[(v * Pp + p) * ld + c] = tile[threadIdx.x][i];
   }
 }
 
-__global__ void k_pack_misc(const float* __restrict__ viewdir, const float* __restrict__ pix, int64_t P, int V,
-                            float* __restrict__ vd, float* __restrict__ pix_mean) {
+__global__ void k_pack_misc(const float* __restrict__ viewdir, const float* __restrict__ pix, int64_t P, int64_t Pp,
+                            int V, float* __restrict__ vd, float* __restrict__ pix_mean) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < P * VD_LD) {
     int64_t p = i / VD_LD;
@@ -295,7 +298,7 @@ __global__ void k_pack_misc(const float* __restrict__ viewdir, const float* __re
   }
   if (i < P * PIX_LD) {
     float s = 0.f;
-    for (int v = 0; v < V; ++v) s += pix[(int64_t)v * P * PIX_LD + i];
+    for (int v = 0; v < V; ++v) s += pix[(int64_t)v * Pp * PIX_LD + i];
     pix_mean[i] = __fdiv_rn(s, (float)V);
   }
 }
@@ -304,11 +307,14 @@ int launch_pack_inputs(const float* human_rep, const float* pixel_feat, const fl
                        const MlpBuffers& b, cudaStream_t st) {
   if (P <= 0) return TH_OK;
   dim3 block(32, 8);
-  k_pack_cmajor<<<dim3((unsigned)cdiv(P, 32), REP_LD / 32, V), block, 0, st>>>(human_rep, TH_C_REP, P, b.rep, REP_LD);
+  const int64_t Pp = pad_points(P);
+  k_pack_cmajor<<<dim3((unsigned)cdiv(P, 32), REP_LD / 32, V), block, 0, st>>>(human_rep, TH_C_REP, P, Pp, b.rep,
+                                                                             REP_LD);
   TH_LAUNCHED();
-  k_pack_cmajor<<<dim3((unsigned)cdiv(P, 32), PIX_LD / 32, V), block, 0, st>>>(pixel_feat, TH_C_PIX, P, b.pix, PIX_LD);
+  k_pack_cmajor<<<dim3((unsigned)cdiv(P, 32), PIX_LD / 32, V), block, 0, st>>>(pixel_feat, TH_C_PIX, P, Pp, b.pix,
+                                                                             PIX_LD);
   TH_LAUNCHED();
-  k_pack_misc<<<(unsigned)cdiv(P * PIX_LD, 256), 256, 0, st>>>(viewdir, b.pix, P, V, b.vd, b.pix_mean);
+  k_pack_misc<<<(unsigned)cdiv(P * PIX_LD, 256), 256, 0, st>>>(viewdir, b.pix, P, Pp, V, b.vd, b.pix_mean);
   TH_LAUNCHED();
   return TH_OK;
 }
@@ -321,15 +327,14 @@ size_t mlp_buffer_floats_per_point(int V) {
   return (size_t)V * (REP_LD + PIX_LD + 256 * 4 + 128 * 2) + PIX_LD + VD_LD + 256 + 128 + 4;
 }
 
-struct MlpScratch {
-  float *o, *t, *alpha;
-};
-
+// All buffers are sized and strided for Pp = pad_points(P) rows per view.
 void mlp_carve(float* base, int64_t P, int V, MlpBuffers* b) {
-  float* p = base;
+  const int64_t Pp = pad_points(P);
+  // tile images need 1 KB alignment; every buffer size below is a multiple of 1 KB because Pp % 256 == 0
+  float* p = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(base) + 1023) & ~uintptr_t(1023));
   auto take = [&](size_t per_point) {
     float* r = p;
-    p += (size_t)P * per_point;
+    p += (size_t)Pp * per_point;
     return r;
   };
   b->rep = take((size_t)V * REP_LD);
@@ -347,143 +352,215 @@ void mlp_carve(float* base, int64_t P, int V, MlpBuffers* b) {
 
 static const float* wf(const MlpRun& run, uint64_t off) { return reinterpret_cast<const float*>(run.weights + off); }
 
-int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& h, cudaStream_t st) {
-  const int64_t P = run.P;
-  const int V = run.V;
-  if (P <= 0) return TH_OK;
-  const int64_t R = (int64_t)V * P;
-  float* o = b.vd + (size_t)P * VD_LD;
-  float* t = o + (size_t)P * 256;
-  float* alpha = t + (size_t)P * 128;
+static GemmSeg seg_f32(const float* ptr, int ld, int K, int64_t row_mod = 0) {
+  GemmSeg g{};
+  g.ptr = ptr;
+  g.ld = ld;
+  g.K = K;
+  g.row_mod = row_mod;
+  return g;
+}
+static GemmSeg seg_img(const float* buf, int K) {
+  GemmSeg g{};
+  g.K = K;
+  g.img = reinterpret_cast<const unsigned char*>(buf);
+  return g;
+}
 
-  auto gemm = [&](GemmArgs& g, uint64_t w_hi_lo) -> int {
-    if (run.use_tensor_cores) return launch_gemm_tc(g, run.weights + w_hi_lo, st);
-    return launch_gemm_simt(g, st);
-  };
-  auto one = [&](const float* A, int lda, int K, const float* W, const float* bias, float* C, int N, int64_t M,
-                 int relu, uint64_t hl) -> int {
+// Heads shared by both schedules.
+static int run_heads(const MlpRun& run, const float* o, const float* t, float* alpha, const PackedHeader& h,
+                     bool rgb, cudaStream_t st) {
+  const int64_t P = run.P;
+  if (!rgb) {
+    {
+      ProfScope prof_(PROF_POINTWISE, st);
+      k_alpha_head<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(o, wf(run, h.afc_w), wf(run, h.afc_b), alpha, P);
+    }
+    TH_LAUNCHED();
+    if (run.alpha_only) {
+      ProfScope prof_(PROF_POINTWISE, st);
+      k_write_alpha<<<(unsigned)cdiv(P, 256), 256, 0, st>>>(alpha, run.dst_ids, run.first, P, run.alpha_out, run.raw);
+      TH_LAUNCHED();
+    }
+    return TH_OK;
+  }
+  {
+    ProfScope prof_(PROF_POINTWISE, st);
+    k_rgb_head<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(t, wf(run, h.rgb_w), wf(run, h.rgb_b), alpha, run.dst_ids,
+                                                     run.first, P, run.zero_rgb_if_transparent, run.raw);
+  }
+  TH_LAUNCHED();
+  return TH_OK;
+}
+
+// fp32 schedule (CUDA-core GEMM): every activation is an fp32 row-major buffer.
+static int mlp_forward_simt(const MlpRun& run, const MlpBuffers& b, const PackedHeader& h, cudaStream_t st) {
+  const int64_t P = run.P, Pp = pad_points(P);
+  const int V = run.V;
+  const int64_t R = (int64_t)V * Pp;
+  float* o = b.vd + (size_t)Pp * VD_LD;
+  float* t = o + (size_t)Pp * 256;
+  float* alpha = t + (size_t)Pp * 128;
+  auto gemm = [&](std::initializer_list<GemmSeg> segs, const float* W, int ldw, const float* bias, float* C, int N,
+                  int64_t M, int relu) -> int {
     GemmArgs g{};
-    g.seg[0] = {A, lda, K, 0};
-    g.nseg = 1;
+    for (const GemmSeg& sg : segs) g.seg[g.nseg++] = sg;
     g.W = W;
-    g.ldw = K;
+    g.ldw = ldw;
     g.bias = bias;
     g.C = C;
     g.ldc = N;
     g.M = M;
     g.N = N;
     g.relu = relu;
-    return gemm(g, hl);
+    return launch_gemm_simt(g, st);
   };
   int rc;
-  // S, X
-  if ((rc = one(b.rep, REP_LD, 256, wf(run, h.fc0_w), wf(run, h.fc0_b), b.s, 256, R, 1, h.h_fc0))) return rc;
-  if ((rc = one(b.pix, PIX_LD, 384, wf(run, h.ar0_w), wf(run, h.ar0_b), b.x, 256, R, 1, h.h_ar0))) return rc;
-  // keys
-  if ((rc = one(b.x, 256, 256, wf(run, h.k0_w), wf(run, h.k0_b), b.kp, 128, R, 0, h.h_k0))) return rc;
-  if ((rc = one(b.s, 256, 256, wf(run, h.k1_w), wf(run, h.k1_b), b.ks, 128, R, 0, h.h_k1))) return rc;
+  if ((rc = gemm({seg_f32(b.rep, REP_LD, 256)}, wf(run, h.fc0_w), 256, wf(run, h.fc0_b), b.s, 256, R, 1))) return rc;
+  if ((rc = gemm({seg_f32(b.pix, PIX_LD, 384)}, wf(run, h.ar0_w), 384, wf(run, h.ar0_b), b.x, 256, R, 1))) return rc;
+  if ((rc = gemm({seg_f32(b.x, 256, 256)}, wf(run, h.k0_w), 256, wf(run, h.k0_b), b.kp, 128, R, 0))) return rc;
+  if ((rc = gemm({seg_f32(b.s, 256, 256)}, wf(run, h.k1_w), 256, wf(run, h.k1_b), b.ks, 128, R, 0))) return rc;
   {
     ProfScope prof_(PROF_POINTWISE, st);
-    k_attn_mix<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(b.kp, b.ks, b.x, b.xt, P, V);
+    k_attn_mix<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(b.kp, b.ks, b.x, b.xt, P, Pp, V);
   }
   TH_LAUNCHED();
-  {  // NET = [S | XT] W_v^T
-    GemmArgs g{};
-    g.seg[0] = {b.s, 256, 256, 0};
-    g.seg[1] = {b.xt, 256, 256, 0};
-    g.nseg = 2;
-    g.W = wf(run, h.v_w);
-    g.ldw = 512;
-    g.bias = wf(run, h.v_b);
-    g.C = b.net;
-    g.ldc = 256;
-    g.M = R;
-    g.N = 256;
-    g.relu = 0;
-    if ((rc = gemm(g, h.h_v))) return rc;
-  }
+  if ((rc = gemm({seg_f32(b.s, 256, 256), seg_f32(b.xt, 256, 256)}, wf(run, h.v_w), 512, wf(run, h.v_b), b.net, 256, R,
+                 0)))
+    return rc;
   float* n1 = b.x;      // X is dead after the mix
   float* inter = b.xt;  // XT is dead after NET
-  if ((rc = one(b.net, 256, 256, wf(run, h.fc1_w), wf(run, h.fc1_b), n1, 256, R, 1, h.h_fc1))) return rc;
-  if ((rc = one(n1, 256, 256, wf(run, h.fc2_w), wf(run, h.fc2_b), inter, 256, R, 1, h.h_fc2))) return rc;
+  if ((rc = gemm({seg_f32(b.net, 256, 256)}, wf(run, h.fc1_w), 256, wf(run, h.fc1_b), n1, 256, R, 1))) return rc;
+  if ((rc = gemm({seg_f32(n1, 256, 256)}, wf(run, h.fc2_w), 256, wf(run, h.fc2_b), inter, 256, R, 1))) return rc;
   {  // O = relu(mean_v(INTER) fc_3^T): mean folded into K
     GemmArgs g{};
-    for (int v = 0; v < V; ++v) g.seg[v] = {inter + (size_t)v * P * 256, 256, 256, 0};
+    for (int v = 0; v < V; ++v) g.seg[v] = seg_f32(inter + (size_t)v * Pp * 256, 256, 256);
     g.nseg = V;
     g.W = wf(run, h.fc3m_w);
     g.ldw = 256 * V;
     g.bias = wf(run, h.fc3m_b);
     g.C = o;
     g.ldc = 256;
-    g.M = P;
+    g.M = Pp;
     g.N = 256;
     g.relu = 1;
-    if ((rc = gemm(g, h.h_fc3m))) return rc;
+    if ((rc = launch_gemm_simt(g, st))) return rc;
   }
-  {
-    ProfScope prof_(PROF_POINTWISE, st);
-    k_alpha_head<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(o, wf(run, h.afc_w), wf(run, h.afc_b), alpha, P);
-  }
-  TH_LAUNCHED();
-  if (run.alpha_only) {
-    k_write_alpha<<<(unsigned)cdiv(P, 256), 256, 0, st>>>(alpha, run.dst_ids, run.first, P, run.alpha_out, run.raw);
-    TH_LAUNCHED();
-    return TH_OK;
-  }
-  float* f = b.s;   // S is dead after NET
+  if ((rc = run_heads(run, o, nullptr, alpha, h, false, st))) return rc;
+  if (run.alpha_only) return TH_OK;
+  float* f = b.s;      // S is dead after NET
   float* gbuf = b.kp;  // keys are dead after the mix
-  {  // F = [INTER | pix] W_f^T
-    GemmArgs g{};
-    g.seg[0] = {inter, 256, 256, 0};
-    g.seg[1] = {b.pix, PIX_LD, 384, 0};
-    g.nseg = 2;
-    g.W = wf(run, h.f_w);
-    g.ldw = 640;
-    g.bias = wf(run, h.f_b);
-    g.C = f;
-    g.ldc = 256;
-    g.M = R;
-    g.N = 256;
-    g.relu = 0;
-    if ((rc = gemm(g, h.h_f))) return rc;
-  }
-  {  // G = relu([F | viewdir] view_fc^T)
-    GemmArgs g{};
-    g.seg[0] = {f, 256, 256, 0};
-    g.seg[1] = {b.vd, VD_LD, VD_LD, P};
-    g.nseg = 2;
-    g.W = wf(run, h.view_w);
-    g.ldw = 320;
-    g.bias = wf(run, h.view_b);
-    g.C = gbuf;
-    g.ldc = 128;
-    g.M = R;
-    g.N = 128;
-    g.relu = 1;
-    if ((rc = gemm(g, h.h_view))) return rc;
-  }
+  if ((rc = gemm({seg_f32(inter, 256, 256), seg_f32(b.pix, PIX_LD, 384)}, wf(run, h.f_w), 640, wf(run, h.f_b), f, 256,
+                 R, 0)))
+    return rc;
+  if ((rc = gemm({seg_f32(f, 256, 256), seg_f32(b.vd, VD_LD, VD_LD, Pp)}, wf(run, h.view_w), 320, wf(run, h.view_b),
+                 gbuf, 128, R, 1)))
+    return rc;
   {  // T = relu([G_0|..|G_{V-1}| mean pix] W_t^T)
     GemmArgs g{};
-    for (int v = 0; v < V; ++v) g.seg[v] = {gbuf + (size_t)v * P * 128, 128, 128, 0};
-    g.seg[V] = {b.pix_mean, PIX_LD, 384, 0};
+    for (int v = 0; v < V; ++v) g.seg[v] = seg_f32(gbuf + (size_t)v * Pp * 128, 128, 128);
+    g.seg[V] = seg_f32(b.pix_mean, PIX_LD, 384);
     g.nseg = V + 1;
     g.W = wf(run, h.t_w);
     g.ldw = 128 * V + 384;
     g.bias = wf(run, h.t_b);
     g.C = t;
     g.ldc = 128;
-    g.M = P;
+    g.M = Pp;
     g.N = 128;
     g.relu = 1;
-    if ((rc = gemm(g, h.h_t))) return rc;
+    if ((rc = launch_gemm_simt(g, st))) return rc;
   }
+  return run_heads(run, o, t, alpha, h, true, st);
+}
+
+// Tensor-core schedule: the GEMM -> GEMM activations (S, NET, N1, INTER, F, G) are
+// written by the producing epilogue as fp16 hi/lo tile images and consumed by the
+// next layer with one 32 KB bulk copy per k-block; inputs produced by other
+// kernels (rep, pix, X for the attention, XT, viewdir, mean pix) and the outputs
+// read by the heads / attention (X, KP, KS, O, T) stay fp32 rows.
+static int mlp_forward_tc(const MlpRun& run, const MlpBuffers& b, const PackedHeader& h, cudaStream_t st) {
+  const int64_t P = run.P, Pp = pad_points(P);
+  const int V = run.V;
+  const int64_t R = (int64_t)V * Pp;
+  float* o = b.vd + (size_t)Pp * VD_LD;
+  float* t = o + (size_t)Pp * 256;
+  float* alpha = t + (size_t)Pp * 128;
+  auto gemm = [&](std::initializer_list<GemmSeg> segs, uint64_t w_img, const float* bias, float* C, bool c_is_img, int N,
+                  int64_t M, int relu) -> int {
+    GemmArgs g{};
+    for (const GemmSeg& sg : segs) g.seg[g.nseg++] = sg;
+    g.bias = bias;
+    if (c_is_img)
+      g.C_img = reinterpret_cast<unsigned char*>(C);
+    else
+      g.C = C;
+    g.ldc = N;
+    g.M = M;
+    g.N = N;
+    g.relu = relu;
+    return launch_gemm_tc(g, run.weights + w_img, st);
+  };
+  // image of a (V*Pp, C) activation: the slice of view v starts (v*Pp/128) row tiles in
+  auto view_img = [&](const float* buf, int C, int v) {
+    return seg_img(buf + (size_t)v * Pp * C, C);
+  };
+  int rc;
+  if ((rc = gemm({seg_f32(b.rep, REP_LD, 256)}, h.h_fc0, wf(run, h.fc0_b), b.s, true, 256, R, 1))) return rc;
+  if ((rc = gemm({seg_f32(b.pix, PIX_LD, 384)}, h.h_ar0, wf(run, h.ar0_b), b.x, false, 256, R, 1))) return rc;
+  if ((rc = gemm({seg_f32(b.x, 256, 256)}, h.h_k0, wf(run, h.k0_b), b.kp, false, 128, R, 0))) return rc;
+  if ((rc = gemm({seg_img(b.s, 256)}, h.h_k1, wf(run, h.k1_b), b.ks, false, 128, R, 0))) return rc;
   {
     ProfScope prof_(PROF_POINTWISE, st);
-    k_rgb_head<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(t, wf(run, h.rgb_w), wf(run, h.rgb_b), alpha, run.dst_ids,
-                                                   run.first, P, run.zero_rgb_if_transparent, run.raw);
+    k_attn_mix<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(b.kp, b.ks, b.x, b.xt, P, Pp, V);
   }
   TH_LAUNCHED();
-  return TH_OK;
+  if ((rc = gemm({seg_img(b.s, 256), seg_f32(b.xt, 256, 256)}, h.h_v, wf(run, h.v_b), b.net, true, 256, R, 0)))
+    return rc;
+  float* n1 = b.x;      // X is dead after the mix
+  float* inter = b.xt;  // XT is dead after NET
+  if ((rc = gemm({seg_img(b.net, 256)}, h.h_fc1, wf(run, h.fc1_b), n1, true, 256, R, 1))) return rc;
+  if ((rc = gemm({seg_img(n1, 256)}, h.h_fc2, wf(run, h.fc2_b), inter, true, 256, R, 1))) return rc;
+  {
+    GemmArgs g{};
+    for (int v = 0; v < V; ++v) g.seg[v] = view_img(inter, 256, v);
+    g.nseg = V;
+    g.bias = wf(run, h.fc3m_b);
+    g.C = o;
+    g.ldc = 256;
+    g.M = Pp;
+    g.N = 256;
+    g.relu = 1;
+    if ((rc = launch_gemm_tc(g, run.weights + h.h_fc3m, st))) return rc;
+  }
+  if ((rc = run_heads(run, o, nullptr, alpha, h, false, st))) return rc;
+  if (run.alpha_only) return TH_OK;
+  float* f = b.s;      // S is dead after NET
+  float* gbuf = b.kp;  // keys are dead after the mix
+  if ((rc = gemm({seg_img(inter, 256), seg_f32(b.pix, PIX_LD, 384)}, h.h_f, wf(run, h.f_b), f, true, 256, R, 0)))
+    return rc;
+  if ((rc = gemm({seg_img(f, 256), seg_f32(b.vd, VD_LD, VD_LD, Pp)}, h.h_view, wf(run, h.view_b), gbuf, true, 128, R,
+                 1)))
+    return rc;
+  {
+    GemmArgs g{};
+    for (int v = 0; v < V; ++v) g.seg[v] = view_img(gbuf, 128, v);
+    g.seg[V] = seg_f32(b.pix_mean, PIX_LD, 384);
+    g.nseg = V + 1;
+    g.bias = wf(run, h.t_b);
+    g.C = t;
+    g.ldc = 128;
+    g.M = Pp;
+    g.N = 128;
+    g.relu = 1;
+    if ((rc = launch_gemm_tc(g, run.weights + h.h_t, st))) return rc;
+  }
+  return run_heads(run, o, t, alpha, h, true, st);
+}
+
+int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& h, cudaStream_t st) {
+  if (run.P <= 0) return TH_OK;
+  return run.use_tensor_cores ? mlp_forward_tc(run, b, h, st) : mlp_forward_simt(run, b, h, st);
 }
 
 }  // namespace th

@@ -9,17 +9,21 @@
 //     D += A_hi B_hi ;  D += A_lo B_hi ;  D += A_hi B_lo        (lo*lo ~ 2^-22 dropped)
 // Weights are split once on the host (th_pack_weights) and stored as ready-made
 // shared-memory tile images (128B-swizzled, K-major), so a k-block of B is one
-// cp.async.bulk; activations are split on the fly by the producer warps.
+// cp.async.bulk.  An A segment is either fp32 rows (split on the fly by the
+// producer warps) or an activation that a previous GEMM's epilogue already wrote
+// in the same tile-image format (one 32 KB cp.async.bulk per k-block, no LSU work).
 //
-// Persistent, warp-specialised CTA (one per SM), BM = 128 rows, BN = N (128 or
+// Persistent, warp-specialised 2-CTA cluster (cta_group::2) per TPC; each CTA owns
+// 128 rows of a 256-row super-tile and half of every weight tile; BN = N (128 or
 // 256: A is read once), BK = 64:
 //   warps 0-7   A producers: coalesced fp32 loads -> hi/lo fp16 -> swizzled smem
 //                            (two groups alternating k-blocks, register prefetched)
-//   warp  8     B loader:    cp.async.bulk of the packed weight tile images
-//   warp  9     MMA issuer:  one thread issues tcgen05.mma (kind::f16, M=128)
-//   warps 10-13 epilogue:    tcgen05.ld -> bias/ReLU -> smem staging -> full-line
-//                            stores; overlaps the next tile's mainloop through a
-//                            double-buffered accumulator
+//   warp  8     loader:      cp.async.bulk of weight tile images and image-format A
+//   warp  9     MMA issuer (leader CTA) / stage-full relay (peer CTA)
+//   warps 10-13 epilogue:    tcgen05.ld -> bias/ReLU -> fp32 rows (smem-staged
+//                            full-line stores) or hi/lo tile image (smem-staged 4 KB
+//                            bulk stores); overlaps the next tile's mainloop through
+//                            a double-buffered TMEM accumulator
 // Pipelines: smem full/empty mbarriers per stage, TMEM full/empty per buffer.
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -71,6 +75,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// shared -> global bulk store (async proxy); completion tracked per thread by bulk groups
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -133,233 +145,8 @@ struct TcArgs {
   int num_tiles;
 };
 
-template <int N>
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const TcArgs a) {
-  constexpr int B_TILE_BYTES = N * BK * 2;                      // one of hi / lo
-  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  constexpr int NSTAGE = N == 256 ? 2 : 3;
-  constexpr int TMEM_COLS = 2 * N;                              // double-buffered fp32 accumulator
-
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  // control block after the stages
-  const uint32_t ctrl = base + NSTAGE * STAGE_BYTES;
-  const uint32_t bar_full = ctrl, bar_empty = ctrl + 8 * NSTAGE, bar_tfull = ctrl + 16 * NSTAGE,
-                 bar_tempty = bar_tfull + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + NSTAGE * STAGE_BYTES + 16 * NSTAGE + 32);
-  float* s_bias = reinterpret_cast<float*>(base_ptr + NSTAGE * STAGE_BYTES + 16 * NSTAGE + 64);
-  float* s_stage = s_bias + N;  // 4 epilogue warps x 32 rows x EPI_LD floats
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(bar_full + 8 * s, 128 + 1);  // 128 A-producer threads + the B loader's expect_tx arrive
-      mbar_init(bar_empty + 8 * s, 1);       // tcgen05.commit
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_tfull + 8 * b, 1);       // tcgen05.commit
-      mbar_init(bar_tempty + 8 * b, 128);    // epilogue threads
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < N; i += NUM_THREADS) s_bias[i] = a.g.bias ? a.g.bias[i] : 0.f;
-  if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int64_t M = a.g.M;
-
-  if (warp < 8) {
-    // ===================== A producers =====================
-    // Two groups of 4 warps alternate k-blocks (group g takes k-blocks g, g+2, ...),
-    // each software pipelined: the global loads of a group's next k-block are issued
-    // right after the current one has been written to shared memory, so 2 x 32 KB of
-    // loads are in flight per SM while the producers wait for free stages.
-    // Lane mapping per pass (16 rows x 64 columns per warp): row = lane>>1, 8 float4
-    // loads at columns 8*i + 4*(lane&1): 16 full 32-byte sectors per load instruction,
-    // and the 8-byte swizzled stores of a half-warp hit 8 distinct 16-byte chunks.
-    const int grp = warp >> 2, wq = warp & 3;
-    float4 v[2][8];
-    auto load_block = [&](int tile, int sgi, int kin) {
-      const GemmSeg sg = a.g.seg[sgi];
-      const int64_t m0 = (int64_t)tile * BM;
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int r = pass * 64 + wq * 16 + (lane >> 1);
-        const int64_t m = m0 + r;
-        const bool row_ok = m < M;
-        const int64_t row = sg.row_mod ? m % sg.row_mod : m;
-        const float* src = sg.ptr + row * sg.ld + kin + 4 * (lane & 1);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          v[pass][i] = (row_ok && kin + 8 * i + 4 * (lane & 1) < sg.K)
-                           ? __ldg(reinterpret_cast<const float4*>(src + 8 * i))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    // k-block cursor (tile, segment, offset); advance() moves it by one k-block
-    int tile = blockIdx.x, sgi = 0, kin = 0;
-    auto advance = [&]() {
-      kin += BK;
-      if (kin >= a.g.seg[sgi].K) {
-        kin = 0;
-        if (++sgi == a.g.nseg) {
-          sgi = 0;
-          tile += gridDim.x;
-        }
-      }
-    };
-    int kcount = 0;
-    if (grp == 1 && tile < a.num_tiles) {
-      advance();
-      kcount = 1;
-    }
-    if (tile < a.num_tiles) load_block(tile, sgi, kin);
-    while (tile < a.num_tiles) {
-      const int s = kcount % NSTAGE;
-      const uint32_t ph = (kcount / NSTAGE) & 1;
-      mbar_wait(bar_empty + 8 * s, ph ^ 1);
-      unsigned char* a_hi = base_ptr + s * STAGE_BYTES;
-      unsigned char* a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int r = pass * 64 + wq * 16 + (lane >> 1);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint2 hi, lo;
-          split2(v[pass][i].x, v[pass][i].y, hi.x, lo.x);
-          split2(v[pass][i].z, v[pass][i].w, hi.y, lo.y);
-          // columns [8i + 4*(lane&1), +4): 16-byte chunk i of the 128-byte row, 8-byte half (lane&1)
-          const int off = r * 128 + ((i ^ (r & 7)) << 4) + ((lane & 1) << 3);
-          *reinterpret_cast<uint2*>(a_hi + off) = hi;
-          *reinterpret_cast<uint2*>(a_lo + off) = lo;
-        }
-      }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(bar_full + 8 * s);
-      advance();
-      if (tile < a.num_tiles) advance();
-      kcount += 2;
-      if (tile < a.num_tiles) load_block(tile, sgi, kin);
-    }
-  } else if (warp == 8) {
-    // ===================== B loader =====================
-    if (lane == 0) {
-      int kcount = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < a.nkb; ++kb, ++kcount) {
-          const int s = kcount % NSTAGE;
-          const uint32_t ph = (kcount / NSTAGE) & 1;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          mbar_arrive_expect_tx(bar_full + 8 * s, 2 * B_TILE_BYTES);
-          bulk_g2s(base + s * STAGE_BYTES + 2 * A_TILE_BYTES, a.wimg + (size_t)kb * (2 * B_TILE_BYTES),
-                   2 * B_TILE_BYTES, bar_full + 8 * s);
-        }
-      }
-    }
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(N);
-      int kcount = 0, it = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-        const int ab = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * ab, aph ^ 1);  // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ab * N;
-        for (int kb = 0; kb < a.nkb; ++kb, ++kcount) {
-          const int s = kcount % NSTAGE;
-          const uint32_t ph = (kcount / NSTAGE) & 1;
-          mbar_wait(bar_full + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t sa = base + s * STAGE_BYTES;
-          const uint64_t d_ahi = umma_desc(sa), d_alo = umma_desc(sa + A_TILE_BYTES);
-          const uint64_t d_bhi = umma_desc(sa + 2 * A_TILE_BYTES),
-                         d_blo = umma_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < BK / 16; ++ks) {
-            const uint64_t adv = (uint64_t)((ks * 32) >> 4);  // 16 fp16 = 32 bytes along K inside the swizzle row
-            umma_f16(d_tmem, d_ahi + adv, d_bhi + adv, idesc, (kb | ks) ? 1u : 0u);
-            umma_f16(d_tmem, d_alo + adv, d_bhi + adv, idesc, 1u);
-            umma_f16(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
-          }
-          umma_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs have read it
-        }
-        umma_commit(bar_tfull + 8 * ab);   // accumulator complete
-      }
-    }
-  } else {
-    // ===================== epilogue =====================
-    // TMEM -> registers (one row per thread) -> bias/ReLU -> per-warp 32x32 staging
-    // tile in shared memory -> global stores in which 8 lanes cover one full
-    // 128-byte line of a row (row-strided 16-byte stores would cost 32 L2 write
-    // requests per instruction).
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    float* stage = s_stage + q * (32 * EPI_LD);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-      const int ab = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
-      mbar_wait(bar_tfull + 8 * ab, aph);
-      tc_fence_after();
-      const int64_t mbase = (int64_t)tile * BM + q * 32;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * N;
-#pragma unroll 1
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o;
-          o.x = __uint_as_float(v[j + 0]) + s_bias[c0 + j + 0];
-          o.y = __uint_as_float(v[j + 1]) + s_bias[c0 + j + 1];
-          o.z = __uint_as_float(v[j + 2]) + s_bias[c0 + j + 2];
-          o.w = __uint_as_float(v[j + 3]) + s_bias[c0 + j + 3];
-          if (a.g.relu) {
-            o.x = fmaxf(o.x, 0.f);
-            o.y = fmaxf(o.y, 0.f);
-            o.z = fmaxf(o.z, 0.f);
-            o.w = fmaxf(o.w, 0.f);
-          }
-          *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = o;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int rr = 0; rr < 32; rr += 4) {
-          const int row = rr + (lane >> 3);
-          const int64_t m = mbase + row;
-          const float4 o = *reinterpret_cast<const float4*>(stage + row * EPI_LD + (lane & 7) * 4);
-          if (m < M) *reinterpret_cast<float4*>(a.g.C + m * a.g.ldc + c0 + (lane & 7) * 4) = o;
-        }
-        __syncwarp();
-      }
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * ab);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-  }
-}
-
 // ===========================================================================
-// 2-CTA variant (cta_group::2): a cluster of two CTAs (one TPC) works on a
+// The kernel (cta_group::2): a cluster of two CTAs (one TPC) works on a
 // 256-row super-tile.  Each CTA stages its own 128 rows of A and HALF of the
 // weight tile (N/2 rows); the leader CTA issues tcgen05.mma.cta_group::2 (M=256),
 // whose operand fetch reads both halves, so every SM reads and loads only half of
@@ -412,7 +199,8 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * HALF_BYTES;
   static constexpr int NSTAGE = N == 256 ? 3 : 4;
   static constexpr int CTRL_BYTES = 256;
-  static constexpr size_t SMEM = 1024 + (size_t)NSTAGE * STAGE_BYTES + CTRL_BYTES + N * 4 + 4 * 32 * EPI_LD * 4 + 64;
+  static constexpr int STAGING_BYTES = 4 * 8192;                // per epilogue warp: 32x36 fp32 or [hi 4 KB | lo 4 KB]
+  static constexpr size_t SMEM = 1024 + (size_t)NSTAGE * STAGE_BYTES + CTRL_BYTES + N * 4 + STAGING_BYTES + 64;
 };
 
 template <int N>
@@ -431,7 +219,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
   unsigned char* ctrl_ptr = base_ptr + NSTAGE * STAGE_BYTES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl_ptr + 160);
   float* s_bias = reinterpret_cast<float*>(ctrl_ptr + C::CTRL_BYTES);
-  float* s_stage = s_bias + N;
+  unsigned char* s_stage = reinterpret_cast<unsigned char*>(s_bias + N);  // 4 x 8 KB, 1 KB-aligned offsets not needed
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -502,47 +290,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
       advance();
       kcount = 1;
     }
-    if (st < num_super) load_block(st, sgi, kin);
+    if (st < num_super && !a.g.seg[sgi].img) load_block(st, sgi, kin);
     while (st < num_super) {
       const int s = kcount % NSTAGE;
       const uint32_t ph = (kcount / NSTAGE) & 1;
+      const bool is_img = a.g.seg[sgi].img != nullptr;  // the loader warp brings image-format k-blocks
       mbar_wait(bar_empty + 8 * s, ph ^ 1);
-      unsigned char* a_hi = base_ptr + s * STAGE_BYTES;
-      unsigned char* a_lo = a_hi + A_TILE_BYTES;
+      if (!is_img) {
+        unsigned char* a_hi = base_ptr + s * STAGE_BYTES;
+        unsigned char* a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int r = pass * 64 + wq * 16 + (lane >> 1);
+        for (int pass = 0; pass < 2; ++pass) {
+          const int r = pass * 64 + wq * 16 + (lane >> 1);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint2 hi, lo;
-          split2(v[pass][i].x, v[pass][i].y, hi.x, lo.x);
-          split2(v[pass][i].z, v[pass][i].w, hi.y, lo.y);
-          const int off = r * 128 + ((i ^ (r & 7)) << 4) + ((lane & 1) << 3);
-          *reinterpret_cast<uint2*>(a_hi + off) = hi;
-          *reinterpret_cast<uint2*>(a_lo + off) = lo;
+          for (int i = 0; i < 8; ++i) {
+            uint2 hi, lo;
+            split2(v[pass][i].x, v[pass][i].y, hi.x, lo.x);
+            split2(v[pass][i].z, v[pass][i].w, hi.y, lo.y);
+            const int off = r * 128 + ((i ^ (r & 7)) << 4) + ((lane & 1) << 3);
+            *reinterpret_cast<uint2*>(a_hi + off) = hi;
+            *reinterpret_cast<uint2*>(a_lo + off) = lo;
+          }
         }
+        fence_proxy_async();
       }
-      fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
       advance();
       if (st < num_super) advance();
       kcount += 2;
-      if (st < num_super) load_block(st, sgi, kin);
+      if (st < num_super && !a.g.seg[sgi].img) load_block(st, sgi, kin);
     }
   } else if (warp == 8) {
-    // ===================== B loader: this CTA's half of every weight plane =====================
+    // ===================== loader: this CTA's half of every weight plane, and A k-blocks
+    // that are already in tile-image format (one 32 KB bulk copy each) =====================
     if (lane == 0) {
       int kcount = 0;
       for (int st = cluster_id; st < num_super; st += nclusters) {
-        for (int kb = 0; kb < a.nkb; ++kb, ++kcount) {
-          const int s = kcount % NSTAGE;
-          const uint32_t ph = (kcount / NSTAGE) & 1;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          mbar_arrive_expect_tx(bar_full + 8 * s, 2 * C::HALF_BYTES);
-          const unsigned char* src = a.wimg + (size_t)kb * (2 * C::PLANE_BYTES) + (size_t)rank * C::HALF_BYTES;
-          const uint32_t dst = base + s * STAGE_BYTES + 2 * A_TILE_BYTES;
-          bulk_g2s(dst, src, C::HALF_BYTES, bar_full + 8 * s);
-          bulk_g2s(dst + C::HALF_BYTES, src + C::PLANE_BYTES, C::HALF_BYTES, bar_full + 8 * s);
+        const int64_t tile = 2 * (int64_t)st + rank;  // this CTA's 128-row tile
+        int kb = 0;
+        for (int sgi = 0; sgi < a.g.nseg; ++sgi) {
+          const GemmSeg sg = a.g.seg[sgi];
+          const int seg_kbs = (sg.K + BK - 1) / BK;
+          for (int kk = 0; kk < seg_kbs; ++kk, ++kb, ++kcount) {
+            const int s = kcount % NSTAGE;
+            const uint32_t ph = (kcount / NSTAGE) & 1;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            const uint32_t sa = base + s * STAGE_BYTES;
+            mbar_arrive_expect_tx(bar_full + 8 * s, 2 * C::HALF_BYTES + (sg.img ? 2 * A_TILE_BYTES : 0));
+            if (sg.img)
+              bulk_g2s(sa, sg.img + ((size_t)tile * seg_kbs + kk) * (2 * A_TILE_BYTES), 2 * A_TILE_BYTES,
+                       bar_full + 8 * s);
+            const unsigned char* src = a.wimg + (size_t)kb * (2 * C::PLANE_BYTES) + (size_t)rank * C::HALF_BYTES;
+            bulk_g2s(sa + 2 * A_TILE_BYTES, src, C::HALF_BYTES, bar_full + 8 * s);
+            bulk_g2s(sa + 2 * A_TILE_BYTES + C::HALF_BYTES, src + C::PLANE_BYTES, C::HALF_BYTES, bar_full + 8 * s);
+          }
         }
       }
     }
@@ -595,45 +396,90 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;
-    float* stage = s_stage + q * (32 * EPI_LD);
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    unsigned char* stage_b = s_stage + q * 8192;
+    float* stage = reinterpret_cast<float*>(stage_b);
     int it = 0;
     for (int st = cluster_id; st < num_super; st += nclusters, ++it) {
       const int ab = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(bar_tfull + 8 * ab, aph);
       tc_fence_after();
-      const int64_t mbase = (int64_t)st * (2 * BM) + rank * BM + q * 32;
+      const int64_t tile = 2 * (int64_t)st + rank;
+      const int64_t mbase = tile * BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * N;
+      if (a.g.C_img) {
+        // hi/lo fp16 tile image: per 64-wide k-block this warp owns rows [32q, 32q+32) of both
+        // planes = two contiguous 4 KB slabs; stage them swizzled, then two bulk stores.
+        const int r = q * 32 + lane;  // row inside the 128-row tile
 #pragma unroll 1
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int kb = 0; kb < N / BK; ++kb) {
+          if (lane == 0) bulk_wait_read0();  // previous slabs have been read out of the staging buffer
+          __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o;
-          o.x = __uint_as_float(v[j + 0]) + s_bias[c0 + j + 0];
-          o.y = __uint_as_float(v[j + 1]) + s_bias[c0 + j + 1];
-          o.z = __uint_as_float(v[j + 2]) + s_bias[c0 + j + 2];
-          o.w = __uint_as_float(v[j + 3]) + s_bias[c0 + j + 3];
-          if (a.g.relu) {
-            o.x = fmaxf(o.x, 0.f);
-            o.y = fmaxf(o.y, 0.f);
-            o.z = fmaxf(o.z, 0.f);
-            o.w = fmaxf(o.w, 0.f);
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld32(taddr + kb * BK + h * 32, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float x[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                x[e] = __uint_as_float(v[j + e]) + s_bias[kb * BK + h * 32 + j + e];
+                if (a.g.relu) x[e] = fmaxf(x[e], 0.f);
+              }
+              uint4 hi, lo;
+              split2(x[0], x[1], hi.x, lo.x);
+              split2(x[2], x[3], hi.y, lo.y);
+              split2(x[4], x[5], hi.z, lo.z);
+              split2(x[6], x[7], hi.w, lo.w);
+              const int chunk = h * 4 + (j >> 3);  // 16-byte chunk of the 128-byte row
+              const int off = lane * 128 + ((chunk ^ (r & 7)) << 4);
+              *reinterpret_cast<uint4*>(stage_b + off) = hi;
+              *reinterpret_cast<uint4*>(stage_b + 4096 + off) = lo;
+            }
           }
-          *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = o;
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            unsigned char* dst = a.g.C_img + ((size_t)tile * (N / BK) + kb) * (2 * A_TILE_BYTES) + (size_t)q * 4096;
+            bulk_s2g(dst, smem_u32(stage_b), 4096);
+            bulk_s2g(dst + A_TILE_BYTES, smem_u32(stage_b + 4096), 4096);
+            bulk_commit();
+          }
         }
-        __syncwarp();
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int rr = 0; rr < 32; rr += 4) {
-          const int row = rr + (lane >> 3);
-          const int64_t m = mbase + row;
-          const float4 o = *reinterpret_cast<const float4*>(stage + row * EPI_LD + (lane & 7) * 4);
-          if (m < M) *reinterpret_cast<float4*>(a.g.C + m * a.g.ldc + c0 + (lane & 7) * 4) = o;
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[j + 0]) + s_bias[c0 + j + 0];
+            o.y = __uint_as_float(v[j + 1]) + s_bias[c0 + j + 1];
+            o.z = __uint_as_float(v[j + 2]) + s_bias[c0 + j + 2];
+            o.w = __uint_as_float(v[j + 3]) + s_bias[c0 + j + 3];
+            if (a.g.relu) {
+              o.x = fmaxf(o.x, 0.f);
+              o.y = fmaxf(o.y, 0.f);
+              o.z = fmaxf(o.z, 0.f);
+              o.w = fmaxf(o.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = o;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 4) {
+            const int row = rr + (lane >> 3);
+            const int64_t m = mbase + row;
+            const float4 o = *reinterpret_cast<const float4*>(stage + row * EPI_LD + (lane & 7) * 4);
+            if (m < M) *reinterpret_cast<float4*>(a.g.C + m * a.g.ldc + c0 + (lane & 7) * 4) = o;
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       tc_fence_before();
       if (rank == 0)
@@ -641,6 +487,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
       else
         mbar_arrive_remote(bar_ptempty + 8 * ab, 0);
     }
+    if (a.g.C_img && lane == 0) bulk_wait_all0();  // image stores complete before the kernel ends
   }
 
   tc_fence_before();
@@ -651,13 +498,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
   }
-}
-
-template <int N>
-static size_t smem_bytes() {
-  constexpr int NSTAGE = N == 256 ? 2 : 3;
-  return 1024 + (size_t)NSTAGE * (2 * A_TILE_BYTES + 2 * N * BK * 2) + 16 * NSTAGE + 64 + N * 4 +
-         4 * 32 * EPI_LD * 4 + 64;
 }
 
 }  // namespace tc
@@ -675,11 +515,20 @@ int launch_gemm_tc(const GemmArgs& a, const void* w_image, cudaStream_t st) {
     set_error("gemm_tc: N=%d unsupported (128 or 256)", a.N);
     return TH_EINVAL;
   }
-  for (int s = 0; s < a.nseg; ++s)
-    if (a.seg[s].K % 16 != 0 || a.seg[s].ld % 4 != 0 || (reinterpret_cast<uintptr_t>(a.seg[s].ptr) & 15)) {
-      set_error("gemm_tc: segment %d K=%d ld=%d unsupported", s, a.seg[s].K, a.seg[s].ld);
+  for (int s = 0; s < a.nseg; ++s) {
+    const GemmSeg& g = a.seg[s];
+    const bool ok = g.img ? (g.K % tc::BK == 0 && (reinterpret_cast<uintptr_t>(g.img) & 1023) == 0 && !g.row_mod)
+                          : (g.K % 16 == 0 && g.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g.ptr) & 15) == 0);
+    if (!ok) {
+      set_error("gemm_tc: segment %d K=%d ld=%d unsupported", s, g.K, g.ld);
       return TH_EINVAL;
     }
+  }
+  if ((a.C_img != nullptr) == (a.C != nullptr) || (a.C_img && (a.M % (2 * tc::BM) != 0 ||
+                                                                (reinterpret_cast<uintptr_t>(a.C_img) & 1023)))) {
+    set_error("gemm_tc: exactly one of C / C_img, image output needs M %% 256 == 0");
+    return TH_EINVAL;
+  }
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -691,48 +540,24 @@ int launch_gemm_tc(const GemmArgs& a, const void* w_image, cudaStream_t st) {
   t.wimg = static_cast<const unsigned char*>(w_image);
   t.nkb = tc_image_kblocks(a);
   t.num_tiles = (int)cdiv(a.M, tc::BM);
-  const int grid = t.num_tiles < num_sms ? t.num_tiles : num_sms;
-  static int use_1cta = -1;
-  if (use_1cta < 0) {
-    const char* e = getenv("TH_GEMM_1CTA");
-    use_1cta = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (!use_1cta) {
-    const int num_super = (t.num_tiles + 1) / 2;
-    const int nclusters = num_super < num_sms / 2 ? num_super : num_sms / 2;
-    if (a.N == 256) {
-      static bool cfg = false;
-      if (!cfg) {
-        TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)tc::Cfg2<256>::SMEM));
-        cfg = true;
-      }
-      tc::k_gemm_tc2<256><<<2 * nclusters, tc::NUM_THREADS, tc::Cfg2<256>::SMEM, st>>>(t);
-    } else {
-      static bool cfg = false;
-      if (!cfg) {
-        TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)tc::Cfg2<128>::SMEM));
-        cfg = true;
-      }
-      tc::k_gemm_tc2<128><<<2 * nclusters, tc::NUM_THREADS, tc::Cfg2<128>::SMEM, st>>>(t);
-    }
-  } else if (a.N == 256) {
+  const int num_super = (t.num_tiles + 1) / 2;
+  const int nclusters = num_super < num_sms / 2 ? num_super : num_sms / 2;
+  if (a.N == 256) {
     static bool cfg = false;
-    const size_t smem = tc::smem_bytes<256>();
     if (!cfg) {
-      TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)tc::Cfg2<256>::SMEM));
       cfg = true;
     }
-    tc::k_gemm_tc<256><<<grid, tc::NUM_THREADS, smem, st>>>(t);
+    tc::k_gemm_tc2<256><<<2 * nclusters, tc::NUM_THREADS, tc::Cfg2<256>::SMEM, st>>>(t);
   } else {
     static bool cfg = false;
-    const size_t smem = tc::smem_bytes<128>();
     if (!cfg) {
-      TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)tc::Cfg2<128>::SMEM));
       cfg = true;
     }
-    tc::k_gemm_tc<128><<<grid, tc::NUM_THREADS, smem, st>>>(t);
+    tc::k_gemm_tc2<128><<<2 * nclusters, tc::NUM_THREADS, tc::Cfg2<128>::SMEM, st>>>(t);
   }
   TH_LAUNCHED();
   return TH_OK;
