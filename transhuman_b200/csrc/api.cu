@@ -396,6 +396,15 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
     fo.do_pix = 1;
     fo.do_vd = alpha_only ? 0 : 1;
     fo.rep_pad = 1;
+    const int use_tc = (f->flags & TH_FLAG_SIMT_MLP) ? 0 : 1;
+    if (use_tc) {  // the feature kernel writes the GEMM operands directly as fp16 hi/lo tile images
+      fo.rep_img = reinterpret_cast<unsigned char*>(b.rep);
+      fo.pix_img = reinterpret_cast<unsigned char*>(b.pix);
+      fo.pixm_img = alpha_only ? nullptr : reinterpret_cast<unsigned char*>(b.pix_mean);
+      fo.vd_img = reinterpret_cast<unsigned char*>(b.vd);
+      fo.img_view_rows = Pp;
+      fo.pix_mean = nullptr;
+    }
     src.ids = ids;
     src.first = first;
     int rc = launch_features(fr, src, P, fo, st);
@@ -410,7 +419,8 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
     run.alpha_out = alpha_out;
     run.alpha_only = alpha_only;
     run.zero_rgb_if_transparent = zero_rgb;
-    run.use_tensor_cores = (f->flags & TH_FLAG_SIMT_MLP) ? 0 : 1;
+    run.use_tensor_cores = use_tc;
+    run.inputs_are_images = use_tc;
     rc = mlp_forward(run, b, hdr, st);
     if (rc) return rc;
   }

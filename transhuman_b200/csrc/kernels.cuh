@@ -24,6 +24,10 @@ struct FeatOut {
   float* vd;         // (P, 32) view-direction embedding, zero padded (or nullptr)
   int64_t* knn_idx;  // (P, K) or nullptr
   float* knn_d2;     // (P, K) or nullptr
+  // GEMM-layout outputs can instead be written as fp16 hi/lo tile images (tensor-core
+  // path): rep (V*Pp,256), pix (V*Pp,384), pix_mean (Pp,384), vd (Pp,64: 27 + zeros).
+  unsigned char *rep_img, *pix_img, *pixm_img, *vd_img;
+  int64_t img_view_rows;  // Pp
   int do_rep, do_pix, do_vd;
   int rep_pad;       // write channel 255 = 0 (GEMM layout)
   int pts_are_smpl;  // explicit points are already in SMPL coordinates (staged a8)
@@ -94,6 +98,15 @@ struct PackedHeader {
 };
 constexpr uint32_t PACK_MAGIC = 0x31574854u;
 
+// Byte offset of the hi element (row, col) of a (rows, C) activation in tile-image
+// format; the lo element sits 16384 bytes further.
+__host__ __device__ inline size_t img_offset(int64_t row, int col, int C) {
+  const int64_t tile = row >> 7;
+  const int r = (int)(row & 127), kb = col >> 6, kk = col & 63;
+  return ((size_t)(tile * (C >> 6) + kb) << 15) + (size_t)r * 128 + (size_t)(((kk >> 3) ^ (r & 7)) << 4) +
+         (size_t)(kk & 7) * 2;
+}
+
 // ---- per-point network on GEMM-layout activations (mlp_simt.cu / mlp_tc.cu) ----
 // Activation buffers of one chunk (fp32, row-major, rows = view-major (v*Pp + p)
 // with Pp = P rounded up to 256 so that every view starts on a 2-CTA super-tile;
@@ -127,6 +140,7 @@ struct MlpRun {
   int alpha_only;
   int zero_rgb_if_transparent;
   int use_tensor_cores;
+  int inputs_are_images;  // rep / pix / pix_mean / vd buffers hold tile images (fused path)
 };
 // Pp = pad_points(P): view stride of every buffer in `b`.
 int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& hdr_host, cudaStream_t st);
@@ -143,6 +157,7 @@ struct GemmSeg {
   int K;        // multiple of 16
   int64_t row_mod;  // rows wrap modulo this (0 = no wrap)
   const unsigned char* img;
+  int64_t img_tile_mod;  // image segments: row tiles wrap modulo this (0 = no wrap)
 };
 struct GemmArgs {
   GemmSeg seg[TH_MAX_VIEWS + 1];

@@ -17,6 +17,8 @@
 //   G   = relu([F | viewdir] view_fc^T)                  (V*P,128) <- K 288
 //   T   = relu([G_0|..|G_{V-1}| mean_v pix] [fc_4/V ...| fc_4 rgb_res_1]^T)
 //   rgb = T rgb_fc^T
+#include <cuda_fp16.h>
+
 #include <initializer_list>
 
 #include "kernels.cuh"
@@ -148,6 +150,8 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // cross-view attention mix (cross_transformer.py:128-149): one warp per point.
 // ---------------------------------------------------------------------------
+// IMG: X is read from, and XT written to, fp16 hi/lo tile images (tensor-core path).
+template <bool IMG>
 __global__ void __launch_bounds__(256) k_attn_mix(const float* __restrict__ kp, const float* __restrict__ ks,
                                                   const float* __restrict__ x, float* __restrict__ xt, int64_t P,
                                                   int64_t Pp, int V) {
@@ -193,7 +197,19 @@ __global__ void __launch_bounds__(256) k_attn_mix(const float* __restrict__ kp, 
     float4 xv[TH_MAX_VIEWS];
 #pragma unroll
     for (int i = 0; i < TH_MAX_VIEWS; ++i)
-      if (i < V) xv[i] = *reinterpret_cast<const float4*>(x + (i * Pp + p) * 256 + c);
+      if (i < V) {
+        if (IMG) {
+          const unsigned char* q = reinterpret_cast<const unsigned char*>(x) + img_offset(i * Pp + p, c, 256);
+          const uint2 h = *reinterpret_cast<const uint2*>(q), l = *reinterpret_cast<const uint2*>(q + 16384);
+          const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)),
+                       h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y)),
+                       l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)),
+                       l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+          xv[i] = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+        } else {
+          xv[i] = *reinterpret_cast<const float4*>(x + (i * Pp + p) * 256 + c);
+        }
+      }
 #pragma unroll
     for (int j = 0; j < TH_MAX_VIEWS; ++j)
       if (j < V) {
@@ -206,7 +222,17 @@ __global__ void __launch_bounds__(256) k_attn_mix(const float* __restrict__ kp, 
             o.z = fmaf(A[i][j], xv[i].z, o.z);
             o.w = fmaf(A[i][j], xv[i].w, o.w);
           }
-        *reinterpret_cast<float4*>(xt + (j * Pp + p) * 256 + c) = o;
+        if (IMG) {
+          __half2 ha = __floats2half2_rn(o.x, o.y), hb = __floats2half2_rn(o.z, o.w);
+          const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+          __half2 la = __floats2half2_rn(o.x - fa.x, o.y - fa.y), lb = __floats2half2_rn(o.z - fb.x, o.w - fb.y);
+          unsigned char* q = reinterpret_cast<unsigned char*>(xt) + img_offset(j * Pp + p, c, 256);
+          *reinterpret_cast<uint2*>(q) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+          *reinterpret_cast<uint2*>(q + 16384) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+        } else {
+          *reinterpret_cast<float4*>(xt + (j * Pp + p) * 256 + c) = o;
+        }
       }
   }
 }
@@ -324,7 +350,7 @@ int launch_pack_inputs(const float* human_rep, const float* pixel_feat, const fl
 // ---------------------------------------------------------------------------
 size_t mlp_buffer_floats_per_point(int V) {
   // rep, pix, s, x, xt, net: per view; kp, ks: per view; per point: pix_mean, vd, o, t, alpha
-  return (size_t)V * (REP_LD + PIX_LD + 256 * 4 + 128 * 2) + PIX_LD + VD_LD + 256 + 128 + 4;
+  return (size_t)V * (REP_LD + PIX_LD + 256 * 4 + 128 * 2) + PIX_LD + 2 * VD_LD + 256 + 128 + 4;
 }
 
 // All buffers are sized and strided for Pp = pad_points(P) rows per view.
@@ -346,7 +372,7 @@ void mlp_carve(float* base, int64_t P, int V, MlpBuffers* b) {
   b->kp = take((size_t)V * 128);
   b->ks = take((size_t)V * 128);
   b->pix_mean = take(PIX_LD);
-  b->vd = take(VD_LD);
+  b->vd = take(2 * VD_LD);  // 32 fp32 channels, or a 64-wide fp16 hi/lo image (same 256 B / point)
   // o (256), t (128), alpha (4, padded) follow: see mlp_forward
 }
 
@@ -398,7 +424,7 @@ static int mlp_forward_simt(const MlpRun& run, const MlpBuffers& b, const Packed
   const int64_t P = run.P, Pp = pad_points(P);
   const int V = run.V;
   const int64_t R = (int64_t)V * Pp;
-  float* o = b.vd + (size_t)Pp * VD_LD;
+  float* o = b.vd + (size_t)Pp * 2 * VD_LD;
   float* t = o + (size_t)Pp * 256;
   float* alpha = t + (size_t)Pp * 128;
   auto gemm = [&](std::initializer_list<GemmSeg> segs, const float* W, int ldw, const float* bias, float* C, int N,
@@ -422,7 +448,7 @@ static int mlp_forward_simt(const MlpRun& run, const MlpBuffers& b, const Packed
   if ((rc = gemm({seg_f32(b.s, 256, 256)}, wf(run, h.k1_w), 256, wf(run, h.k1_b), b.ks, 128, R, 0))) return rc;
   {
     ProfScope prof_(PROF_POINTWISE, st);
-    k_attn_mix<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(b.kp, b.ks, b.x, b.xt, P, Pp, V);
+    k_attn_mix<false><<<(unsigned)cdiv(P, 8), 256, 0, st>>>(b.kp, b.ks, b.x, b.xt, P, Pp, V);
   }
   TH_LAUNCHED();
   if ((rc = gemm({seg_f32(b.s, 256, 256), seg_f32(b.xt, 256, 256)}, wf(run, h.v_w), 512, wf(run, h.v_b), b.net, 256, R,
@@ -483,7 +509,7 @@ static int mlp_forward_tc(const MlpRun& run, const MlpBuffers& b, const PackedHe
   const int64_t P = run.P, Pp = pad_points(P);
   const int V = run.V;
   const int64_t R = (int64_t)V * Pp;
-  float* o = b.vd + (size_t)Pp * VD_LD;
+  float* o = b.vd + (size_t)Pp * 2 * VD_LD;
   float* t = o + (size_t)Pp * 256;
   float* alpha = t + (size_t)Pp * 128;
   auto gemm = [&](std::initializer_list<GemmSeg> segs, uint64_t w_img, const float* bias, float* C, bool c_is_img, int N,
@@ -505,18 +531,19 @@ static int mlp_forward_tc(const MlpRun& run, const MlpBuffers& b, const PackedHe
   auto view_img = [&](const float* buf, int C, int v) {
     return seg_img(buf + (size_t)v * Pp * C, C);
   };
+  const bool in_img = run.inputs_are_images != 0;
+  auto in_seg = [&](const float* buf, int ld, int K) { return in_img ? seg_img(buf, K) : seg_f32(buf, ld, K); };
   int rc;
-  if ((rc = gemm({seg_f32(b.rep, REP_LD, 256)}, h.h_fc0, wf(run, h.fc0_b), b.s, true, 256, R, 1))) return rc;
-  if ((rc = gemm({seg_f32(b.pix, PIX_LD, 384)}, h.h_ar0, wf(run, h.ar0_b), b.x, false, 256, R, 1))) return rc;
-  if ((rc = gemm({seg_f32(b.x, 256, 256)}, h.h_k0, wf(run, h.k0_b), b.kp, false, 128, R, 0))) return rc;
+  if ((rc = gemm({in_seg(b.rep, REP_LD, 256)}, h.h_fc0, wf(run, h.fc0_b), b.s, true, 256, R, 1))) return rc;
+  if ((rc = gemm({in_seg(b.pix, PIX_LD, 384)}, h.h_ar0, wf(run, h.ar0_b), b.x, true, 256, R, 1))) return rc;
+  if ((rc = gemm({seg_img(b.x, 256)}, h.h_k0, wf(run, h.k0_b), b.kp, false, 128, R, 0))) return rc;
   if ((rc = gemm({seg_img(b.s, 256)}, h.h_k1, wf(run, h.k1_b), b.ks, false, 128, R, 0))) return rc;
   {
     ProfScope prof_(PROF_POINTWISE, st);
-    k_attn_mix<<<(unsigned)cdiv(P, 8), 256, 0, st>>>(b.kp, b.ks, b.x, b.xt, P, Pp, V);
+    k_attn_mix<true><<<(unsigned)cdiv(P, 8), 256, 0, st>>>(b.kp, b.ks, b.x, b.xt, P, Pp, V);
   }
   TH_LAUNCHED();
-  if ((rc = gemm({seg_img(b.s, 256), seg_f32(b.xt, 256, 256)}, h.h_v, wf(run, h.v_b), b.net, true, 256, R, 0)))
-    return rc;
+  if ((rc = gemm({seg_img(b.s, 256), seg_img(b.xt, 256)}, h.h_v, wf(run, h.v_b), b.net, true, 256, R, 0))) return rc;
   float* n1 = b.x;      // X is dead after the mix
   float* inter = b.xt;  // XT is dead after NET
   if ((rc = gemm({seg_img(b.net, 256)}, h.h_fc1, wf(run, h.fc1_b), n1, true, 256, R, 1))) return rc;
@@ -537,15 +564,20 @@ static int mlp_forward_tc(const MlpRun& run, const MlpBuffers& b, const PackedHe
   if (run.alpha_only) return TH_OK;
   float* f = b.s;      // S is dead after NET
   float* gbuf = b.kp;  // keys are dead after the mix
-  if ((rc = gemm({seg_img(inter, 256), seg_f32(b.pix, PIX_LD, 384)}, h.h_f, wf(run, h.f_b), f, true, 256, R, 0)))
+  if ((rc = gemm({seg_img(inter, 256), in_seg(b.pix, PIX_LD, 384)}, h.h_f, wf(run, h.f_b), f, true, 256, R, 0)))
     return rc;
-  if ((rc = gemm({seg_img(f, 256), seg_f32(b.vd, VD_LD, VD_LD, Pp)}, h.h_view, wf(run, h.view_b), gbuf, true, 128, R,
-                 1)))
-    return rc;
+  {
+    GemmSeg vd = seg_f32(b.vd, VD_LD, VD_LD, Pp);
+    if (in_img) {
+      vd = seg_img(b.vd, 64);
+      vd.img_tile_mod = Pp / 128;
+    }
+    if ((rc = gemm({seg_img(f, 256), vd}, h.h_view, wf(run, h.view_b), gbuf, true, 128, R, 1))) return rc;
+  }
   {
     GemmArgs g{};
     for (int v = 0; v < V; ++v) g.seg[v] = view_img(gbuf, 128, v);
-    g.seg[V] = seg_f32(b.pix_mean, PIX_LD, 384);
+    g.seg[V] = in_seg(b.pix_mean, PIX_LD, 384);
     g.nseg = V + 1;
     g.bias = wf(run, h.t_b);
     g.C = t;

@@ -337,9 +337,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
             const uint32_t sa = base + s * STAGE_BYTES;
             mbar_arrive_expect_tx(bar_full + 8 * s, 2 * C::HALF_BYTES + (sg.img ? 2 * A_TILE_BYTES : 0));
-            if (sg.img)
-              bulk_g2s(sa, sg.img + ((size_t)tile * seg_kbs + kk) * (2 * A_TILE_BYTES), 2 * A_TILE_BYTES,
+            if (sg.img) {
+              const int64_t tl = sg.img_tile_mod ? tile % sg.img_tile_mod : tile;
+              bulk_g2s(sa, sg.img + ((size_t)tl * seg_kbs + kk) * (2 * A_TILE_BYTES), 2 * A_TILE_BYTES,
                        bar_full + 8 * s);
+            }
             const unsigned char* src = a.wimg + (size_t)kb * (2 * C::PLANE_BYTES) + (size_t)rank * C::HALF_BYTES;
             bulk_g2s(sa + 2 * A_TILE_BYTES, src, C::HALF_BYTES, bar_full + 8 * s);
             bulk_g2s(sa + 2 * A_TILE_BYTES + C::HALF_BYTES, src + C::PLANE_BYTES, C::HALF_BYTES, bar_full + 8 * s);
@@ -517,7 +519,7 @@ int launch_gemm_tc(const GemmArgs& a, const void* w_image, cudaStream_t st) {
   }
   for (int s = 0; s < a.nseg; ++s) {
     const GemmSeg& g = a.seg[s];
-    const bool ok = g.img ? (g.K % tc::BK == 0 && (reinterpret_cast<uintptr_t>(g.img) & 1023) == 0 && !g.row_mod)
+    const bool ok = g.img ? (g.K % tc::BK == 0 && (reinterpret_cast<uintptr_t>(g.img) & 1023) == 0)
                           : (g.K % 16 == 0 && g.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g.ptr) & 15) == 0);
     if (!ok) {
       set_error("gemm_tc: segment %d K=%d ld=%d unsupported", s, g.K, g.ld);
