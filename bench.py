@@ -283,12 +283,15 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("gemm_dram_bytes_per_launch")
+    # the split scheme issues 3 fp16 tensor products per algorithmic MAC: its ceiling is 1/3 of the fp16 rate
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-                "kernel": "k_gemm_simt (fp32 CUDA cores)" if args.simt else "k_gemm_tc (tcgen05, fp16x3 split)",
+                "kernel": "k_gemm_simt (fp32 CUDA cores)" if args.simt else "k_gemm_tc2 (tcgen05 cta_group::2, fp16x3 split)",
                 "launches_per_step": gemm_launches // args.steps, "gemm_ms_per_step": gemm_ms_step,
                 "share_of_step": gemm_ms_step / ms_step, "peak_source": peaks["source"],
                 "flops_per_point": flops_per_point(args.views),
+                "tensor_products_per_mac": 1 if args.simt else 3,
+                "issued_tensor_frac": (1 if args.simt else 3) * achieved / peaks["bf16_tflops"],
                 "hbm_algorithmic_gbs": BYTES_PER_RAY * N_rays / (ms_step * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
     breakdown = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
