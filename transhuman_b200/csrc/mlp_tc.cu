@@ -225,10 +225,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int num_super = (a.num_tiles + 1) >> 1;  // 256-row super-tiles
+  // fp32-row A segments need the producer warps; with every segment in tile-image format
+  // (the fused path) the loader alone fills a stage and the producers retire at once
+  bool any_f32 = false;
+  for (int i = 0; i < a.g.nseg; ++i) any_f32 |= (a.g.seg[i].img == nullptr);
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(bar_full + 8 * s, 128 + 1);
+      mbar_init(bar_full + 8 * s, (any_f32 ? 128 : 0) + 1);  // producer threads + the loader's expect_tx arrive
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_pfull + 8 * s, 1);
     }
@@ -254,7 +258,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
   const int64_t M = a.g.M;
 
   if (warp < 8) {
-    // ===================== A producers (as in the 1-CTA kernel) =====================
+    // ===================== A producers (fp32-row segments only) =====================
+    // Two groups of 4 warps alternate k-blocks, each software pipelined (the global loads of a
+    // group's next k-block are in flight while it waits for a free stage).  Lane mapping per
+    // pass (16 rows x 64 columns per warp): row = lane>>1, 8 float4 loads at columns
+    // 8*i + 4*(lane&1); the 8-byte swizzled stores of a half-warp hit 8 distinct 16-byte chunks.
     const int grp = warp >> 2, wq = warp & 3;
     float4 v[2][8];
     auto load_block = [&](int st, int sgi, int kin) {
@@ -286,6 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
       }
     };
     int kcount = 0;
+    if (!any_f32) st = num_super;  // nothing to produce
     if (grp == 1 && st < num_super) {
       advance();
       kcount = 1;
