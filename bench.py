@@ -303,10 +303,13 @@ def main():
     if not args.no_culled and world == 1:
         # render_fast semantics (what run.py executes): cull at 0.1 m + progressive RGB
         ms_c = timed(lambda: step(dev_rays, ops.TH_RENDER_MASKED), max(1, args.steps), 1)
+        ops.profile_start()
         _, oc = step(dev_rays, ops.TH_RENDER_MASKED)
+        prof_c = ops.profile_stop()
         extra["culled"] = {"rays_per_s": N_rays / (ms_c * 1e-3), "ms_per_step": ms_c,
                            "points_in_radius": oc["counters"][0], "rays_surviving": oc["counters"][1],
-                           "point_fraction": oc["counters"][0] / P_step}
+                           "point_fraction": oc["counters"][0] / P_step,
+                           "ms_by_category": {k: round(v[0], 3) for k, v in prof_c.items()}}
 
     if rank == 0:
         cpu = None
