@@ -63,8 +63,8 @@ def test_pack_weights_folds_layers(lib):
         assert lib.th_pack_weights(C.byref(wstruct), V, blob.ctypes.data, 16) == -2
         assert b"need" in lib.th_last_error()
         magic, nviews, total = struct.unpack_from("<IiQ", blob, 0)
-        assert magic == 0x31574854 and nviews == V and total == pw_bytes
-        offs = struct.unpack_from("<37Q", blob, 16)
+        assert magic == 0x32574854 and nviews == V and total == pw_bytes
+        offs = struct.unpack_from("<43Q", blob, 16)
         f32 = lambda off, n: blob[off:off + 4 * n].view(np.float32)
         # fc_0: K padded 255 -> 256 with a zero column
         fc0 = f32(offs[0], 256 * 256).reshape(256, 256)
@@ -86,7 +86,24 @@ def test_pack_weights_folds_layers(lib):
         wantb = w["fc_4.weight"].astype(np.float64) @ w["rgb_res_1.bias"].astype(np.float64) + w["fc_4.bias"]
         np.testing.assert_allclose(bt, wantb, rtol=0, atol=1e-7)
         # fp16 hi/lo tile images (128B-swizzled, per 64-wide k-block) reconstruct fc_0 to ~2^-22
-        h_fc0 = offs[26]
+        # layers folded across a missing non-linearity (tensor-core schedule)
+        f64 = lambda k: w[k].astype(np.float64)
+        fc1f = f32(offs[26], 256 * 512).reshape(256, 512)
+        np.testing.assert_allclose(fc1f[:, :256], f64("fc_1.weight") @ f64("spatial_key_value_1.value_embed.weight"),
+                                   rtol=0, atol=1e-7)
+        np.testing.assert_allclose(fc1f[:, 256:], f64("fc_1.weight") @ f64("spatial_key_value_0.value_embed.weight"),
+                                   rtol=0, atol=1e-7)
+        bv = f64("spatial_key_value_1.value_embed.bias") + f64("spatial_key_value_0.value_embed.bias")
+        np.testing.assert_allclose(f32(offs[27], 256), f64("fc_1.weight") @ bv + f64("fc_1.bias"), rtol=0, atol=1e-7)
+        gvf = f32(offs[28], 128 * 704).reshape(128, 704)
+        v1, v2 = f64("view_fc.weight")[:, :256], w["view_fc.weight"][:, 256:]
+        np.testing.assert_allclose(gvf[:, :256], v1 @ f64("feature_fc.weight"), rtol=0, atol=1e-7)
+        np.testing.assert_allclose(gvf[:, 256:640], v1 @ f64("rgb_res_0.weight"), rtol=0, atol=1e-7)
+        assert np.array_equal(gvf[:, 640:667], v2) and np.all(gvf[:, 667:] == 0)
+        np.testing.assert_allclose(f32(offs[29], 128),
+                                   v1 @ (f64("feature_fc.bias") + f64("rgb_res_0.bias")) + f64("view_fc.bias"),
+                                   rtol=0, atol=1e-7)
+        h_fc0 = offs[30]
         img = blob[h_fc0:h_fc0 + 4 * 65536].view(np.float16).astype(np.float32).reshape(4, 2, 256, 64)
         n = np.arange(256)[:, None]
         kk = np.arange(64)[None, :]

@@ -93,6 +93,8 @@ static std::vector<MatSpec> mat_specs(int V) {
       {&H::view_w, &H::view_b, &H::h_view, 128, 320},
       {&H::t_w, &H::t_b, &H::h_t, 128, 128 * V + 384},
       {&H::rgb_w, &H::rgb_b, nullptr, 3, 128},
+      {&H::fc1f_w, &H::fc1f_b, &H::h_fc1f, 256, 512},
+      {&H::gvf_w, &H::gvf_b, &H::h_gvf, 128, 704},
   };
 }
 
@@ -237,6 +239,44 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
       double s = w->fc_4_b[n];
       for (int j = 0; j < 128; ++j) s += (double)w->fc_4_w[n * 128 + j] * (double)w->rgb_res_1_b[j];
       W(h.t_b)[n] = (float)s;
+    }
+  }
+  // layers folded across a missing non-linearity (tensor-core schedule), products in float64
+  {
+    // N1 = relu(fc_1 (v1 S + v0 XT + b_v) + b_1): W_fc1f = [fc_1 @ v1 | fc_1 @ v0]
+    for (int n = 0; n < 256; ++n) {
+      for (int k = 0; k < 256; ++k) {
+        double s1 = 0.0, s0 = 0.0;
+        for (int j = 0; j < 256; ++j) {
+          const double f = (double)w->fc_1_w[n * 256 + j];
+          s1 += f * (double)w->skv1_value_w[j * 256 + k];
+          s0 += f * (double)w->skv0_value_w[j * 256 + k];
+        }
+        W(h.fc1f_w)[(size_t)n * 512 + k] = (float)s1;
+        W(h.fc1f_w)[(size_t)n * 512 + 256 + k] = (float)s0;
+      }
+      double s = w->fc_1_b[n];
+      for (int j = 0; j < 256; ++j)
+        s += (double)w->fc_1_w[n * 256 + j] * ((double)w->skv1_value_b[j] + (double)w->skv0_value_b[j]);
+      W(h.fc1f_b)[n] = (float)s;
+    }
+    // G = relu(V1 (feature_fc INTER + rgb_res_0 pix + b_f) + V2 viewdir + b_view), view_fc = [V1 | V2]
+    for (int n = 0; n < 128; ++n) {
+      const float* v1 = w->view_fc_w + (size_t)n * 283;
+      for (int k = 0; k < 256; ++k) {
+        double s = 0.0;
+        for (int j = 0; j < 256; ++j) s += (double)v1[j] * (double)w->feature_fc_w[j * 256 + k];
+        W(h.gvf_w)[(size_t)n * 704 + k] = (float)s;
+      }
+      for (int k = 0; k < 384; ++k) {
+        double s = 0.0;
+        for (int j = 0; j < 256; ++j) s += (double)v1[j] * (double)w->rgb_res_0_w[j * 384 + k];
+        W(h.gvf_w)[(size_t)n * 704 + 256 + k] = (float)s;
+      }
+      for (int k = 0; k < 27; ++k) W(h.gvf_w)[(size_t)n * 704 + 640 + k] = v1[256 + k];
+      double s = w->view_fc_b[n];
+      for (int j = 0; j < 256; ++j) s += (double)v1[j] * ((double)w->feature_fc_b[j] + (double)w->rgb_res_0_b[j]);
+      W(h.gvf_b)[n] = (float)s;
     }
   }
   memcpy(W(h.rgb_w), w->rgb_fc_w, 3 * 128 * 4);

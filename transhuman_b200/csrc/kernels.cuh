@@ -75,8 +75,14 @@ int launch_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w
 //   W_f    = [feature_fc | rgb_res_0]                   b_f = b_ff + b_r0
 //   W_view = [view_fc[:, :256] | view_fc[:, 256:283] | 0(37)]   (K = 320)
 //   W_t    = [fc_4/V | ... | fc_4/V | fc_4 @ rgb_res_1] b_t = fc_4 @ b_r1 + b_4
+// Tensor-core schedule only (no non-linearity sits between the folded layers, so
+// the products are exact in real arithmetic; the fp32 CUDA-core schedule keeps the
+// unfolded W_v / fc_1 and W_f / W_view and so cross-checks the folds):
+//   W_fc1f = [fc_1 @ value_embed_1 | fc_1 @ value_embed_0]      b = fc_1 @ b_v + b_fc1
+//   W_gvf  = [V1 @ feature_fc | V1 @ rgb_res_0 | view_fc[:, 256:283] | 0(37)]  (K = 704)
+//            with V1 = view_fc[:, :256];  b = V1 @ b_f + b_view
 struct PackedHeader {
-  uint32_t magic;      // 'THW1'
+  uint32_t magic;      // 'THW2'
   int32_t n_views;
   uint64_t total_bytes;
   // fp32 matrices, row-major (N, K) with K contiguous; offsets in bytes from blob start
@@ -93,10 +99,12 @@ struct PackedHeader {
   uint64_t view_w, view_b;      // (128,320)
   uint64_t t_w, t_b;            // (128,128*V+384)
   uint64_t rgb_w, rgb_b;        // (3,128), (3)
+  uint64_t fc1f_w, fc1f_b;      // (256,512)
+  uint64_t gvf_w, gvf_b;        // (128,704)
   // fp16 hi/lo tile images for the tensor-core path (see th_pack_weights)
-  uint64_t h_fc0, h_ar0, h_k0, h_k1, h_v, h_fc1, h_fc2, h_fc3m, h_f, h_view, h_t;
+  uint64_t h_fc0, h_ar0, h_k0, h_k1, h_v, h_fc1, h_fc2, h_fc3m, h_f, h_view, h_t, h_fc1f, h_gvf;
 };
-constexpr uint32_t PACK_MAGIC = 0x31574854u;
+constexpr uint32_t PACK_MAGIC = 0x32574854u;
 
 // Byte offset of the hi element (row, col) of a (rows, C) activation in tile-image
 // format; the lo element sits 16384 bytes further.

@@ -543,10 +543,10 @@ static int mlp_forward_tc(const MlpRun& run, const MlpBuffers& b, const PackedHe
     k_attn_mix<true><<<(unsigned)cdiv(P, 8), 256, 0, st>>>(b.kp, b.ks, b.x, b.xt, P, Pp, V);
   }
   TH_LAUNCHED();
-  if ((rc = gemm({seg_img(b.s, 256), seg_img(b.xt, 256)}, h.h_v, wf(run, h.v_b), b.net, true, 256, R, 0))) return rc;
+  // value embeds folded into fc_1 (no non-linearity between them): N1 = relu([S | XT] W_fc1f^T)
   float* n1 = b.x;      // X is dead after the mix
-  float* inter = b.xt;  // XT is dead after NET
-  if ((rc = gemm({seg_img(b.net, 256)}, h.h_fc1, wf(run, h.fc1_b), n1, true, 256, R, 1))) return rc;
+  float* inter = b.xt;  // XT is dead after N1
+  if ((rc = gemm({seg_img(b.s, 256), seg_img(b.xt, 256)}, h.h_fc1f, wf(run, h.fc1f_b), n1, true, 256, R, 1))) return rc;
   if ((rc = gemm({seg_img(n1, 256)}, h.h_fc2, wf(run, h.fc2_b), inter, true, 256, R, 1))) return rc;
   {
     GemmArgs g{};
@@ -562,17 +562,17 @@ static int mlp_forward_tc(const MlpRun& run, const MlpBuffers& b, const PackedHe
   }
   if ((rc = run_heads(run, o, nullptr, alpha, h, false, st))) return rc;
   if (run.alpha_only) return TH_OK;
-  float* f = b.s;      // S is dead after NET
   float* gbuf = b.kp;  // keys are dead after the mix
-  if ((rc = gemm({seg_img(inter, 256), in_seg(b.pix, PIX_LD, 384)}, h.h_f, wf(run, h.f_b), f, true, 256, R, 0)))
-    return rc;
   {
+    // feature_fc + rgb_res_0 folded into view_fc: G = relu([INTER | pix | viewdir] W_gvf^T)
     GemmSeg vd = seg_f32(b.vd, VD_LD, VD_LD, Pp);
     if (in_img) {
       vd = seg_img(b.vd, 64);
       vd.img_tile_mod = Pp / 128;
     }
-    if ((rc = gemm({seg_img(f, 256), vd}, h.h_view, wf(run, h.view_b), gbuf, true, 128, R, 1))) return rc;
+    if ((rc = gemm({seg_img(inter, 256), in_seg(b.pix, PIX_LD, 384), vd}, h.h_gvf, wf(run, h.gvf_b), gbuf, true, 128, R,
+                   1)))
+      return rc;
   }
   {
     GemmArgs g{};
