@@ -461,7 +461,23 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
     run.zero_rgb_if_transparent = zero_rgb;
     run.use_tensor_cores = use_tc;
     run.inputs_are_images = use_tc;
-    rc = mlp_forward(run, b, hdr, st);
+    // one layer-chained launch per chunk (mlp_chain.cu) unless TH_CHAIN=0 asks for the
+    // layer-at-a-time schedule; its scratch is the (otherwise unused) S/X/XT/NET/KP/KS block
+    static const int use_chain = [] {
+      const char* e = getenv("TH_CHAIN");
+      return e ? atoi(e) : 1;
+    }();
+    static int num_sms = 0;
+    if (!num_sms) {
+      int dev = 0;
+      TH_CUDA(cudaGetDevice(&dev));
+      TH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const size_t scratch_room = (size_t)Pp * V * (256 * 4 + 128 * 2) * 4;  // b.s ... b.ks are contiguous
+    if (use_tc && use_chain && chain_supported(V) && chain_scratch_bytes(P, V, num_sms) <= scratch_room)
+      rc = mlp_forward_chain(run, b, hdr, reinterpret_cast<unsigned char*>(b.s), nullptr, st);
+    else
+      rc = mlp_forward(run, b, hdr, st);
     if (rc) return rc;
   }
   return TH_OK;

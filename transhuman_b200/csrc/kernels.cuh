@@ -153,6 +153,14 @@ struct MlpRun {
 // Pp = pad_points(P): view stride of every buffer in `b`.
 int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& hdr_host, cudaStream_t st);
 
+// mlp_chain.cu: the same network as ONE launch per chunk (layer-chained persistent kernel;
+// inputs must be the feature kernel's tile images, V <= 3).  `scratch` is 1 KB aligned and
+// holds chain_scratch_bytes(P, V, sm count) bytes; `alpha` (Pp floats) may be nullptr.
+bool chain_supported(int V);
+size_t chain_scratch_bytes(int64_t P, int V, int num_sms);
+int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader& hdr_host, unsigned char* scratch,
+                      float* alpha, cudaStream_t st);
+
 // mlp_simt.cu: C[M,N] = act(sum_seg A_seg[M,K_seg] W[:, koff:koff+K_seg]^T + bias)
 // One K-segment of the A operand.  Either fp32 rows (`ptr`, `ld`), converted to
 // fp16 hi/lo on the fly, or -- tensor-core path only -- an activation already in

@@ -1,0 +1,727 @@
+// Layer-chained tcgen05 kernel for the per-point network (rows a9/a10), sm_100a.
+//
+// mlp_tc.cu runs the network one layer per launch: every activation makes a round
+// trip through HBM (55 KB per point) and the layers sit on the HBM roof.  This kernel
+// runs a whole PROGRAM of layers per launch.  The unit of work is 256 sample points
+// (128 per CTA of a 2-CTA cluster, all V views of them); a cluster walks its unit
+// through every job of the program -- one job = one layer applied to one view's
+// 128-row tile -- before it moves to the next unit, so that
+//   * activations between layers live in a small per-CTA scratch (768 KB) that is
+//     written by the epilogue's bulk stores and read back by the loader's bulk
+//     copies while it is still in L2 -- no HBM round trip, no second launch;
+//   * the cross-view attention needs no kernel of its own: the key embeds stay in
+//     TMEM, the 3x3 scores and their softmax are computed by the epilogue threads
+//     (one thread = one point), and the otherwise idle warps 0-7 mix X in place;
+//   * the alpha / rgb heads are dot products inside the fc_3 / fc_4 epilogues.
+// All synchronisation is CTA- or cluster-local (same rows stay on the same CTA):
+//   stage full/empty mbarriers (loader <-> MMA), tfull mbarriers (MMA -> epilogue),
+//   and monotonic shared-memory counters for epilogue -> MMA (TMEM reuse),
+//   epilogue -> loader (a stored activation may be loaded), scores -> mix -> loader.
+// The MMA scheme (fp16 hi/lo split, 3 products, cta_group::2, M = 256) and the tile
+// image format are those of mlp_tc.cu.
+#include <stdlib.h>
+
+#include "kernels.cuh"
+#include "tc_ptx.cuh"
+
+namespace th {
+namespace chain {
+using namespace tc;
+
+constexpr int NUM_THREADS = 448;  // warps 0-7 mix, 8 loader, 9 MMA issuer / relay, 10-13 epilogue
+constexpr int NSTAGE = 3;
+constexpr int STAGE_BYTES = 65536;  // A hi/lo (32 KB) + this CTA's half of B hi/lo (<= 32 KB)
+constexpr int MAX_SEG = 5, MAX_JOBS = 24;
+constexpr int EPI_LD = 36;
+constexpr uint32_t TILE_IMG = 2 * A_TILE_BYTES;       // one 128-row x 64-column hi/lo k-block
+constexpr uint32_t SCR_ACT = 4 * TILE_IMG;            // a 256-wide activation tile: 128 KB
+constexpr int CHAIN_MAX_V = 3;                        // V key embeds + one more must fit 512 TMEM columns
+// Per-CTA scratch for V views: slot A (S -> N1 -> INTER) and slot B (X -> XT -> G), V tiles each, then
+// the attention table (128 points x 16 floats).
+__host__ __device__ inline uint32_t scratch_stride(int V) { return 2u * (uint32_t)V * SCR_ACT + 128 * 16 * 4; }
+
+enum { EPI_IMG = 0, EPI_ROWS = 1, EPI_KEEP = 2, EPI_SCORES = 3, EPI_ALPHA = 4, EPI_RGB = 5 };
+
+struct Seg {
+  const unsigned char* img;  // chunk-level tile image, or nullptr = this CTA's scratch
+  int64_t tile_off;          // chunk images: row tile of point tile 0 (view * Pp / 128)
+  uint32_t scratch_off;
+  int32_t kbs;
+  int32_t dep;      // job (same unit) whose stored output this segment reads, -1 = chunk input
+  int32_t dep_mix;  // 1 = written by the mix warps, released per k-block
+};
+struct Job {
+  Seg seg[MAX_SEG];
+  const unsigned char* wimg;
+  const float* bias;
+  const float* bias2;       // EPI_SCORES: bias of the kept key embed
+  unsigned char* out_img;   // EPI_IMG: chunk-level image, or nullptr = scratch at out_off
+  float* out_rows;          // EPI_ROWS: (rows, N) fp32
+  int64_t out_tile_off;
+  uint32_t out_off;
+  int32_t nseg, nkb, N, relu, epi, tmem_col, wait_back, view;
+};
+struct Program {
+  Job job[MAX_JOBS];
+  unsigned char* scratch;
+  const float *afc_w, *afc_b, *rgb_w, *rgb_b;
+  float* alpha;  // (Pp) chunk-local alpha_raw
+  float* raw;
+  float* alpha_out;
+  const int32_t* dst_ids;
+  int64_t first, P;
+  int32_t njobs, num_units, V, has_mix, zero_rgb, alpha_only, kp_col;
+  int32_t ks_col[TH_MAX_VIEWS];
+};
+
+// ---- shared-memory counters (monotonic; one writer side, one spinning reader) ----
+__device__ __forceinline__ uint32_t ld_acquire_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_counter(uint32_t addr, uint32_t target, int what) {
+  const long long t0 = clock64();
+  while ((int32_t)(ld_acquire_u32(addr) - target) < 0) {
+    if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
+      printf("k_chain: counter wait timed out (block %d thread %d what %d target %u have %u)\n", blockIdx.x,
+             threadIdx.x, what, target, ld_acquire_u32(addr));
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void add_release_local(uint32_t addr) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void add_release_remote(uint32_t addr, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "red.release.cluster.shared::cluster.add.u32 [ra], 1;\n\t}" ::"r"(addr),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ uint4 ldcg16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldcg_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __half2 h = __floats2half2_rn(x, y);
+  float2 hf = __half22float2(h);
+  __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+  return make_float2(h.x + l.x, h.y + l.y);
+}
+
+constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 4 * 8192 + 2 * 256 * 4 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+    k_chain(const __grid_constant__ Program pg) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  unsigned char* s_stage = smem_raw + NSTAGE * STAGE_BYTES;                 // 4 x 8 KB epilogue staging
+  float* s_bias = reinterpret_cast<float*>(s_stage + 4 * 8192);             // 2 x 256
+  unsigned char* ctrl_ptr = reinterpret_cast<unsigned char*>(s_bias + 512);
+  const uint32_t ctrl = base + NSTAGE * STAGE_BYTES + 4 * 8192 + 2048;
+  const uint32_t bar_full = ctrl, bar_empty = ctrl + 24, bar_pfull = ctrl + 48, bar_tfull = ctrl + 72;
+  const uint32_t cnt_epi = ctrl + 96, cnt_mix = ctrl + 100, cnt_scores = ctrl + 104, cnt_job = ctrl + 128;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl_ptr + 88);
+  uint32_t* counters = reinterpret_cast<uint32_t*>(ctrl_ptr + 96);  // epi, mix, scores, pad[5], job[MAX_JOBS]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int njobs = pg.njobs, V = pg.V;
+  const uint32_t flip_on = (njobs & 1) ? 256u : 0u;  // odd programs alternate TMEM halves from unit to unit
+  unsigned char* scratch = pg.scratch + (size_t)blockIdx.x * scratch_stride(V);
+  const uint32_t scr_atab = 2u * (uint32_t)V * SCR_ACT;
+
+  if (tid == 0) {
+    if (base & 1023u) {
+      printf("k_chain: dynamic shared memory is not 1 KB aligned (%u)\n", base);
+      __trap();
+    }
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_pfull + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tfull + 8, 1);
+    for (int i = 0; i < 8 + MAX_JOBS; ++i) counters[i] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ===================== mix warps: XT_j = sum_i A[i][j] X_i, in place =====================
+    // (cross_transformer.py:144-146).  Same tile-image layout in and out, so the work is
+    // elementwise over 16-byte chunks: position = (row, physical chunk); a thread owns 4 rows.
+    if (pg.has_mix) {
+      const float* atab = reinterpret_cast<const float*>(scratch + scr_atab);
+      unsigned char* xbase = scratch + (size_t)V * SCR_ACT;  // slot B: X_v at v * SCR_ACT
+      int it = 0;
+      for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
+        if (lane == 0) wait_counter(cnt_scores, 4u * (uint32_t)(it + 1), 1);
+        __syncwarp();
+        fence_proxy_async_all();
+        float A[4][TH_MAX_VIEWS][TH_MAX_VIEWS];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int row = (tid >> 3) + 32 * i4;
+#pragma unroll
+          for (int i = 0; i < TH_MAX_VIEWS; ++i)
+#pragma unroll
+            for (int j = 0; j < TH_MAX_VIEWS; ++j)
+              A[i4][i][j] = (i < V && j < V) ? ldcg_f32(atab + row * 16 + i * TH_MAX_VIEWS + j) : 0.f;
+        }
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const uint32_t off = (uint32_t)kb * TILE_IMG + (uint32_t)((tid >> 3) + 32 * i4) * 128 + (tid & 7) * 16;
+            float2 x[TH_MAX_VIEWS][4];
+#pragma unroll
+            for (int i = 0; i < TH_MAX_VIEWS; ++i)
+              if (i < V) {
+                const uint4 h = ldcg16(xbase + (size_t)i * SCR_ACT + off);
+                const uint4 l = ldcg16(xbase + (size_t)i * SCR_ACT + off + A_TILE_BYTES);
+                x[i][0] = join2(h.x, l.x);
+                x[i][1] = join2(h.y, l.y);
+                x[i][2] = join2(h.z, l.z);
+                x[i][3] = join2(h.w, l.w);
+              }
+#pragma unroll
+            for (int j = 0; j < TH_MAX_VIEWS; ++j)
+              if (j < V) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float ox = 0.f, oy = 0.f;
+#pragma unroll
+                  for (int i = 0; i < TH_MAX_VIEWS; ++i)
+                    if (i < V) {
+                      ox = fmaf(A[i4][i][j], x[i][e].x, ox);
+                      oy = fmaf(A[i4][i][j], x[i][e].y, oy);
+                    }
+                  split2(ox, oy, hi[e], lo[e]);
+                }
+                unsigned char* dst = xbase + (size_t)j * SCR_ACT + off;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(dst + A_TILE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+          }
+          __threadfence();
+          fence_proxy_async_all();  // generic-proxy stores -> the loader's bulk (async-proxy) reads
+          __syncwarp();
+          if (lane == 0) add_release_local(cnt_mix);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== loader =====================
+    if (lane == 0) {
+      uint32_t kcount = 0;
+      int it = 0;
+      for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
+        const int64_t ptile = 2 * (int64_t)u + rank;
+        for (int j = 0; j < njobs; ++j) {
+          const Job& jb = pg.job[j];
+          const uint32_t half_b = (uint32_t)(jb.N / 2) * 128u, plane = (uint32_t)jb.N * 128u;
+          int kb = 0;
+          for (int sgi = 0; sgi < jb.nseg; ++sgi) {
+            const Seg& sg = jb.seg[sgi];
+            if (sg.dep >= 0) {
+              wait_counter(cnt_job + 4 * sg.dep, 4u * (uint32_t)(it + 1), 2);
+              fence_proxy_async_all();
+            }
+            for (int kk = 0; kk < sg.kbs; ++kk, ++kb, ++kcount) {
+              if (sg.dep_mix) {
+                wait_counter(cnt_mix, 8u * (uint32_t)(4 * it + kk + 1), 3);
+                fence_proxy_async_all();
+              }
+              const uint32_t s = kcount % NSTAGE, ph = (kcount / NSTAGE) & 1;
+              mbar_wait(bar_empty + 8 * s, ph ^ 1);
+              const uint32_t sa = base + s * STAGE_BYTES;
+              mbar_arrive_expect_tx(bar_full + 8 * s, TILE_IMG + 2 * half_b);
+              const unsigned char* src =
+                  sg.img ? sg.img + ((size_t)(sg.tile_off + ptile) * sg.kbs + kk) * TILE_IMG
+                         : scratch + sg.scratch_off + (size_t)kk * TILE_IMG;
+              bulk_g2s(sa, src, TILE_IMG, bar_full + 8 * s);
+              const unsigned char* w = jb.wimg + (size_t)kb * (2 * plane) + (size_t)rank * half_b;
+              bulk_g2s(sa + TILE_IMG, w, half_b, bar_full + 8 * s);
+              bulk_g2s(sa + TILE_IMG + half_b, w + plane, half_b, bar_full + 8 * s);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      if (rank == 0) {
+        // ===================== MMA issuer (leader CTA) =====================
+        uint32_t kcount = 0, G = 0;
+        int it = 0;
+        for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
+          const uint32_t flip = (it & 1) ? flip_on : 0u;
+          for (int j = 0; j < njobs; ++j, ++G) {
+            const Job& jb = pg.job[j];
+            if ((int32_t)(G - jb.wait_back) >= 0) wait_counter(cnt_epi, 8u * (G - jb.wait_back + 1), 4);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (((uint32_t)jb.tmem_col + flip) & 511u);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(jb.N >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+            const uint32_t half_b = (uint32_t)(jb.N / 2) * 128u;
+            for (int kb = 0; kb < jb.nkb; ++kb, ++kcount) {
+              const uint32_t s = kcount % NSTAGE, ph = (kcount / NSTAGE) & 1;
+              mbar_wait(bar_full + 8 * s, ph);
+              mbar_wait(bar_pfull + 8 * s, ph);
+              tc_fence_after();
+              const uint32_t sa = base + s * STAGE_BYTES;
+              const uint64_t d_ahi = umma_desc(sa), d_alo = umma_desc(sa + A_TILE_BYTES);
+              const uint64_t d_bhi = umma_desc(sa + TILE_IMG), d_blo = umma_desc(sa + TILE_IMG + half_b);
+#pragma unroll
+              for (int ks = 0; ks < BK / 16; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                umma_f16_2cta(d_tmem, d_ahi + adv, d_bhi + adv, idesc, (kb | ks) ? 1u : 0u);
+                umma_f16_2cta(d_tmem, d_alo + adv, d_bhi + adv, idesc, 1u);
+                umma_f16_2cta(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+              }
+              umma_commit_2cta(bar_empty + 8 * s);
+            }
+            umma_commit_2cta(bar_tfull + 8 * (G & 1));
+          }
+        }
+      } else {
+        // ===================== relay (peer CTA): forward "stage full" to the leader =====================
+        uint32_t kcount = 0;
+        for (int u = cluster_id; u < pg.num_units; u += nclusters)
+          for (int j = 0; j < njobs; ++j)
+            for (int kb = 0; kb < pg.job[j].nkb; ++kb, ++kcount) {
+              const uint32_t s = kcount % NSTAGE, ph = (kcount / NSTAGE) & 1;
+              mbar_wait(bar_full + 8 * s, ph);
+              mbar_arrive_remote(bar_pfull + 8 * s, 0);
+            }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;          // TMEM lane quadrant
+    const int et = q * 32 + lane;    // row inside the 128-row tile = epilogue thread index
+    unsigned char* stage_b = s_stage + q * 8192;
+    float* stage = reinterpret_cast<float*>(stage_b);
+    float* atab = reinterpret_cast<float*>(scratch + scr_atab) + et * 16;
+    float alpha_reg = 0.f;
+    uint32_t G = 0;
+    int it = 0;
+    for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
+      const uint32_t flip = (it & 1) ? flip_on : 0u;
+      const int64_t ptile = 2 * (int64_t)u + rank;
+      const int64_t pt = ptile * BM + et;  // chunk-local point of this thread (per-point jobs)
+      for (int j = 0; j < njobs; ++j, ++G) {
+        const Job& jb = pg.job[j];
+        const int N = jb.N, epi = jb.epi;
+        float* bias_s = s_bias + (G & 1) * 256;
+        // this job's bias -> shared memory (double buffered by job parity; the named barrier of EVERY
+        // job keeps a warp at most one job ahead of the slowest reader of the other buffer)
+        if (epi != EPI_KEEP) {
+          for (int c = et; c < N; c += 128) bias_s[c] = jb.bias ? __ldg(jb.bias + c) : 0.f;
+          if (epi == EPI_SCORES) bias_s[128 + et] = __ldg(jb.bias2 + et);
+        }
+        epi_bar();
+        mbar_wait(bar_tfull + 8 * (G & 1), (G >> 1) & 1);
+        tc_fence_after();
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t taddr = lane_addr + (((uint32_t)jb.tmem_col + flip) & 511u);
+        if (epi == EPI_IMG) {
+          unsigned char* out = jb.out_img ? jb.out_img + (size_t)(jb.out_tile_off + ptile) * (N / BK) * TILE_IMG
+                                          : scratch + jb.out_off;
+#pragma unroll 1
+          for (int kb = 0; kb < N / BK; ++kb) {
+            if (lane == 0) bulk_wait_read0();  // previous slabs have been read out of the staging buffer
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t v[32];
+              tmem_ld32(taddr + kb * BK + h * 32, v);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int jj = 0; jj < 32; jj += 8) {
+                float x[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  x[e] = __uint_as_float(v[jj + e]) + bias_s[kb * BK + h * 32 + jj + e];
+                  if (jb.relu) x[e] = fmaxf(x[e], 0.f);
+                }
+                uint4 hi, lo;
+                split2(x[0], x[1], hi.x, lo.x);
+                split2(x[2], x[3], hi.y, lo.y);
+                split2(x[4], x[5], hi.z, lo.z);
+                split2(x[6], x[7], hi.w, lo.w);
+                const int chunk = h * 4 + (jj >> 3);
+                const int off = lane * 128 + ((chunk ^ (et & 7)) << 4);
+                *reinterpret_cast<uint4*>(stage_b + off) = hi;
+                *reinterpret_cast<uint4*>(stage_b + 4096 + off) = lo;
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              unsigned char* dst = out + (size_t)kb * TILE_IMG + (size_t)q * 4096;
+              bulk_s2g(dst, smem_u32(stage_b), 4096);
+              bulk_s2g(dst + A_TILE_BYTES, smem_u32(stage_b + 4096), 4096);
+              bulk_commit();
+            }
+          }
+          if (lane == 0) {
+            bulk_wait_all0();  // the tile is in memory: the loader may fetch it for a later job
+            fence_proxy_async_all();
+            add_release_local(cnt_job + 4 * j);
+          }
+        } else if (epi == EPI_ROWS) {
+          const int64_t mbase = (jb.out_tile_off + ptile) * BM + q * 32;
+#pragma unroll 1
+          for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 4) {
+              float4 o;
+              o.x = __uint_as_float(v[jj + 0]) + bias_s[c0 + jj + 0];
+              o.y = __uint_as_float(v[jj + 1]) + bias_s[c0 + jj + 1];
+              o.z = __uint_as_float(v[jj + 2]) + bias_s[c0 + jj + 2];
+              o.w = __uint_as_float(v[jj + 3]) + bias_s[c0 + jj + 3];
+              if (jb.relu) {
+                o.x = fmaxf(o.x, 0.f);
+                o.y = fmaxf(o.y, 0.f);
+                o.z = fmaxf(o.z, 0.f);
+                o.w = fmaxf(o.w, 0.f);
+              }
+              *reinterpret_cast<float4*>(stage + lane * EPI_LD + jj) = o;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < 32; rr += 4) {
+              const int row = rr + (lane >> 3);
+              const float4 o = *reinterpret_cast<const float4*>(stage + row * EPI_LD + (lane & 7) * 4);
+              *reinterpret_cast<float4*>(jb.out_rows + (mbase + row) * N + c0 + (lane & 7) * 4) = o;
+            }
+            __syncwarp();
+          }
+        } else if (epi == EPI_SCORES) {
+          // A[i][j] = (KP_i + b0) . (KS_j + b1) / sqrt(128) for i = this job's view; the key embeds of
+          // every view j sit in TMEM (EPI_KEEP jobs).  One thread = one point, no shuffles.
+          float sc[TH_MAX_VIEWS];
+#pragma unroll
+          for (int jv = 0; jv < TH_MAX_VIEWS; ++jv) sc[jv] = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t kp[32];
+            tmem_ld32(taddr + c0, kp);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int e = 0; e < 32; ++e) kp[e] = __float_as_uint(__uint_as_float(kp[e]) + bias_s[c0 + e]);
+#pragma unroll
+            for (int jv = 0; jv < TH_MAX_VIEWS; ++jv)
+              if (jv < V) {
+                uint32_t ks[32];
+                tmem_ld32(lane_addr + (((uint32_t)pg.ks_col[jv] + flip) & 511u) + c0, ks);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                  sc[jv] = fmaf(__uint_as_float(kp[e]), __uint_as_float(ks[e]) + bias_s[128 + c0 + e], sc[jv]);
+              }
+          }
+          const int i = jb.view;
+#pragma unroll
+          for (int jv = 0; jv < TH_MAX_VIEWS; ++jv)
+            if (jv < V) atab[i * TH_MAX_VIEWS + jv] = __fdiv_rn(sc[jv], 11.313708498984761f);
+          if (i == V - 1) {
+            // softmax over i for every j (dim=1 of (P, V_i, V_j), cross_transformer.py:144)
+            for (int jv = 0; jv < V; ++jv) {
+              float a[TH_MAX_VIEWS], m = -3.4e38f, sum = 0.f;
+              for (int ii = 0; ii < V; ++ii) {
+                a[ii] = atab[ii * TH_MAX_VIEWS + jv];
+                m = fmaxf(m, a[ii]);
+              }
+              for (int ii = 0; ii < V; ++ii) {
+                a[ii] = expf(a[ii] - m);
+                sum += a[ii];
+              }
+              for (int ii = 0; ii < V; ++ii) atab[ii * TH_MAX_VIEWS + jv] = __fdiv_rn(a[ii], sum);
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) add_release_local(cnt_scores);
+          }
+        } else if (epi == EPI_ALPHA) {
+          // alpha = relu(O) . alpha_fc + b (cross_transformer.py:324-328): O never leaves the SM
+          float acc = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              acc = fmaf(fmaxf(__uint_as_float(v[e]) + bias_s[c0 + e], 0.f), __ldg(pg.afc_w + c0 + e), acc);
+          }
+          alpha_reg = acc + __ldg(pg.afc_b);
+          if (pt < pg.P) {
+            if (pg.alpha) pg.alpha[pt] = alpha_reg;
+            if (pg.alpha_only) {
+              const int64_t dst = pg.dst_ids ? (int64_t)pg.dst_ids[pg.first + pt] : pg.first + pt;
+              if (pg.alpha_out) pg.alpha_out[dst] = alpha_reg;
+              if (pg.raw) reinterpret_cast<float4*>(pg.raw)[dst] = make_float4(0.f, 0.f, 0.f, alpha_reg);
+            }
+          }
+        } else if (epi == EPI_RGB) {
+          // rgb = relu(T) rgb_fc^T + b (cross_transformer.py:349-351); raw = (rgb, alpha)
+          float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float t = fmaxf(__uint_as_float(v[e]) + bias_s[c0 + e], 0.f);
+              o0 = fmaf(t, __ldg(pg.rgb_w + c0 + e), o0);
+              o1 = fmaf(t, __ldg(pg.rgb_w + 128 + c0 + e), o1);
+              o2 = fmaf(t, __ldg(pg.rgb_w + 256 + c0 + e), o2);
+            }
+          }
+          if (pt < pg.P) {
+            o0 += __ldg(pg.rgb_b);
+            o1 += __ldg(pg.rgb_b + 1);
+            o2 += __ldg(pg.rgb_b + 2);
+            if (pg.zero_rgb && !(alpha_reg > 0.f)) o0 = o1 = o2 = 0.f;
+            const int64_t dst = pg.dst_ids ? (int64_t)pg.dst_ids[pg.first + pt] : pg.first + pt;
+            reinterpret_cast<float4*>(pg.raw)[dst] = make_float4(o0, o1, o2, alpha_reg);
+          }
+        }
+        // this warp is done with the accumulator of job G
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0)
+            add_release_local(cnt_epi);
+          else
+            add_release_remote(cnt_epi, 0);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side: program construction
+// ---------------------------------------------------------------------------
+struct Builder {
+  Program pg{};
+  int V;
+  int64_t tiles_per_view;  // Pp / 128
+  Builder(int V_, int64_t Pp) : V(V_), tiles_per_view(Pp / 128) {
+    pg.V = V_;
+    pg.kp_col = 128 * V_;
+    for (int v = 0; v < V_; ++v) pg.ks_col[v] = 128 * v;
+  }
+  uint32_t slotA(int v) const { return (uint32_t)v * SCR_ACT; }
+  uint32_t slotB(int v) const { return (uint32_t)(V + v) * SCR_ACT; }
+  Seg in_view(const float* buf, int C, int v) const {  // chunk-level image of a (V*Pp, C) activation
+    Seg s{};
+    s.img = reinterpret_cast<const unsigned char*>(buf);
+    s.tile_off = v * tiles_per_view;
+    s.kbs = C / 64;
+    s.dep = -1;
+    return s;
+  }
+  Seg in_point(const float* buf, int C) const { return in_view(buf, C, 0); }
+  static Seg scr(uint32_t off, int C, int dep, int dep_mix = 0) {
+    Seg s{};
+    s.scratch_off = off;
+    s.kbs = C / 64;
+    s.dep = dep;
+    s.dep_mix = dep_mix;
+    return s;
+  }
+  // returns the job index
+  int add(std::initializer_list<Seg> segs, const unsigned char* wimg, const float* bias, int N, int relu, int epi,
+          uint32_t out_off, int view = 0, int col = -1, int wait_back = 2) {
+    const int j = pg.njobs++;
+    Job& jb = pg.job[j];
+    jb = Job{};
+    for (const Seg& s : segs) {
+      jb.seg[jb.nseg++] = s;
+      jb.nkb += s.kbs;
+    }
+    jb.wimg = wimg;
+    jb.bias = bias;
+    jb.N = N;
+    jb.relu = relu;
+    jb.epi = epi;
+    jb.out_off = out_off;
+    jb.view = view;
+    jb.tmem_col = col >= 0 ? col : (j & 1) * 256;
+    jb.wait_back = wait_back;
+    return j;
+  }
+};
+
+}  // namespace chain
+
+// Bytes of scratch one launch over P points touches (2 CTAs per 256-point unit, at most one CTA per SM).
+size_t chain_scratch_bytes(int64_t P, int V, int num_sms) {
+  const int64_t units = pad_points(P) / 256;
+  const int64_t ctas = 2 * units < num_sms ? 2 * units : num_sms;
+  return (size_t)ctas * chain::scratch_stride(V);
+}
+bool chain_supported(int V) { return V >= 1 && V <= chain::CHAIN_MAX_V; }
+
+// The whole per-point network for one chunk in ONE launch.  Inputs (rep, pix, pix_mean, vd)
+// are the tile images the feature kernel wrote; `scratch` holds chain_scratch_bytes().
+int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader& h, unsigned char* scratch,
+                      float* alpha, cudaStream_t st) {
+  using namespace chain;
+  ProfScope prof_(PROF_GEMM, st);
+  const int64_t P = run.P, Pp = pad_points(P);
+  const int V = run.V;
+  if (!chain_supported(V)) {
+    set_error("mlp_forward_chain: V=%d needs more than 512 TMEM columns for the key embeds", V);
+    return TH_EUNSUPPORTED;
+  }
+  auto wimg = [&](uint64_t off) { return run.weights + off; };
+  auto wf = [&](uint64_t off) { return reinterpret_cast<const float*>(run.weights + off); };
+  Builder B(V, Pp);
+  int j_s[TH_MAX_VIEWS], j_x[TH_MAX_VIEWS], j_n1[TH_MAX_VIEWS], j_int[TH_MAX_VIEWS], j_g[TH_MAX_VIEWS];
+  // front: X_v = relu(alpha_res_0 pix_v) -> slot B ; S_v = relu(fc_0 rep_v) -> slot A
+  for (int v = 0; v < V; ++v)
+    j_x[v] = B.add({B.in_view(b.pix, PIX_LD, v)}, wimg(h.h_ar0), wf(h.ar0_b), 256, 1, EPI_IMG, B.slotB(v));
+  for (int v = 0; v < V; ++v)
+    j_s[v] = B.add({B.in_view(b.rep, REP_LD, v)}, wimg(h.h_fc0), wf(h.fc0_b), 256, 1, EPI_IMG, B.slotA(v));
+  // key embeds: KS_v = key_embed_1 S_v stays in TMEM; KP_v = key_embed_0 X_v is consumed by the score epilogue
+  for (int v = 0; v < V; ++v)
+    B.add({Builder::scr(B.slotA(v), 256, j_s[v])}, wimg(h.h_k1), nullptr, 128, 0, EPI_KEEP, 0, v, 128 * v, 2);
+  for (int v = 0; v < V; ++v) {
+    const int j = B.add({Builder::scr(B.slotB(v), 256, j_x[v])}, wimg(h.h_k0), wf(h.k0_b), 128, 0, EPI_SCORES,
+                        0, v, 128 * V, v == 0 ? 2 : 1);
+    B.pg.job[j].bias2 = wf(h.k1_b);
+  }
+  B.pg.has_mix = 1;
+  // N1_v = relu([S_v | XT_v] W_fc1f^T) in place of S_v; INTER_v = relu(fc_2 N1_v) in place again
+  for (int v = 0; v < V; ++v)
+    j_n1[v] = B.add({Builder::scr(B.slotA(v), 256, -1), Builder::scr(B.slotB(v), 256, -1, 1)},
+                    wimg(h.h_fc1f), wf(h.fc1f_b), 256, 1, EPI_IMG, B.slotA(v), v, -1, v == 0 ? 1 : 2);
+  for (int v = 0; v < V; ++v)
+    j_int[v] = B.add({Builder::scr(B.slotA(v), 256, j_n1[v])}, wimg(h.h_fc2), wf(h.fc2_b), 256, 1, EPI_IMG,
+                     B.slotA(v));
+  auto add_fc3 = [&]() {
+    const int j = B.pg.njobs++;
+    Job& jb = B.pg.job[j];
+    jb = Job{};
+    for (int v = 0; v < V; ++v) {
+      jb.seg[jb.nseg++] = Builder::scr(B.slotA(v), 256, j_int[v]);
+      jb.nkb += 4;
+    }
+    jb.wimg = wimg(h.h_fc3m);
+    jb.bias = wf(h.fc3m_b);
+    jb.N = 256;
+    jb.relu = 1;
+    jb.epi = EPI_ALPHA;
+    jb.tmem_col = (j & 1) * 256;
+    jb.wait_back = 2;
+  };
+  if (run.alpha_only) {
+    add_fc3();
+  } else {
+    auto add_gvf = [&](int v) {
+      j_g[v] = B.add({Builder::scr(B.slotA(v), 256, j_int[v]), B.in_view(b.pix, PIX_LD, v), B.in_point(b.vd, 64)},
+                     wimg(h.h_gvf), wf(h.gvf_b), 128, 1, EPI_IMG, B.slotB(v));
+    };
+    for (int v = 0; v + 1 < V; ++v) add_gvf(v);
+    add_fc3();
+    add_gvf(V - 1);
+    {  // T = relu([mean pix | G_0 | ... ] W_t^T): the chunk input first, the freshest G last
+      const int j = B.pg.njobs++;
+      Job& jb = B.pg.job[j];
+      jb = Job{};
+      for (int v = 0; v < V; ++v) {
+        jb.seg[jb.nseg++] = Builder::scr(B.slotB(v), 128, j_g[v]);
+        jb.nkb += 2;
+      }
+      jb.seg[jb.nseg++] = B.in_point(b.pix_mean, PIX_LD);
+      jb.nkb += PIX_LD / 64;
+      jb.wimg = wimg(h.h_t);
+      jb.bias = wf(h.t_b);
+      jb.N = 128;
+      jb.relu = 1;
+      jb.epi = EPI_RGB;
+      jb.tmem_col = (j & 1) * 256;
+      jb.wait_back = 2;
+    }
+  }
+  Program& pg = B.pg;
+  pg.scratch = scratch;
+  pg.afc_w = wf(h.afc_w);
+  pg.afc_b = wf(h.afc_b);
+  pg.rgb_w = wf(h.rgb_w);
+  pg.rgb_b = wf(h.rgb_b);
+  pg.alpha = alpha;
+  pg.raw = run.raw;
+  pg.alpha_out = run.alpha_out;
+  pg.dst_ids = run.dst_ids;
+  pg.first = run.first;
+  pg.P = P;
+  pg.zero_rgb = run.zero_rgb_if_transparent;
+  pg.alpha_only = run.alpha_only;
+  pg.num_units = (int)(Pp / 256);
+
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    TH_CUDA(cudaGetDevice(&dev));
+    TH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  static bool cfg = false;
+  if (!cfg) {
+    TH_CUDA(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    cfg = true;
+  }
+  const int nclusters = pg.num_units < num_sms / 2 ? pg.num_units : num_sms / 2;
+  k_chain<<<2 * nclusters, NUM_THREADS, SMEM_BYTES, st>>>(pg);
+  TH_LAUNCHED();
+  return TH_OK;
+}
+
+}  // namespace th
