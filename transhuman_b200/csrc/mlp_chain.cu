@@ -21,6 +21,8 @@
 // image format are those of mlp_tc.cu.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
 
@@ -28,19 +30,21 @@ namespace th {
 namespace chain {
 using namespace tc;
 
-constexpr int NUM_THREADS = 448;  // warps 0-7 mix, 8 loader, 9 MMA issuer / relay, 10-13 epilogue
+// 16 warps = 4 per scheduler, so every thread may use 128 registers:
+// warps 0-5 mix, 6 loader, 7 MMA issuer / relay, 8-15 epilogue (2 per TMEM lane quadrant)
+constexpr int NUM_THREADS = 512;
+constexpr int MIX_THREADS = 192, LOADER_WARP = 6, MMA_WARP = 7, EPI_WARP0 = 8;
+constexpr int EPI_WARPS = 8;
 constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = 65536;  // A hi/lo (32 KB) + this CTA's half of B hi/lo (<= 32 KB)
 constexpr int MAX_SEG = 5, MAX_JOBS = 24;
-constexpr int EPI_LD = 36;
 constexpr uint32_t TILE_IMG = 2 * A_TILE_BYTES;       // one 128-row x 64-column hi/lo k-block
 constexpr uint32_t SCR_ACT = 4 * TILE_IMG;            // a 256-wide activation tile: 128 KB
 constexpr int CHAIN_MAX_V = 3;                        // V key embeds + one more must fit 512 TMEM columns
-// Per-CTA scratch for V views: slot A (S -> N1 -> INTER) and slot B (X -> XT -> G), V tiles each, then
-// the attention table (128 points x 16 floats).
-__host__ __device__ inline uint32_t scratch_stride(int V) { return 2u * (uint32_t)V * SCR_ACT + 128 * 16 * 4; }
+// Per-CTA scratch for V views: slot A (S -> N1 -> INTER) and slot B (X -> XT -> G), V tiles each.
+__host__ __device__ inline uint32_t scratch_stride(int V) { return 2u * (uint32_t)V * SCR_ACT; }
 
-enum { EPI_IMG = 0, EPI_ROWS = 1, EPI_KEEP = 2, EPI_SCORES = 3, EPI_ALPHA = 4, EPI_RGB = 5 };
+enum { EPI_IMG = 0, EPI_KEEP = 2, EPI_SCORES = 3, EPI_ALPHA = 4, EPI_RGB = 5 };
 
 struct Seg {
   const unsigned char* img;  // chunk-level tile image, or nullptr = this CTA's scratch
@@ -55,11 +59,9 @@ struct Job {
   const unsigned char* wimg;
   const float* bias;
   const float* bias2;       // EPI_SCORES: bias of the kept key embed
-  unsigned char* out_img;   // EPI_IMG: chunk-level image, or nullptr = scratch at out_off
-  float* out_rows;          // EPI_ROWS: (rows, N) fp32
-  int64_t out_tile_off;
-  uint32_t out_off;
+  uint32_t out_off;         // EPI_IMG: destination inside the CTA's scratch
   int32_t nseg, nkb, N, relu, epi, tmem_col, wait_back, view;
+  int32_t signal_now;  // EPI_IMG: the next job reads this tile, publish it at once
 };
 struct Program {
   Job job[MAX_JOBS];
@@ -72,6 +74,7 @@ struct Program {
   int64_t first, P;
   int32_t njobs, num_units, V, has_mix, zero_rgb, alpha_only, kp_col;
   int32_t ks_col[TH_MAX_VIEWS];
+  unsigned long long* stats;  // TH_CHAIN_STATS=1: per-CTA wait-time counters (cycles), else nullptr
 };
 
 // ---- shared-memory counters (monotonic; one writer side, one spinning reader) ----
@@ -80,9 +83,13 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(uint32_t addr) {
   asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ void wait_counter(uint32_t addr, uint32_t target, int what) {
+// `nap` nanoseconds between polls: a spinning single thread otherwise competes for issue slots with
+// the epilogue warp that shares its scheduler.
+__device__ __forceinline__ void wait_counter(uint32_t addr, uint32_t target, int what, unsigned nap = 32) {
+  if ((int32_t)(ld_acquire_u32(addr) - target) >= 0) return;
   const long long t0 = clock64();
   while ((int32_t)(ld_acquire_u32(addr) - target) < 0) {
+    __nanosleep(nap);
     if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
       printf("k_chain: counter wait timed out (block %d thread %d what %d target %u have %u)\n", blockIdx.x,
              threadIdx.x, what, target, ld_acquire_u32(addr));
@@ -102,16 +109,31 @@ __device__ __forceinline__ void add_release_remote(uint32_t addr, uint32_t cta) 
       : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// scratch accesses of the mix warps: never allocate in L1 (the tiles are rewritten by the async
+// proxy every unit, L1 is not coherent with it), keep them in L2 (evict last)
 __device__ __forceinline__ uint4 ldcg16(const void* p) {
   uint4 v;
-  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(L2_EVICT_LAST));
   return v;
+}
+__device__ __forceinline__ void st16_keep(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w), "l"(L2_EVICT_LAST)
+               : "memory");
 }
 __device__ __forceinline__ float ldcg_f32(const float* p) {
   float v;
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
+}
+// 32-byte store of 16 fp16 (two 16-byte chunks of one 32-byte sector) that stays in L2
+__device__ __forceinline__ void st32_keep(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(p),
+               "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(L2_EVICT_LAST)
+               : "memory");
 }
 __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
   __half2 h = __floats2half2_rn(x, y);
@@ -126,16 +148,17 @@ __device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
   return make_float2(h.x + l.x, h.y + l.y);
 }
 
-constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 4 * 8192 + 2 * 256 * 4 + 256;
+constexpr int ATAB_LD = 9;  // attention table row stride (floats): V x V <= 9 entries per point
+constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 2 * 256 * 4 + 128 * ATAB_LD * 4 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     k_chain(const __grid_constant__ Program pg) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
-  unsigned char* s_stage = smem_raw + NSTAGE * STAGE_BYTES;                 // 4 x 8 KB epilogue staging
-  float* s_bias = reinterpret_cast<float*>(s_stage + 4 * 8192);             // 2 x 256
-  unsigned char* ctrl_ptr = reinterpret_cast<unsigned char*>(s_bias + 512);
-  const uint32_t ctrl = base + NSTAGE * STAGE_BYTES + 4 * 8192 + 2048;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + NSTAGE * STAGE_BYTES);  // 2 x 256
+  float* s_atab = s_bias + 512;                                               // 128 x ATAB_LD
+  unsigned char* ctrl_ptr = reinterpret_cast<unsigned char*>(s_atab + 128 * ATAB_LD);
+  const uint32_t ctrl = base + NSTAGE * STAGE_BYTES + 2048 + 128 * ATAB_LD * 4;
   const uint32_t bar_full = ctrl, bar_empty = ctrl + 24, bar_pfull = ctrl + 48, bar_tfull = ctrl + 72;
   const uint32_t cnt_epi = ctrl + 96, cnt_mix = ctrl + 100, cnt_scores = ctrl + 104, cnt_job = ctrl + 128;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl_ptr + 88);
@@ -147,7 +170,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   const int njobs = pg.njobs, V = pg.V;
   const uint32_t flip_on = (njobs & 1) ? 256u : 0u;  // odd programs alternate TMEM halves from unit to unit
   unsigned char* scratch = pg.scratch + (size_t)blockIdx.x * scratch_stride(V);
-  const uint32_t scr_atab = 2u * (uint32_t)V * SCR_ACT;
 
   if (tid == 0) {
     if (base & 1023u) {
@@ -164,7 +186,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     for (int i = 0; i < 8 + MAX_JOBS; ++i) counters[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(512u)
                  : "memory");
@@ -175,73 +197,100 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // optional wait-time accounting (one slot per question; cycles summed over the launch)
+  unsigned long long* stats = pg.stats ? pg.stats + (size_t)blockIdx.x * 32 : nullptr;
+  long long tw[6] = {0, 0, 0, 0, 0, 0};
+#define TH_TIMED(slot, stmt)            \
+  do {                                  \
+    if (stats) {                        \
+      const long long t_ = clock64();   \
+      stmt;                             \
+      tw[slot] += clock64() - t_;       \
+    } else {                            \
+      stmt;                             \
+    }                                   \
+  } while (0)
+  const long long t_begin = clock64();
 
-  if (warp < 8) {
+  if (warp < LOADER_WARP) {
     // ===================== mix warps: XT_j = sum_i A[i][j] X_i, in place =====================
     // (cross_transformer.py:144-146).  Same tile-image layout in and out, so the work is
     // elementwise over 16-byte chunks: position = (row, physical chunk); a thread owns 4 rows.
     if (pg.has_mix) {
-      const float* atab = reinterpret_cast<const float*>(scratch + scr_atab);
       unsigned char* xbase = scratch + (size_t)V * SCR_ACT;  // slot B: X_v at v * SCR_ACT
       int it = 0;
       for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
-        if (lane == 0) wait_counter(cnt_scores, 4u * (uint32_t)(it + 1), 1);
-        __syncwarp();
+        TH_TIMED(0, if (lane == 0) wait_counter(cnt_scores, 4u * (uint32_t)(it + 1), 1, 256); __syncwarp());
+        const long long t_mix = clock64();
         fence_proxy_async_all();
-        float A[4][TH_MAX_VIEWS][TH_MAX_VIEWS];
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const int row = (tid >> 3) + 32 * i4;
-#pragma unroll
-          for (int i = 0; i < TH_MAX_VIEWS; ++i)
-#pragma unroll
-            for (int j = 0; j < TH_MAX_VIEWS; ++j)
-              A[i4][i][j] = (i < V && j < V) ? ldcg_f32(atab + row * 16 + i * TH_MAX_VIEWS + j) : 0.f;
-        }
 #pragma unroll 1
         for (int kb = 0; kb < 4; ++kb) {
+          // software pipelined over positions: the next position's 2V loads are in flight while
+          // this one is mixed and stored (positions are disjoint, so the order is free)
+          uint4 ch[CHAIN_MAX_V], cl[CHAIN_MAX_V], nh[CHAIN_MAX_V], nl[CHAIN_MAX_V];
+          auto fetch = [&](int pos, uint4 (&h)[CHAIN_MAX_V], uint4 (&l)[CHAIN_MAX_V]) {
+            const uint32_t off = (uint32_t)kb * TILE_IMG + (uint32_t)(pos >> 3) * 128 + (pos & 7) * 16;
 #pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const uint32_t off = (uint32_t)kb * TILE_IMG + (uint32_t)((tid >> 3) + 32 * i4) * 128 + (tid & 7) * 16;
-            float2 x[TH_MAX_VIEWS][4];
-#pragma unroll
-            for (int i = 0; i < TH_MAX_VIEWS; ++i)
+            for (int i = 0; i < CHAIN_MAX_V; ++i)
               if (i < V) {
-                const uint4 h = ldcg16(xbase + (size_t)i * SCR_ACT + off);
-                const uint4 l = ldcg16(xbase + (size_t)i * SCR_ACT + off + A_TILE_BYTES);
-                x[i][0] = join2(h.x, l.x);
-                x[i][1] = join2(h.y, l.y);
-                x[i][2] = join2(h.z, l.z);
-                x[i][3] = join2(h.w, l.w);
+                h[i] = ldcg16(xbase + (size_t)i * SCR_ACT + off);
+                l[i] = ldcg16(xbase + (size_t)i * SCR_ACT + off + A_TILE_BYTES);
               }
+          };
+          fetch(tid, ch, cl);
+#pragma unroll 1
+          for (int pos = tid; pos < 1024; pos += MIX_THREADS) {
+            const bool more = pos + MIX_THREADS < 1024;
+            if (more) fetch(pos + MIX_THREADS, nh, nl);
+            const int row = pos >> 3;
+            const uint32_t off = (uint32_t)kb * TILE_IMG + (uint32_t)row * 128 + (pos & 7) * 16;
+            float2 x[CHAIN_MAX_V][4];
 #pragma unroll
-            for (int j = 0; j < TH_MAX_VIEWS; ++j)
+            for (int i = 0; i < CHAIN_MAX_V; ++i)
+              if (i < V) {
+                x[i][0] = join2(ch[i].x, cl[i].x);
+                x[i][1] = join2(ch[i].y, cl[i].y);
+                x[i][2] = join2(ch[i].z, cl[i].z);
+                x[i][3] = join2(ch[i].w, cl[i].w);
+              }
+            const float* A = s_atab + row * ATAB_LD;
+#pragma unroll
+            for (int j = 0; j < CHAIN_MAX_V; ++j)
               if (j < V) {
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   float ox = 0.f, oy = 0.f;
 #pragma unroll
-                  for (int i = 0; i < TH_MAX_VIEWS; ++i)
+                  for (int i = 0; i < CHAIN_MAX_V; ++i)
                     if (i < V) {
-                      ox = fmaf(A[i4][i][j], x[i][e].x, ox);
-                      oy = fmaf(A[i4][i][j], x[i][e].y, oy);
+                      const float a = A[i * V + j];
+                      ox = fmaf(a, x[i][e].x, ox);
+                      oy = fmaf(a, x[i][e].y, oy);
                     }
                   split2(ox, oy, hi[e], lo[e]);
                 }
                 unsigned char* dst = xbase + (size_t)j * SCR_ACT + off;
-                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(dst + A_TILE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                st16_keep(dst, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                st16_keep(dst + A_TILE_BYTES, make_uint4(lo[0], lo[1], lo[2], lo[3]));
               }
+            if (more) {
+#pragma unroll
+              for (int i = 0; i < CHAIN_MAX_V; ++i) {
+                ch[i] = nh[i];
+                cl[i] = nl[i];
+              }
+            }
           }
           __threadfence();
           fence_proxy_async_all();  // generic-proxy stores -> the loader's bulk (async-proxy) reads
           __syncwarp();
           if (lane == 0) add_release_local(cnt_mix);
         }
+        if (stats) tw[1] += clock64() - t_mix;
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == LOADER_WARP) {
     // ===================== loader =====================
     if (lane == 0) {
       uint32_t kcount = 0;
@@ -255,31 +304,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           for (int sgi = 0; sgi < jb.nseg; ++sgi) {
             const Seg& sg = jb.seg[sgi];
             if (sg.dep >= 0) {
-              wait_counter(cnt_job + 4 * sg.dep, 4u * (uint32_t)(it + 1), 2);
+              TH_TIMED(0, wait_counter(cnt_job + 4 * sg.dep, (uint32_t)EPI_WARPS * (uint32_t)(it + 1), 2));
               fence_proxy_async_all();
             }
             for (int kk = 0; kk < sg.kbs; ++kk, ++kb, ++kcount) {
               if (sg.dep_mix) {
-                wait_counter(cnt_mix, 8u * (uint32_t)(4 * it + kk + 1), 3);
+                TH_TIMED(1, wait_counter(cnt_mix, (uint32_t)(MIX_THREADS / 32) * (uint32_t)(4 * it + kk + 1), 3));
                 fence_proxy_async_all();
               }
               const uint32_t s = kcount % NSTAGE, ph = (kcount / NSTAGE) & 1;
-              mbar_wait(bar_empty + 8 * s, ph ^ 1);
+              TH_TIMED(2, mbar_wait(bar_empty + 8 * s, ph ^ 1));
               const uint32_t sa = base + s * STAGE_BYTES;
               mbar_arrive_expect_tx(bar_full + 8 * s, TILE_IMG + 2 * half_b);
               const unsigned char* src =
                   sg.img ? sg.img + ((size_t)(sg.tile_off + ptile) * sg.kbs + kk) * TILE_IMG
                          : scratch + sg.scratch_off + (size_t)kk * TILE_IMG;
-              bulk_g2s(sa, src, TILE_IMG, bar_full + 8 * s);
+              // chunk inputs stream through L2 once (evict first); scratch tiles and weights are the
+              // working set that must stay resident (evict last)
+              bulk_g2s_hint(sa, src, TILE_IMG, bar_full + 8 * s, sg.img ? L2_EVICT_FIRST : L2_EVICT_LAST);
               const unsigned char* w = jb.wimg + (size_t)kb * (2 * plane) + (size_t)rank * half_b;
-              bulk_g2s(sa + TILE_IMG, w, half_b, bar_full + 8 * s);
-              bulk_g2s(sa + TILE_IMG + half_b, w + plane, half_b, bar_full + 8 * s);
+              bulk_g2s_hint(sa + TILE_IMG, w, half_b, bar_full + 8 * s, L2_EVICT_LAST);
+              bulk_g2s_hint(sa + TILE_IMG + half_b, w + plane, half_b, bar_full + 8 * s, L2_EVICT_LAST);
             }
           }
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == MMA_WARP) {
     if (lane == 0) {
       if (rank == 0) {
         // ===================== MMA issuer (leader CTA) =====================
@@ -289,15 +340,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           const uint32_t flip = (it & 1) ? flip_on : 0u;
           for (int j = 0; j < njobs; ++j, ++G) {
             const Job& jb = pg.job[j];
-            if ((int32_t)(G - jb.wait_back) >= 0) wait_counter(cnt_epi, 8u * (G - jb.wait_back + 1), 4);
+            if ((int32_t)(G - jb.wait_back) >= 0) TH_TIMED(0, wait_counter(cnt_epi, 2u * EPI_WARPS * (G - jb.wait_back + 1), 4, 20));
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (((uint32_t)jb.tmem_col + flip) & 511u);
             const uint32_t idesc = (1u << 4) | ((uint32_t)(jb.N >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
             const uint32_t half_b = (uint32_t)(jb.N / 2) * 128u;
             for (int kb = 0; kb < jb.nkb; ++kb, ++kcount) {
               const uint32_t s = kcount % NSTAGE, ph = (kcount / NSTAGE) & 1;
-              mbar_wait(bar_full + 8 * s, ph);
-              mbar_wait(bar_pfull + 8 * s, ph);
+              TH_TIMED(1, mbar_wait(bar_full + 8 * s, ph));
+              TH_TIMED(2, mbar_wait(bar_pfull + 8 * s, ph));
               tc_fence_after();
               const uint32_t sa = base + s * STAGE_BYTES;
               const uint64_t d_ahi = umma_desc(sa), d_alo = umma_desc(sa + A_TILE_BYTES);
@@ -328,12 +379,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     }
   } else {
     // ===================== epilogue =====================
+    // Two warps per TMEM lane quadrant: group g takes half of the accumulator's columns of an image
+    // job; the per-point epilogues (scores, heads) are group 0's.
     const int q = warp & 3;          // TMEM lane quadrant
-    const int et = q * 32 + lane;    // row inside the 128-row tile = epilogue thread index
-    unsigned char* stage_b = s_stage + q * 8192;
-    float* stage = reinterpret_cast<float*>(stage_b);
-    float* atab = reinterpret_cast<float*>(scratch + scr_atab) + et * 16;
+    const int grp = (warp - EPI_WARP0) >> 2;
+    const int et = q * 32 + lane;    // row inside the 128-row tile
+    float* atab = s_atab + et * ATAB_LD;
     float alpha_reg = 0.f;
+    int pending_job = -1;  // image job whose "stored" signal is still owed
     uint32_t G = 0;
     int it = 0;
     for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
@@ -347,90 +400,79 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         // this job's bias -> shared memory (double buffered by job parity; the named barrier of EVERY
         // job keeps a warp at most one job ahead of the slowest reader of the other buffer)
         if (epi != EPI_KEEP) {
-          for (int c = et; c < N; c += 128) bias_s[c] = jb.bias ? __ldg(jb.bias + c) : 0.f;
-          if (epi == EPI_SCORES) bias_s[128 + et] = __ldg(jb.bias2 + et);
+          for (int c = grp * 128 + et; c < N; c += 256) bias_s[c] = jb.bias ? __ldg(jb.bias + c) : 0.f;
+          if (epi == EPI_SCORES && grp == 1) bias_s[128 + et] = __ldg(jb.bias2 + et);
         }
-        epi_bar();
-        mbar_wait(bar_tfull + 8 * (G & 1), (G >> 1) & 1);
+        TH_TIMED(0, epi_bar());
+        TH_TIMED(1, mbar_wait(bar_tfull + 8 * (G & 1), (G >> 1) & 1));
+        if (pending_job >= 0) {
+          TH_TIMED(2, __threadfence(); fence_proxy_async_all());
+          __syncwarp();
+          if (lane == 0) add_release_local(cnt_job + 4 * pending_job);
+          pending_job = -1;
+        }
+        const long long t_work = clock64();
         tc_fence_after();
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t taddr = lane_addr + (((uint32_t)jb.tmem_col + flip) & 511u);
         if (epi == EPI_IMG) {
-          unsigned char* out = jb.out_img ? jb.out_img + (size_t)(jb.out_tile_off + ptile) * (N / BK) * TILE_IMG
-                                          : scratch + jb.out_off;
-#pragma unroll 1
-          for (int kb = 0; kb < N / BK; ++kb) {
-            if (lane == 0) bulk_wait_read0();  // previous slabs have been read out of the staging buffer
-            __syncwarp();
+          // bias / ReLU / fp16 hi-lo split straight from the accumulator to the scratch tile image:
+          // a thread owns one row; 16 columns = one 32-byte sector of the hi plane and one of the lo
+          // plane (the 128-byte swizzle permutes 16-byte chunks inside a sector pair-wise).
+          unsigned char* out = scratch + jb.out_off + (size_t)et * 128;
+          const int ncol = N >> 1, cbeg = grp * ncol;
+          const bool swap = (et & 1) != 0;
+          // 32 accumulator columns -> 2 x (hi sector, lo sector)
+          auto emit = [&](const uint32_t (&v)[32], int c0) {
+            unsigned char* kb_out = out + (size_t)(c0 >> 6) * TILE_IMG;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              uint32_t v[32];
-              tmem_ld32(taddr + kb * BK + h * 32, v);
-              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int half = 0; half < 2; ++half) {  // 16 columns each
+              uint4 hi[2], lo[2];
 #pragma unroll
-              for (int jj = 0; jj < 32; jj += 8) {
+              for (int cc = 0; cc < 2; ++cc) {
                 float x[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  x[e] = __uint_as_float(v[jj + e]) + bias_s[kb * BK + h * 32 + jj + e];
+                  x[e] = __uint_as_float(v[half * 16 + cc * 8 + e]) + bias_s[c0 + half * 16 + cc * 8 + e];
                   if (jb.relu) x[e] = fmaxf(x[e], 0.f);
                 }
-                uint4 hi, lo;
-                split2(x[0], x[1], hi.x, lo.x);
-                split2(x[2], x[3], hi.y, lo.y);
-                split2(x[4], x[5], hi.z, lo.z);
-                split2(x[6], x[7], hi.w, lo.w);
-                const int chunk = h * 4 + (jj >> 3);
-                const int off = lane * 128 + ((chunk ^ (et & 7)) << 4);
-                *reinterpret_cast<uint4*>(stage_b + off) = hi;
-                *reinterpret_cast<uint4*>(stage_b + 4096 + off) = lo;
+                split2(x[0], x[1], hi[cc].x, lo[cc].x);
+                split2(x[2], x[3], hi[cc].y, lo[cc].y);
+                split2(x[4], x[5], hi[cc].z, lo[cc].z);
+                split2(x[6], x[7], hi[cc].w, lo[cc].w);
               }
+              // logical chunks (2m, 2m+1) -> physical (2m ^ x, (2m+1) ^ x), x = row & 7: same sector,
+              // halves swapped when x is odd
+              const int chunk = ((c0 & 63) >> 3) + half * 2;
+              unsigned char* dst = kb_out + (((chunk ^ (et & 7)) & ~1) << 4);
+              st32_keep(dst, swap ? hi[1] : hi[0], swap ? hi[0] : hi[1]);
+              st32_keep(dst + A_TILE_BYTES, swap ? lo[1] : lo[0], swap ? lo[0] : lo[1]);
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              unsigned char* dst = out + (size_t)kb * TILE_IMG + (size_t)q * 4096;
-              bulk_s2g(dst, smem_u32(stage_b), 4096);
-              bulk_s2g(dst + A_TILE_BYTES, smem_u32(stage_b + 4096), 4096);
-              bulk_commit();
-            }
-          }
-          if (lane == 0) {
-            bulk_wait_all0();  // the tile is in memory: the loader may fetch it for a later job
-            fence_proxy_async_all();
-            add_release_local(cnt_job + 4 * j);
-          }
-        } else if (epi == EPI_ROWS) {
-          const int64_t mbase = (jb.out_tile_off + ptile) * BM + q * 32;
+          };
+          // software pipelined: the next 32 columns are in flight from TMEM while these are converted
+          uint32_t va[32], vb[32];
+          tmem_ld32(taddr + cbeg, va);
 #pragma unroll 1
-          for (int c0 = 0; c0 < N; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c0, v);
+          for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 64) {
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int jj = 0; jj < 32; jj += 4) {
-              float4 o;
-              o.x = __uint_as_float(v[jj + 0]) + bias_s[c0 + jj + 0];
-              o.y = __uint_as_float(v[jj + 1]) + bias_s[c0 + jj + 1];
-              o.z = __uint_as_float(v[jj + 2]) + bias_s[c0 + jj + 2];
-              o.w = __uint_as_float(v[jj + 3]) + bias_s[c0 + jj + 3];
-              if (jb.relu) {
-                o.x = fmaxf(o.x, 0.f);
-                o.y = fmaxf(o.y, 0.f);
-                o.z = fmaxf(o.z, 0.f);
-                o.w = fmaxf(o.w, 0.f);
-              }
-              *reinterpret_cast<float4*>(stage + lane * EPI_LD + jj) = o;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int rr = 0; rr < 32; rr += 4) {
-              const int row = rr + (lane >> 3);
-              const float4 o = *reinterpret_cast<const float4*>(stage + row * EPI_LD + (lane & 7) * 4);
-              *reinterpret_cast<float4*>(jb.out_rows + (mbase + row) * N + c0 + (lane & 7) * 4) = o;
-            }
-            __syncwarp();
+            tmem_ld32(taddr + c0 + 32, vb);  // ncol is a multiple of 64
+            emit(va, c0);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c0 + 64 < cbeg + ncol) tmem_ld32(taddr + c0 + 64, va);
+            emit(vb, c0 + 32);
           }
+          // The stores become visible to the loader's bulk (async-proxy) reads with a fence + a counter
+          // increment.  Unless the very next job reads this tile, that is postponed until this warp has
+          // waited for the next accumulator: by then the stores have landed and the fence is free.
+          if (jb.signal_now) {
+            TH_TIMED(2, __threadfence(); fence_proxy_async_all());
+            __syncwarp();
+            if (lane == 0) add_release_local(cnt_job + 4 * j);
+          } else {
+            pending_job = j;
+          }
+        } else if (grp != 0) {
+          // the per-point epilogues below are group 0's
         } else if (epi == EPI_SCORES) {
           // A[i][j] = (KP_i + b0) . (KS_j + b1) / sqrt(128) for i = this job's view; the key embeds of
           // every view j sit in TMEM (EPI_KEEP jobs).  One thread = one point, no shuffles.
@@ -458,22 +500,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           const int i = jb.view;
 #pragma unroll
           for (int jv = 0; jv < TH_MAX_VIEWS; ++jv)
-            if (jv < V) atab[i * TH_MAX_VIEWS + jv] = __fdiv_rn(sc[jv], 11.313708498984761f);
+            if (jv < V) atab[i * V + jv] = __fdiv_rn(sc[jv], 11.313708498984761f);
           if (i == V - 1) {
             // softmax over i for every j (dim=1 of (P, V_i, V_j), cross_transformer.py:144)
             for (int jv = 0; jv < V; ++jv) {
               float a[TH_MAX_VIEWS], m = -3.4e38f, sum = 0.f;
               for (int ii = 0; ii < V; ++ii) {
-                a[ii] = atab[ii * TH_MAX_VIEWS + jv];
+                a[ii] = atab[ii * V + jv];
                 m = fmaxf(m, a[ii]);
               }
               for (int ii = 0; ii < V; ++ii) {
                 a[ii] = expf(a[ii] - m);
                 sum += a[ii];
               }
-              for (int ii = 0; ii < V; ++ii) atab[ii * TH_MAX_VIEWS + jv] = __fdiv_rn(a[ii], sum);
+              for (int ii = 0; ii < V; ++ii) atab[ii * V + jv] = __fdiv_rn(a[ii], sum);
             }
-            __threadfence();
             __syncwarp();
             if (lane == 0) add_release_local(cnt_scores);
           }
@@ -524,6 +565,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           }
         }
         // this warp is done with the accumulator of job G
+        if (stats) tw[3 + (epi == EPI_IMG ? 0 : epi == EPI_SCORES ? 1 : 2)] += clock64() - t_work;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -536,10 +578,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     }
   }
 
+  if (stats && lane == 0 && (warp == LOADER_WARP || warp == MMA_WARP || warp == EPI_WARP0 || warp == 0)) {
+    // slots: loader 0-5, MMA/relay 8-13, epilogue warp 10: 16-21, mix warp 0: 24-29; slot +6 = total cycles
+    const int o = warp == LOADER_WARP ? 0 : warp == MMA_WARP ? 8 : warp == EPI_WARP0 ? 16 : 24;
+    for (int i = 0; i < 6; ++i) stats[o + i] = (unsigned long long)tw[i];
+    stats[o + 6] = (unsigned long long)(clock64() - t_begin);
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 9) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -692,6 +740,13 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     }
   }
   Program& pg = B.pg;
+  for (int j = 0; j < pg.njobs; ++j) {
+    const Job& nx = pg.job[(j + 1) % pg.njobs];
+    bool next_reads = false;
+    if (j + 1 < pg.njobs)
+      for (int sgi = 0; sgi < nx.nseg; ++sgi) next_reads |= (nx.seg[sgi].dep == j);
+    pg.job[j].signal_now = next_reads ? 1 : 0;
+  }
   pg.scratch = scratch;
   pg.afc_w = wf(h.afc_w);
   pg.afc_b = wf(h.afc_b);
@@ -719,8 +774,39 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     cfg = true;
   }
   const int nclusters = pg.num_units < num_sms / 2 ? pg.num_units : num_sms / 2;
+  static const bool want_stats = getenv("TH_CHAIN_STATS") != nullptr;
+  static unsigned long long* d_stats = nullptr;
+  if (want_stats) {
+    if (!d_stats) TH_CUDA(cudaMalloc(&d_stats, (size_t)num_sms * 32 * 8));
+    TH_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)num_sms * 32 * 8, st));
+    pg.stats = d_stats;
+  }
   k_chain<<<2 * nclusters, NUM_THREADS, SMEM_BYTES, st>>>(pg);
   TH_LAUNCHED();
+  if (want_stats) {
+    static int printed = 0;
+    std::vector<unsigned long long> hs((size_t)num_sms * 32);
+    TH_CUDA(cudaMemcpyAsync(hs.data(), d_stats, hs.size() * 8, cudaMemcpyDeviceToHost, st));
+    TH_CUDA(cudaStreamSynchronize(st));
+    if (printed++ < 4 || (printed % 64) == 0) {
+      const char* names[4][7] = {
+          {"dep", "mix", "empty", "-", "-", "-", "total"},
+          {"epi(tmem)", "full", "pfull", "-", "-", "-", "total"},
+          {"bar", "tfull", "store", "w_img", "w_scores", "w_heads", "total"},
+          {"scores", "work", "-", "-", "-", "-", "total"}};
+      const char* roles[4] = {"loader", "mma/relay", "epilogue w10", "mix w0"};
+      for (int r = 0; r < 4; ++r) {
+        fprintf(stderr, "[chain stats] %-12s", roles[r]);
+        for (int i = 0; i < 7; ++i) {
+          if (names[r][i][0] == '-') continue;
+          double lead = 0, peer = 0;
+          for (int c = 0; c < 2 * nclusters; ++c) (c & 1 ? peer : lead) += (double)hs[(size_t)c * 32 + r * 8 + i];
+          fprintf(stderr, " %s=%.0f/%.0f", names[r][i], lead / nclusters / 1e3, peer / nclusters / 1e3);
+        }
+        fprintf(stderr, "  (kcycles per CTA, leader/peer; units=%d clusters=%d)\n", pg.num_units, nclusters);
+      }
+    }
+  }
   return TH_OK;
 }
 
