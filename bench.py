@@ -40,6 +40,16 @@ def flops_per_point(V: int) -> int:
     return 2 * (740_480 * V + 384 * V * V + 82_560) + 126
 
 
+def executed_macs_per_point(V: int) -> int:
+    """Tensor-core MACs the tcgen05 schedule really issues per point (before the x3 of the fp16
+    split): value embeds folded into fc_1, feature_fc/rgb_res_0 folded into view_fc, K padded to 64
+    (DESIGN.md section 3).  Per view row: fc_0 256x256, alpha_res_0 256x384, two key embeds
+    128x256, fc_1' 256x512, fc_2 256x256, view_fc' 128x704; per point: fc_3 256x(256 V),
+    fc_4' 128x(128 V + 384)."""
+    per_view = 256 * 256 + 256 * 384 + 2 * 128 * 256 + 256 * 512 + 256 * 256 + 128 * 704
+    return V * per_view + 256 * 256 * V + 128 * (128 * V + 384)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -284,17 +294,26 @@ def main():
     achieved = flops_step / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    chain = os.environ.get("TH_CHAIN", "1") != "0" and not args.simt and args.views <= 3
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("gemm_dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic = tj.get("chain_dram_bytes_per_launch") if chain else tj.get("gemm_dram_bytes_per_launch")
     # the split scheme issues 3 fp16 tensor products per algorithmic MAC: its ceiling is 1/3 of the fp16 rate
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-                "kernel": "k_gemm_simt (fp32 CUDA cores)" if args.simt else "k_gemm_tc2 (tcgen05 cta_group::2, fp16x3 split)",
+                "kernel": ("k_gemm_simt (fp32 CUDA cores)" if args.simt else
+                           "k_chain (tcgen05 cta_group::2, fp16x3 split, all layers of a 256-point unit per launch)"
+                           if chain else "k_gemm_tc2 (tcgen05 cta_group::2, fp16x3 split, one layer per launch)"),
                 "launches_per_step": gemm_launches // args.steps, "gemm_ms_per_step": gemm_ms_step,
                 "share_of_step": gemm_ms_step / ms_step, "peak_source": peaks["source"],
                 "flops_per_point": flops_per_point(args.views),
                 "tensor_products_per_mac": 1 if args.simt else 3,
-                "issued_tensor_frac": (1 if args.simt else 3) * achieved / peaks["bf16_tflops"],
+                # what the tensor pipe really executes: folded layers, 3 fp16 products per MAC
+                "executed_tensor_tflops": (0.0 if args.simt or gemm_ms_step <= 0 else
+                                           6 * executed_macs_per_point(args.views) * P_step / (gemm_ms_step * 1e-3) / 1e12),
+                "issued_tensor_frac": (achieved / peaks["bf16_tflops"] if args.simt or gemm_ms_step <= 0 else
+                                       6 * executed_macs_per_point(args.views) * P_step / (gemm_ms_step * 1e-3) / 1e12
+                                       / peaks["bf16_tflops"]),
                 "hbm_algorithmic_gbs": BYTES_PER_RAY * N_rays / (ms_step * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
     breakdown = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
@@ -321,7 +340,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "l2": "inputs larger than L2 (1.2 GB feature maps per frame)",
                            "sharding": "one 512x512 target view per rank, NCCL all_gather of the images",
-                           "mlp": "fp32 CUDA cores" if args.simt else "tcgen05 fp16x3 split, fp32 accumulate"},
+                           "mlp": "fp32 CUDA cores" if args.simt else "tcgen05 fp16x3 split, fp32 accumulate" + (", layer-chained" if chain else "")},
                 "clocks": clk,
                 "e2e": {"value": world * N_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},

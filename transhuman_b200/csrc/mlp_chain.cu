@@ -74,6 +74,7 @@ struct Program {
   int64_t first, P;
   int32_t njobs, num_units, V, has_mix, zero_rgb, alpha_only, kp_col;
   int32_t ks_col[TH_MAX_VIEWS];
+  int32_t dbg;  // TH_CHAIN_DBG: timing experiments only, results are wrong (1 = skip the mix, 2 = skip the store fences)
   unsigned long long* stats;  // TH_CHAIN_STATS=1: per-CTA wait-time counters (cycles), else nullptr
 };
 
@@ -225,6 +226,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         fence_proxy_async_all();
 #pragma unroll 1
         for (int kb = 0; kb < 4; ++kb) {
+          if (pg.dbg & 1) {
+            __syncwarp();
+            if (lane == 0) add_release_local(cnt_mix);
+            continue;
+          }
           // software pipelined over positions: the next position's 2V loads are in flight while
           // this one is mixed and stored (positions are disjoint, so the order is free)
           uint4 ch[CHAIN_MAX_V], cl[CHAIN_MAX_V], nh[CHAIN_MAX_V], nl[CHAIN_MAX_V];
@@ -406,7 +412,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         TH_TIMED(0, epi_bar());
         TH_TIMED(1, mbar_wait(bar_tfull + 8 * (G & 1), (G >> 1) & 1));
         if (pending_job >= 0) {
-          TH_TIMED(2, __threadfence(); fence_proxy_async_all());
+          if (!(pg.dbg & 2)) TH_TIMED(2, __threadfence(); fence_proxy_async_all());
           __syncwarp();
           if (lane == 0) add_release_local(cnt_job + 4 * pending_job);
           pending_job = -1;
@@ -422,6 +428,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           unsigned char* out = scratch + jb.out_off + (size_t)et * 128;
           const int ncol = N >> 1, cbeg = grp * ncol;
           const bool swap = (et & 1) != 0;
+          const bool relu = jb.relu != 0;
           // 32 accumulator columns -> 2 x (hi sector, lo sector)
           auto emit = [&](const uint32_t (&v)[32], int c0) {
             unsigned char* kb_out = out + (size_t)(c0 >> 6) * TILE_IMG;
@@ -431,10 +438,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
               for (int cc = 0; cc < 2; ++cc) {
                 float x[8];
+                const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + half * 16 + cc * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + half * 16 + cc * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  x[e] = __uint_as_float(v[half * 16 + cc * 8 + e]) + bias_s[c0 + half * 16 + cc * 8 + e];
-                  if (jb.relu) x[e] = fmaxf(x[e], 0.f);
+                  x[e] = __uint_as_float(v[half * 16 + cc * 8 + e]) + bb[e];
+                  if (relu) x[e] = fmaxf(x[e], 0.f);
                 }
                 split2(x[0], x[1], hi[cc].x, lo[cc].x);
                 split2(x[2], x[3], hi[cc].y, lo[cc].y);
@@ -465,7 +475,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           // increment.  Unless the very next job reads this tile, that is postponed until this warp has
           // waited for the next accumulator: by then the stores have landed and the fence is free.
           if (jb.signal_now) {
-            TH_TIMED(2, __threadfence(); fence_proxy_async_all());
+            if (!(pg.dbg & 2)) TH_TIMED(2, __threadfence(); fence_proxy_async_all());
             __syncwarp();
             if (lane == 0) add_release_local(cnt_job + 4 * j);
           } else {
@@ -775,6 +785,8 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
   }
   const int nclusters = pg.num_units < num_sms / 2 ? pg.num_units : num_sms / 2;
   static const bool want_stats = getenv("TH_CHAIN_STATS") != nullptr;
+  static const int dbg = getenv("TH_CHAIN_DBG") ? atoi(getenv("TH_CHAIN_DBG")) : 0;
+  pg.dbg = dbg;
   static unsigned long long* d_stats = nullptr;
   if (want_stats) {
     if (!d_stats) TH_CUDA(cudaMalloc(&d_stats, (size_t)num_sms * 32 * 8));
