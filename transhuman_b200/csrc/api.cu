@@ -54,13 +54,15 @@ void prof_end(int cat, cudaStream_t st) {
   ++g_prof.launches[cat];
 }
 
-// points per MLP chunk (workspace ~ 26 KiB / point: 7 GB at the default; fewer, larger launches
-// measured faster than L2-sized chunks); TH_CHUNK_PTS overrides (multiple of 256)
+// Points per chunk.  284160 = 148 SMs x 5 resident feature-kernel CTAs x 128 points x 3 waves
+// = 74 clusters x 15 units of 256 points for the chain kernel: both kernels run whole waves
+// (262144 left the feature kernel's third wave 77 % full).  Workspace ~ 26 KiB / point.
+// TH_CHUNK_PTS overrides (multiple of 256).
 static int64_t chunk_pts() {
   static int64_t v = 0;
   if (!v) {
     const char* e = getenv("TH_CHUNK_PTS");
-    v = e ? atoll(e) : 256 * 1024;
+    v = e ? atoll(e) : 284160;
     if (v < 256) v = 256;
     v = v / 256 * 256;
   }
