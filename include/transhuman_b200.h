@@ -57,6 +57,7 @@ extern "C" {
 /* Flags for ThFrame.flags / th_render_rays */
 #define TH_FLAG_WHITE_BKGD 1u /* cfg.white_bkgd, nerf_net_utils.py:56-57 */
 #define TH_FLAG_SIMT_MLP 2u   /* force the fp32 CUDA-core GEMM path (debug / parity) */
+#define TH_FLAG_LAYERWISE 4u  /* tcgen05 GEMMs one layer per launch instead of the layer-chained kernel (cross-check) */
 
 /* Per-frame state: the outputs of the (out-of-scope, torch) prologue that the
  * query path consumes.  Built once per frame by the Python Renderer. */

@@ -340,6 +340,34 @@ def test_one_shot_single_view():
     _compare_maps(got, want, float(fr["far"].max()), "V=1", exclude=_knife_edge_rays(want["raw"], 16))
 
 
+@pytest.mark.parametrize("V", [2, 4])
+def test_other_view_counts(V):
+    """V = 2 runs the layer-chained kernel with two key embeds in TMEM; V = 4 does not fit its 512
+    TMEM columns and takes the layer-at-a-time schedule."""
+    fr = synth.make_frame(H=12, W=12, n_class=300, V=V, feat_hw=16, seed=6, alpha_bias_shift=-10.0)
+    tf = orc.to_torch_frame(fr)
+    tokens = orc.build_tokens(tf)
+    frame, rays = frame_to_device(fr, tokens, DEV)
+    got = ops.render_rays(frame, *rays, 16, mode=ops.TH_RENDER_DENSE)
+    want = orc.render(tf, 16, tokens=tokens)
+    _compare_maps(got, want, float(fr["far"].max()), f"V={V}", exclude=_knife_edge_rays(want["raw"], 16))
+
+
+def test_layerwise_schedule_agrees_with_chain(small):
+    """TH_FLAG_LAYERWISE: the same tcgen05 GEMMs one layer per launch + attention / head kernels.
+    Both schedules evaluate the same folded layers, so raw agrees to fp32 rounding of the attention."""
+    fr, tf, tokens, frame, rays = small
+    a = ops.render_rays(frame, *rays, 16, mode=ops.TH_RENDER_DENSE, want_raw=True)
+    frame.set_flag(ops.TH_FLAG_LAYERWISE, True)
+    try:
+        b = ops.render_rays(frame, *rays, 16, mode=ops.TH_RENDER_DENSE, want_raw=True)
+    finally:
+        frame.set_flag(ops.TH_FLAG_LAYERWISE, False)
+    ra, rb = a["raw"].cpu(), b["raw"].cpu()
+    assert (ra - rb).abs().max().item() <= 2e-5 * max(1.0, ra.abs().max().item())
+    assert (a["rgb_map"] - b["rgb_map"]).abs().max().item() <= 1e-4
+
+
 def test_bad_arguments_report_errors(small):
     from transhuman_b200._lib import TransHumanLibraryError
     fr, tf, tokens, frame, rays = small

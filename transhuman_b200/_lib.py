@@ -17,6 +17,7 @@ TH_MAX_VIEWS = 4
 TH_MAX_KNN = 16
 TH_FLAG_WHITE_BKGD = 1
 TH_FLAG_SIMT_MLP = 2
+TH_FLAG_LAYERWISE = 4
 TH_RENDER_DENSE, TH_RENDER_MASKED, TH_RENDER_FAST = 0, 1, 2
 TH_TRAIN_BRANCH_MAX_RAYS = 2400
 

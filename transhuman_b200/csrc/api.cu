@@ -476,7 +476,8 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
       TH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const size_t scratch_room = (size_t)Pp * V * (256 * 4 + 128 * 2) * 4;  // b.s ... b.ks are contiguous
-    if (use_tc && use_chain && chain_supported(V) && chain_scratch_bytes(P, V, num_sms) <= scratch_room)
+    if (use_tc && use_chain && !(f->flags & TH_FLAG_LAYERWISE) && chain_supported(V) &&
+        chain_scratch_bytes(P, V, num_sms) <= scratch_room)
       rc = mlp_forward_chain(run, b, hdr, reinterpret_cast<unsigned char*>(b.s), nullptr, st);
     else
       rc = mlp_forward(run, b, hdr, st);

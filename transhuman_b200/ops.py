@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (TH_FLAG_SIMT_MLP, TH_FLAG_WHITE_BKGD, TH_RENDER_DENSE, TH_RENDER_FAST, TH_RENDER_MASKED,
+from ._lib import (TH_FLAG_LAYERWISE, TH_FLAG_SIMT_MLP, TH_FLAG_WHITE_BKGD, TH_RENDER_DENSE, TH_RENDER_FAST, TH_RENDER_MASKED,
                    ThFrame, ThOut, ThRays, ThWeightsF32)
 
 __all__ = ["PackedWeights", "Frame", "render_rays", "query_density", "sample_points", "cull_knn1", "cull_grid",
@@ -109,7 +109,8 @@ class Frame:
 
     def __init__(self, *, holder, tok_xyz, tok_rot, verts, feat_nhwc, cam_R, cam_T, cam_K, Rh, Th,
                  weights: PackedWeights, uv_scale, knn: int = 7, knn_dist_alpha: float = 0.5,
-                 cull_radius: float = 0.1, white_bkgd: bool = False, simt_mlp: bool = False):
+                 cull_radius: float = 0.1, white_bkgd: bool = False, simt_mlp: bool = False,
+                 layerwise: bool = False):
         self.holder = _f32(holder, "holder")
         V, n_tok, c = self.holder.shape
         assert c == 192, "token width must be 192"
@@ -138,7 +139,8 @@ class Frame:
         f.knn = knn
         f.uv_scale_x, f.uv_scale_y = float(uv_scale[0]), float(uv_scale[1])
         f.knn_dist_alpha, f.cull_radius = knn_dist_alpha, cull_radius
-        f.flags = (TH_FLAG_WHITE_BKGD if white_bkgd else 0) | (TH_FLAG_SIMT_MLP if simt_mlp else 0)
+        f.flags = ((TH_FLAG_WHITE_BKGD if white_bkgd else 0) | (TH_FLAG_SIMT_MLP if simt_mlp else 0) |
+                   (TH_FLAG_LAYERWISE if layerwise else 0))
         self.c = f
 
     @property
