@@ -84,6 +84,22 @@ def test_simt_and_tensor_core_paths_agree_at_size():
     assert (a["rgb_map"] - b["rgb_map"])[keep].abs().max().item() <= 1e-4
 
 
+def test_chain_kernel_is_insensitive_to_role_timing(monkeypatch):
+    """The layer-chained kernel synchronises its warp roles with mbarriers and counters only.
+    TH_CHAIN_DBG=240 delays the loader, the MMA issuer, the epilogue and the mix warps by random
+    amounts (15 units per cluster here): the arithmetic is deterministic, so the result must be
+    bit-identical.  (Caught a per-k-block counter that assumed the mix warps ran in lockstep.)"""
+    fr, tf, tokens, frame, rays = _frame(300, 256, 64, seed=2)
+    S = 64
+    sel = slice(20000, 20000 + 8192)
+    a = ops.render_rays(frame, *(r[sel] for r in rays), S, mode=ops.TH_RENDER_DENSE, want_raw=True)
+    for bits in ("128", "240"):
+        monkeypatch.setenv("TH_CHAIN_DBG", bits)
+        b = ops.render_rays(frame, *(r[sel] for r in rays), S, mode=ops.TH_RENDER_DENSE, want_raw=True)
+        monkeypatch.delenv("TH_CHAIN_DBG")
+        assert torch.equal(a["raw"], b["raw"]) and torch.equal(a["rgb_map"], b["rgb_map"])
+
+
 def test_config_grid_6000_tokens_density():
     """configs[4] shape: dense voxel grid, 6000 tokens, alpha only (reduced to 96^3
     so the oracle spot check stays small; the kernel path is the same)."""

@@ -74,7 +74,7 @@ struct Program {
   int64_t first, P;
   int32_t njobs, num_units, V, has_mix, zero_rgb, alpha_only, kp_col;
   int32_t ks_col[TH_MAX_VIEWS];
-  int32_t dbg;  // TH_CHAIN_DBG: timing experiments only, results are wrong (1 = skip the mix, 2 = skip the store fences)
+  int32_t dbg;  // TH_CHAIN_DBG: timing experiments only, 1 = skip the mix, 2 = skip the store fences (results wrong); 16/32/64/128 = random delays in the loader / MMA / epilogue / mix role, 256 = publish every tile at once (results valid)
   unsigned long long* stats;  // TH_CHAIN_STATS=1: per-CTA wait-time counters (cycles), else nullptr
 };
 
@@ -97,6 +97,10 @@ __device__ __forceinline__ void wait_counter(uint32_t addr, uint32_t target, int
       __trap();
     }
   }
+}
+// TH_CHAIN_DBG & (16|32|64|128): random delays per role, to shake out ordering bugs (results stay valid)
+__device__ __forceinline__ void jitter(int dbg, int role_bit = 16) {
+  if (dbg & role_bit) __nanosleep((unsigned)((clock64() * 2654435761ull) >> 13) & 2047u);
 }
 __device__ __forceinline__ void add_release_local(uint32_t addr) {
   asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(addr) : "memory");
@@ -161,9 +165,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   unsigned char* ctrl_ptr = reinterpret_cast<unsigned char*>(s_atab + 128 * ATAB_LD);
   const uint32_t ctrl = base + NSTAGE * STAGE_BYTES + 2048 + 128 * ATAB_LD * 4;
   const uint32_t bar_full = ctrl, bar_empty = ctrl + 24, bar_pfull = ctrl + 48, bar_tfull = ctrl + 72;
-  const uint32_t cnt_epi = ctrl + 96, cnt_mix = ctrl + 100, cnt_scores = ctrl + 104, cnt_job = ctrl + 128;
+  // counters (u32): epilogue-done of this CTA / of the peer, scores, mix per k-block [4], stored tile per job
+  const uint32_t cnt_epi = ctrl + 96, cnt_epi_peer = ctrl + 100, cnt_scores = ctrl + 104, cnt_mix = ctrl + 112,
+                 cnt_job = ctrl + 128;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl_ptr + 88);
-  uint32_t* counters = reinterpret_cast<uint32_t*>(ctrl_ptr + 96);  // epi, mix, scores, pad[5], job[MAX_JOBS]
+  uint32_t* counters = reinterpret_cast<uint32_t*>(ctrl_ptr + 96);  // see cnt_* below
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -228,9 +234,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         for (int kb = 0; kb < 4; ++kb) {
           if (pg.dbg & 1) {
             __syncwarp();
-            if (lane == 0) add_release_local(cnt_mix);
+            if (lane == 0) add_release_local(cnt_mix + 4 * kb);
             continue;
           }
+          jitter(pg.dbg, 128);
           // software pipelined over positions: the next position's 2V loads are in flight while
           // this one is mixed and stored (positions are disjoint, so the order is free)
           uint4 ch[CHAIN_MAX_V], cl[CHAIN_MAX_V], nh[CHAIN_MAX_V], nl[CHAIN_MAX_V];
@@ -291,7 +298,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           __threadfence();
           fence_proxy_async_all();  // generic-proxy stores -> the loader's bulk (async-proxy) reads
           __syncwarp();
-          if (lane == 0) add_release_local(cnt_mix);
+          if (lane == 0) add_release_local(cnt_mix + 4 * kb);
         }
         if (stats) tw[1] += clock64() - t_mix;
       }
@@ -315,9 +322,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             }
             for (int kk = 0; kk < sg.kbs; ++kk, ++kb, ++kcount) {
               if (sg.dep_mix) {
-                TH_TIMED(1, wait_counter(cnt_mix, (uint32_t)(MIX_THREADS / 32) * (uint32_t)(4 * it + kk + 1), 3));
+                // one counter per k-block: the mix warps are not in lockstep
+                TH_TIMED(1, wait_counter(cnt_mix + 4 * kk, (uint32_t)(MIX_THREADS / 32) * (uint32_t)(it + 1), 3));
                 fence_proxy_async_all();
               }
+              jitter(pg.dbg, 16);
               const uint32_t s = kcount % NSTAGE, ph = (kcount / NSTAGE) & 1;
               TH_TIMED(2, mbar_wait(bar_empty + 8 * s, ph ^ 1));
               const uint32_t sa = base + s * STAGE_BYTES;
@@ -346,7 +355,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           const uint32_t flip = (it & 1) ? flip_on : 0u;
           for (int j = 0; j < njobs; ++j, ++G) {
             const Job& jb = pg.job[j];
-            if ((int32_t)(G - jb.wait_back) >= 0) TH_TIMED(0, wait_counter(cnt_epi, 2u * EPI_WARPS * (G - jb.wait_back + 1), 4, 20));
+            jitter(pg.dbg, 32);
+            if ((int32_t)(G - jb.wait_back) >= 0) {
+              // one counter per CTA: warps of a CTA stay within one job of each other (named barrier),
+              // the two CTAs of the pair do not
+              TH_TIMED(0, wait_counter(cnt_epi, (uint32_t)EPI_WARPS * (G - jb.wait_back + 1), 4, 20);
+                       wait_counter(cnt_epi_peer, (uint32_t)EPI_WARPS * (G - jb.wait_back + 1), 5, 20));
+            }
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (((uint32_t)jb.tmem_col + flip) & 511u);
             const uint32_t idesc = (1u << 4) | ((uint32_t)(jb.N >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
@@ -418,6 +433,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           pending_job = -1;
         }
         const long long t_work = clock64();
+        jitter(pg.dbg, 64);
         tc_fence_after();
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t taddr = lane_addr + (((uint32_t)jb.tmem_col + flip) & 511u);
@@ -474,7 +490,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           // The stores become visible to the loader's bulk (async-proxy) reads with a fence + a counter
           // increment.  Unless the very next job reads this tile, that is postponed until this warp has
           // waited for the next accumulator: by then the stores have landed and the fence is free.
-          if (jb.signal_now) {
+          if (jb.signal_now || (pg.dbg & 256)) {
             if (!(pg.dbg & 2)) TH_TIMED(2, __threadfence(); fence_proxy_async_all());
             __syncwarp();
             if (lane == 0) add_release_local(cnt_job + 4 * j);
@@ -582,7 +598,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           if (rank == 0)
             add_release_local(cnt_epi);
           else
-            add_release_remote(cnt_epi, 0);
+            add_release_remote(cnt_epi_peer, 0);
         }
       }
     }
@@ -785,8 +801,8 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
   }
   const int nclusters = pg.num_units < num_sms / 2 ? pg.num_units : num_sms / 2;
   static const bool want_stats = getenv("TH_CHAIN_STATS") != nullptr;
-  static const int dbg = getenv("TH_CHAIN_DBG") ? atoi(getenv("TH_CHAIN_DBG")) : 0;
-  pg.dbg = dbg;
+  const char* dbg_env = getenv("TH_CHAIN_DBG");  // read per launch so that a test can toggle it
+  pg.dbg = dbg_env ? atoi(dbg_env) : 0;
   static unsigned long long* d_stats = nullptr;
   if (want_stats) {
     if (!d_stats) TH_CUDA(cudaMalloc(&d_stats, (size_t)num_sms * 32 * 8));
