@@ -292,12 +292,13 @@ def main():
     gemm_ms_step = gemm_ms / args.steps
     flops_step = flops_per_point(args.views) * P_step
     achieved = flops_step / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else 0.0
-    traffic = None
+    traffic = l2_bytes = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     chain = os.environ.get("TH_CHAIN", "1") != "0" and not args.simt and args.views <= 3
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic = tj.get("chain_dram_bytes_per_launch") if chain else tj.get("gemm_dram_bytes_per_launch")
+        l2_bytes = tj.get("chain_l2_bytes_per_launch") if chain else None
     # the split scheme issues 3 fp16 tensor products per algorithmic MAC: its ceiling is 1/3 of the fp16 rate
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
@@ -314,6 +315,13 @@ def main():
                 "issued_tensor_frac": (achieved / peaks["bf16_tflops"] if args.simt or gemm_ms_step <= 0 else
                                        6 * executed_macs_per_point(args.views) * P_step / (gemm_ms_step * 1e-3) / 1e12
                                        / peaks["bf16_tflops"]),
+                # ncu: bytes through L2 per launch; live rate = that / the launch's live duration.  The
+                # kernel sits on L2 -> SM operand bandwidth (practical cap ~6300 B/clk),
+                # neither on HBM nor on the tensor pipe.
+                "l2_bytes_per_launch": l2_bytes,
+                "l2_tbs_live": (l2_bytes * (gemm_launches // args.steps) / (gemm_ms_step * 1e-3) / 1e12
+                                if l2_bytes and gemm_ms_step > 0 else None),
+                "binding": "L2->SM operand bandwidth" if chain else "HBM (K=256 layers) / tensor (K>=512)",
                 "hbm_algorithmic_gbs": BYTES_PER_RAY * N_rays / (ms_step * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
     breakdown = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
