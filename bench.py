@@ -315,13 +315,12 @@ def main():
                 "issued_tensor_frac": (achieved / peaks["bf16_tflops"] if args.simt or gemm_ms_step <= 0 else
                                        6 * executed_macs_per_point(args.views) * P_step / (gemm_ms_step * 1e-3) / 1e12
                                        / peaks["bf16_tflops"]),
-                # ncu: bytes through L2 per launch; live rate = that / the launch's live duration.  The
-                # kernel sits on L2 -> SM operand bandwidth (practical cap ~6300 B/clk),
-                # neither on HBM nor on the tensor pipe.
+                # ncu: bytes through L2 per launch; live rate = that / the launch's live duration
+                # (practical L2 cap ~6300 B/clk)
                 "l2_bytes_per_launch": l2_bytes,
                 "l2_tbs_live": (l2_bytes * (gemm_launches // args.steps) / (gemm_ms_step * 1e-3) / 1e12
                                 if l2_bytes and gemm_ms_step > 0 else None),
-                "binding": "L2->SM operand bandwidth" if chain else "HBM (K=256 layers) / tensor (K>=512)",
+                "binding": "job-pipeline latency (epilogue ~ MMA time per job, serial attention sections); L2->SM at ~80 % of its practical cap" if chain else "HBM (K=256 layers) / tensor (K>=512)",
                 "hbm_algorithmic_gbs": BYTES_PER_RAY * N_rays / (ms_step * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
     breakdown = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
