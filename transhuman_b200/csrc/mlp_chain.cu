@@ -61,7 +61,6 @@ struct Job {
   const float* bias2;       // EPI_SCORES: bias of the kept key embed
   uint32_t out_off;         // EPI_IMG: destination inside the CTA's scratch
   int32_t nseg, nkb, N, relu, epi, tmem_col, wait_back, view;
-  int32_t signal_now;  // EPI_IMG: the next job reads this tile, publish it at once
 };
 struct Program {
   Job job[MAX_JOBS];
@@ -74,7 +73,7 @@ struct Program {
   int64_t first, P;
   int32_t njobs, num_units, V, has_mix, zero_rgb, alpha_only, kp_col;
   int32_t ks_col[TH_MAX_VIEWS];
-  int32_t dbg;  // TH_CHAIN_DBG: timing experiments only, 1 = skip the mix, 2 = skip the store fences (results wrong); 16/32/64/128 = random delays in the loader / MMA / epilogue / mix role, 256 = publish every tile at once (results valid)
+  int32_t dbg;  // TH_CHAIN_DBG: timing experiments only, 1 = skip the mix, 2 = skip the store fences (results wrong); 16/32/64/128 = random delays in the loader / MMA / epilogue / mix role, 512 = writer-side fences as well (results valid)
   unsigned long long* stats;  // TH_CHAIN_STATS=1: per-CTA wait-time counters (cycles), else nullptr
 };
 
@@ -295,8 +294,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
               }
             }
           }
-          __threadfence();
-          fence_proxy_async_all();  // generic-proxy stores -> the loader's bulk (async-proxy) reads
+          if (pg.dbg & 512) {
+            __threadfence();
+            fence_proxy_async_all();
+          }
           __syncwarp();
           if (lane == 0) add_release_local(cnt_mix + 4 * kb);
         }
@@ -318,12 +319,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             const Seg& sg = jb.seg[sgi];
             if (sg.dep >= 0) {
               TH_TIMED(0, wait_counter(cnt_job + 4 * sg.dep, (uint32_t)EPI_WARPS * (uint32_t)(it + 1), 2));
+              __threadfence();  // cumulative: covers the epilogue warps' stores observed through the counter
               fence_proxy_async_all();
             }
             for (int kk = 0; kk < sg.kbs; ++kk, ++kb, ++kcount) {
               if (sg.dep_mix) {
                 // one counter per k-block: the mix warps are not in lockstep
                 TH_TIMED(1, wait_counter(cnt_mix + 4 * kk, (uint32_t)(MIX_THREADS / 32) * (uint32_t)(it + 1), 3));
+                __threadfence();
                 fence_proxy_async_all();
               }
               jitter(pg.dbg, 16);
@@ -407,7 +410,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     const int et = q * 32 + lane;    // row inside the 128-row tile
     float* atab = s_atab + et * ATAB_LD;
     float alpha_reg = 0.f;
-    int pending_job = -1;  // image job whose "stored" signal is still owed
     uint32_t G = 0;
     int it = 0;
     for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
@@ -426,12 +428,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         }
         TH_TIMED(0, epi_bar());
         TH_TIMED(1, mbar_wait(bar_tfull + 8 * (G & 1), (G >> 1) & 1));
-        if (pending_job >= 0) {
-          if (!(pg.dbg & 2)) TH_TIMED(2, __threadfence(); fence_proxy_async_all());
-          __syncwarp();
-          if (lane == 0) add_release_local(cnt_job + 4 * pending_job);
-          pending_job = -1;
-        }
         const long long t_work = clock64();
         jitter(pg.dbg, 64);
         tc_fence_after();
@@ -487,16 +483,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             if (c0 + 64 < cbeg + ncol) tmem_ld32(taddr + c0 + 64, va);
             emit(vb, c0 + 32);
           }
-          // The stores become visible to the loader's bulk (async-proxy) reads with a fence + a counter
-          // increment.  Unless the very next job reads this tile, that is postponed until this warp has
-          // waited for the next accumulator: by then the stores have landed and the fence is free.
-          if (jb.signal_now || (pg.dbg & 256)) {
-            if (!(pg.dbg & 2)) TH_TIMED(2, __threadfence(); fence_proxy_async_all());
-            __syncwarp();
-            if (lane == 0) add_release_local(cnt_job + 4 * j);
-          } else {
-            pending_job = j;
+          // Publication: a CTA-scope release of a counter, nothing else.  The loader, having acquired
+          // it, executes the gpu-scope fence (cumulative over the stores it has thereby observed) and the
+          // proxy fence before its bulk copy reads the tile -- one fence per dependency on an otherwise
+          // idle thread instead of one per warp and job on the epilogue's critical path.
+          if (pg.dbg & 512) {
+            TH_TIMED(2, __threadfence(); fence_proxy_async_all());
           }
+          __syncwarp();
+          if (lane == 0) add_release_local(cnt_job + 4 * j);
         } else if (grp != 0) {
           // the per-point epilogues below are group 0's
         } else if (epi == EPI_SCORES) {
@@ -766,13 +761,6 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     }
   }
   Program& pg = B.pg;
-  for (int j = 0; j < pg.njobs; ++j) {
-    const Job& nx = pg.job[(j + 1) % pg.njobs];
-    bool next_reads = false;
-    if (j + 1 < pg.njobs)
-      for (int sgi = 0; sgi < nx.nseg; ++sgi) next_reads |= (nx.seg[sgi].dep == j);
-    pg.job[j].signal_now = next_reads ? 1 : 0;
-  }
   pg.scratch = scratch;
   pg.afc_w = wf(h.afc_w);
   pg.afc_b = wf(h.afc_b);
