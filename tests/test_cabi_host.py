@@ -63,7 +63,7 @@ def test_pack_weights_folds_layers(lib):
         assert lib.th_pack_weights(C.byref(wstruct), V, blob.ctypes.data, 16) == -2
         assert b"need" in lib.th_last_error()
         magic, nviews, total = struct.unpack_from("<IiQ", blob, 0)
-        assert magic == 0x32574854 and nviews == V and total == pw_bytes
+        assert magic == 0x33574854 and nviews == V and total == pw_bytes
         offs = struct.unpack_from("<43Q", blob, 16)
         f32 = lambda off, n: blob[off:off + 4 * n].view(np.float32)
         # fc_0: K padded 255 -> 256 with a zero column
@@ -104,7 +104,9 @@ def test_pack_weights_folds_layers(lib):
                                    v1 @ (f64("feature_fc.bias") + f64("rgb_res_0.bias")) + f64("view_fc.bias"),
                                    rtol=0, atol=1e-7)
         h_fc0 = offs[30]
-        img = blob[h_fc0:h_fc0 + 4 * 65536].view(np.float16).astype(np.float32).reshape(4, 2, 256, 64)
+        # per k-block: [half 0: hi (128 rows) | lo] [half 1: hi | lo]  (one contiguous copy per CTA of a pair)
+        img = blob[h_fc0:h_fc0 + 4 * 65536].view(np.float16).astype(np.float32).reshape(4, 2, 2, 128, 64)
+        img = img.transpose(0, 2, 1, 3, 4).reshape(4, 2, 256, 64)          # -> (kb, plane, row, 64)
         n = np.arange(256)[:, None]
         kk = np.arange(64)[None, :]
         col = (((kk >> 3) ^ (n & 7)) << 3) + (kk & 7)          # position of element kk inside the swizzled row

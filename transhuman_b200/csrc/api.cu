@@ -284,8 +284,9 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
   memcpy(W(h.rgb_w), w->rgb_fc_w, 3 * 128 * 4);
   memcpy(W(h.rgb_b), w->rgb_fc_b, 3 * 4);
   // fp16 hi/lo split of the GEMM matrices, stored as shared-memory tile images for
-  // the tensor-core path: per 64-wide k-block, [hi image | lo image], each N rows
-  // of 128 bytes, K-major with the 128-byte swizzle (16-byte chunk ^= row & 7).
+  // the tensor-core path: per 64-wide k-block and per half of the N rows (one half per CTA of a
+  // cta_group::2 pair) [hi image | lo image], each N/2 rows of 128 bytes, K-major with the 128-byte
+  // swizzle (16-byte chunk ^= row & 7) -- a CTA's whole share of a k-block is ONE contiguous copy.
   for (const MatSpec& m : mat_specs(V)) {
     if (!m.h) continue;
     const float* src = W(h.*(m.w));
@@ -297,9 +298,10 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
           const __half a = __float2half_rn(x);
           const __half b = __float2half_rn(x - __half2float(a));
           const size_t off = (size_t)n * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
-          unsigned char* tile = img + (size_t)kb * (2 * m.N * 128);
-          memcpy(tile + off, &a, 2);
-          memcpy(tile + (size_t)m.N * 128 + off, &b, 2);
+          const int half_rows = m.N / 2, r = n / half_rows;
+          unsigned char* tile = img + (size_t)kb * (2 * m.N * 128) + (size_t)r * (m.N * 128);  // this half: [hi | lo]
+          memcpy(tile + off - (size_t)r * half_rows * 128, &a, 2);
+          memcpy(tile + (size_t)half_rows * 128 + off - (size_t)r * half_rows * 128, &b, 2);
         }
   }
   return TH_OK;

@@ -82,7 +82,7 @@ int launch_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w
 //   W_gvf  = [V1 @ feature_fc | V1 @ rgb_res_0 | view_fc[:, 256:283] | 0(37)]  (K = 704)
 //            with V1 = view_fc[:, :256];  b = V1 @ b_f + b_view
 struct PackedHeader {
-  uint32_t magic;      // 'THW2'
+  uint32_t magic;      // 'THW3'
   int32_t n_views;
   uint64_t total_bytes;
   // fp32 matrices, row-major (N, K) with K contiguous; offsets in bytes from blob start
@@ -104,7 +104,7 @@ struct PackedHeader {
   // fp16 hi/lo tile images for the tensor-core path (see th_pack_weights)
   uint64_t h_fc0, h_ar0, h_k0, h_k1, h_v, h_fc1, h_fc2, h_fc3m, h_f, h_view, h_t, h_fc1f, h_gvf;
 };
-constexpr uint32_t PACK_MAGIC = 0x32574854u;
+constexpr uint32_t PACK_MAGIC = 0x33574854u;
 
 // Byte offset of the hi element (row, col) of a (rows, C) activation in tile-image
 // format; the lo element sits 16384 bytes further.

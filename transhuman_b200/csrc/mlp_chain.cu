@@ -306,43 +306,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp == LOADER_WARP) {
     // ===================== loader =====================
+    // One thread; its per-k-block path is kept short (incremental pointers and stage index, two bulk
+    // copies: the A tile image and this CTA's contiguous [hi | lo] share of the weight k-block)
+    // because at ~6 cycles per dependent instruction a long path makes the loader the bottleneck.
     if (lane == 0) {
-      uint32_t kcount = 0;
-      int it = 0;
-      for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
+      uint32_t s = 0, ph = 0;  // stage index and its phase bit
+      const int n_it_loader = cluster_id < pg.num_units ? (pg.num_units - cluster_id + nclusters - 1) / nclusters : 0;
+      for (int it = 0; it < n_it_loader; ++it) {
+        const int u = cluster_id + it * nclusters;
         const int64_t ptile = 2 * (int64_t)u + rank;
+        const uint32_t done_target = (uint32_t)EPI_WARPS * (uint32_t)(it + 1);
+        const uint32_t mix_target = (uint32_t)(MIX_THREADS / 32) * (uint32_t)(it + 1);
         for (int j = 0; j < njobs; ++j) {
           const Job& jb = pg.job[j];
-          const uint32_t half_b = (uint32_t)(jb.N / 2) * 128u, plane = (uint32_t)jb.N * 128u;
-          int kb = 0;
-          for (int sgi = 0; sgi < jb.nseg; ++sgi) {
+          const uint32_t b_bytes = (uint32_t)jb.N * 128u;  // N/2 rows x 128 B x (hi, lo)
+          const unsigned char* w = jb.wimg + (size_t)rank * b_bytes;
+          const uint32_t w_step = 2u * b_bytes, tx = TILE_IMG + b_bytes;
+          const int nseg = jb.nseg;
+          for (int sgi = 0; sgi < nseg; ++sgi) {
             const Seg& sg = jb.seg[sgi];
+            const int kbs = sg.kbs, dep_mix = sg.dep_mix;
+            const bool from_chunk = sg.img != nullptr;
+            const unsigned char* src = from_chunk ? sg.img + (size_t)(sg.tile_off + ptile) * kbs * TILE_IMG
+                                                  : scratch + sg.scratch_off;
+            // chunk inputs stream through L2 once (evict first); scratch tiles and weights are the
+            // working set that should stay resident (evict last)
+            const uint64_t pol = from_chunk ? L2_EVICT_FIRST : L2_EVICT_LAST;
             if (sg.dep >= 0) {
-              TH_TIMED(0, wait_counter(cnt_job + 4 * sg.dep, (uint32_t)EPI_WARPS * (uint32_t)(it + 1), 2));
-              __threadfence();  // cumulative: covers the epilogue warps' stores observed through the counter
-              fence_proxy_async_all();
+              TH_TIMED(0, wait_counter(cnt_job + 4 * sg.dep, done_target, 2));
+              // cumulative: covers the epilogue warps' stores observed through the counter
+              TH_TIMED(4, __threadfence(); fence_proxy_async_all());
             }
-            for (int kk = 0; kk < sg.kbs; ++kk, ++kb, ++kcount) {
-              if (sg.dep_mix) {
+            for (int kk = 0; kk < kbs; ++kk) {
+              if (dep_mix) {
                 // one counter per k-block: the mix warps are not in lockstep
-                TH_TIMED(1, wait_counter(cnt_mix + 4 * kk, (uint32_t)(MIX_THREADS / 32) * (uint32_t)(it + 1), 3));
-                __threadfence();
-                fence_proxy_async_all();
+                TH_TIMED(1, wait_counter(cnt_mix + 4 * kk, mix_target, 3));
+                TH_TIMED(4, __threadfence(); fence_proxy_async_all());
               }
               jitter(pg.dbg, 16);
-              const uint32_t s = kcount % NSTAGE, ph = (kcount / NSTAGE) & 1;
               TH_TIMED(2, mbar_wait(bar_empty + 8 * s, ph ^ 1));
-              const uint32_t sa = base + s * STAGE_BYTES;
-              mbar_arrive_expect_tx(bar_full + 8 * s, TILE_IMG + 2 * half_b);
-              const unsigned char* src =
-                  sg.img ? sg.img + ((size_t)(sg.tile_off + ptile) * sg.kbs + kk) * TILE_IMG
-                         : scratch + sg.scratch_off + (size_t)kk * TILE_IMG;
-              // chunk inputs stream through L2 once (evict first); scratch tiles and weights are the
-              // working set that must stay resident (evict last)
-              bulk_g2s_hint(sa, src, TILE_IMG, bar_full + 8 * s, sg.img ? L2_EVICT_FIRST : L2_EVICT_LAST);
-              const unsigned char* w = jb.wimg + (size_t)kb * (2 * plane) + (size_t)rank * half_b;
-              bulk_g2s_hint(sa + TILE_IMG, w, half_b, bar_full + 8 * s, L2_EVICT_LAST);
-              bulk_g2s_hint(sa + TILE_IMG + half_b, w + plane, half_b, bar_full + 8 * s, L2_EVICT_LAST);
+              const long long t_issue = stats ? clock64() : 0;
+              const uint32_t sa = base + s * STAGE_BYTES, bar = bar_full + 8 * s;
+              mbar_arrive_expect_tx(bar, tx);
+              bulk_g2s_hint(sa, src, TILE_IMG, bar, pol);
+              bulk_g2s_hint(sa + TILE_IMG, w, b_bytes, bar, L2_EVICT_LAST);
+              if (stats) tw[3] += clock64() - t_issue;
+              src += TILE_IMG;
+              w += w_step;
+              if (++s == NSTAGE) {
+                s = 0;
+                ph ^= 1;
+              }
             }
           }
         }
@@ -352,7 +366,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     if (lane == 0) {
       if (rank == 0) {
         // ===================== MMA issuer (leader CTA) =====================
-        uint32_t kcount = 0, G = 0;
+        uint32_t s = 0, ph = 0, G = 0;
         int it = 0;
         for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
           const uint32_t flip = (it & 1) ? flip_on : 0u;
@@ -369,8 +383,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             const uint32_t d_tmem = tmem_base + (((uint32_t)jb.tmem_col + flip) & 511u);
             const uint32_t idesc = (1u << 4) | ((uint32_t)(jb.N >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
             const uint32_t half_b = (uint32_t)(jb.N / 2) * 128u;
-            for (int kb = 0; kb < jb.nkb; ++kb, ++kcount) {
-              const uint32_t s = kcount % NSTAGE, ph = (kcount / NSTAGE) & 1;
+            const int nkb = jb.nkb;
+            for (int kb = 0; kb < nkb; ++kb) {
               TH_TIMED(1, mbar_wait(bar_full + 8 * s, ph));
               TH_TIMED(2, mbar_wait(bar_pfull + 8 * s, ph));
               tc_fence_after();
@@ -385,20 +399,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
                 umma_f16_2cta(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
               }
               umma_commit_2cta(bar_empty + 8 * s);
+              if (++s == NSTAGE) {
+                s = 0;
+                ph ^= 1;
+              }
             }
             umma_commit_2cta(bar_tfull + 8 * (G & 1));
           }
         }
       } else {
         // ===================== relay (peer CTA): forward "stage full" to the leader =====================
-        uint32_t kcount = 0;
+        uint32_t s = 0, ph = 0;
         for (int u = cluster_id; u < pg.num_units; u += nclusters)
-          for (int j = 0; j < njobs; ++j)
-            for (int kb = 0; kb < pg.job[j].nkb; ++kb, ++kcount) {
-              const uint32_t s = kcount % NSTAGE, ph = (kcount / NSTAGE) & 1;
+          for (int j = 0; j < njobs; ++j) {
+            const int nkb = pg.job[j].nkb;
+            for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(bar_full + 8 * s, ph);
               mbar_arrive_remote(bar_pfull + 8 * s, 0);
+              if (++s == NSTAGE) {
+                s = 0;
+                ph ^= 1;
+              }
             }
+          }
       }
     }
   } else {
@@ -806,7 +829,7 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     TH_CUDA(cudaStreamSynchronize(st));
     if (printed++ < 4 || (printed % 64) == 0) {
       const char* names[4][7] = {
-          {"dep", "mix", "empty", "-", "-", "-", "total"},
+          {"dep", "mix", "empty", "issue", "fence", "-", "total"},
           {"epi(tmem)", "full", "pfull", "-", "-", "-", "total"},
           {"bar", "tfull", "store", "w_img", "w_scores", "w_heads", "total"},
           {"scores", "work", "-", "-", "-", "-", "total"}};

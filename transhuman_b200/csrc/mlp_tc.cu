@@ -218,9 +218,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
               bulk_g2s(sa, sg.img + ((size_t)tl * seg_kbs + kk) * (2 * A_TILE_BYTES), 2 * A_TILE_BYTES,
                        bar_full + 8 * s);
             }
-            const unsigned char* src = a.wimg + (size_t)kb * (2 * C::PLANE_BYTES) + (size_t)rank * C::HALF_BYTES;
-            bulk_g2s(sa + 2 * A_TILE_BYTES, src, C::HALF_BYTES, bar_full + 8 * s);
-            bulk_g2s(sa + 2 * A_TILE_BYTES + C::HALF_BYTES, src + C::PLANE_BYTES, C::HALF_BYTES, bar_full + 8 * s);
+            // this CTA's half of the k-block: [hi | lo], contiguous in the packed image
+            const unsigned char* src = a.wimg + (size_t)kb * (2 * C::PLANE_BYTES) + (size_t)rank * (2 * C::HALF_BYTES);
+            bulk_g2s(sa + 2 * A_TILE_BYTES, src, 2 * C::HALF_BYTES, bar_full + 8 * s);
           }
         }
       }
