@@ -152,8 +152,9 @@ __device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
   return make_float2(h.x + l.x, h.y + l.y);
 }
 
+constexpr int STATS_PER_CTA = 32 + 3 * MAX_JOBS;  // role totals + per-job MMA waits
 constexpr int ATAB_LD = 9;  // attention table row stride (floats): V x V <= 9 entries per point
-constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 2 * 256 * 4 + 128 * ATAB_LD * 4 + 256;
+constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 2 * 256 * 4 + 128 * ATAB_LD * 4 + 128 * 4 * 4 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     k_chain(const __grid_constant__ Program pg) {
@@ -161,8 +162,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   const uint32_t base = smem_u32(smem_raw);
   float* s_bias = reinterpret_cast<float*>(smem_raw + NSTAGE * STAGE_BYTES);  // 2 x 256
   float* s_atab = s_bias + 512;                                               // 128 x ATAB_LD
-  unsigned char* ctrl_ptr = reinterpret_cast<unsigned char*>(s_atab + 128 * ATAB_LD);
-  const uint32_t ctrl = base + NSTAGE * STAGE_BYTES + 2048 + 128 * ATAB_LD * 4;
+  float* s_part = s_atab + 128 * ATAB_LD;                                     // 128 x 4 partial scores
+  unsigned char* ctrl_ptr = reinterpret_cast<unsigned char*>(s_part + 128 * 4);
+  const uint32_t ctrl = base + NSTAGE * STAGE_BYTES + 2048 + 128 * ATAB_LD * 4 + 128 * 4 * 4;
   const uint32_t bar_full = ctrl, bar_empty = ctrl + 24, bar_pfull = ctrl + 48, bar_tfull = ctrl + 72;
   // counters (u32): epilogue-done of this CTA / of the peer, scores, mix per k-block [4], stored tile per job
   const uint32_t cnt_epi = ctrl + 96, cnt_epi_peer = ctrl + 100, cnt_scores = ctrl + 104, cnt_mix = ctrl + 112,
@@ -204,7 +206,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // optional wait-time accounting (one slot per question; cycles summed over the launch)
-  unsigned long long* stats = pg.stats ? pg.stats + (size_t)blockIdx.x * 32 : nullptr;
+  unsigned long long* stats = pg.stats ? pg.stats + (size_t)blockIdx.x * STATS_PER_CTA : nullptr;
   long long tw[6] = {0, 0, 0, 0, 0, 0};
 #define TH_TIMED(slot, stmt)            \
   do {                                  \
@@ -373,6 +375,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           for (int j = 0; j < njobs; ++j, ++G) {
             const Job& jb = pg.job[j];
             jitter(pg.dbg, 32);
+            const long long w0 = tw[0], w1 = tw[1], w2 = tw[2];
             if ((int32_t)(G - jb.wait_back) >= 0) {
               // one counter per CTA: warps of a CTA stay within one job of each other (named barrier),
               // the two CTAs of the pair do not
@@ -405,6 +408,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
               }
             }
             umma_commit_2cta(bar_tfull + 8 * (G & 1));
+            if (stats) {  // per-job split of the three waits (leader CTA only)
+              stats[32 + 3 * j + 0] += (unsigned long long)(tw[0] - w0);
+              stats[32 + 3 * j + 1] += (unsigned long long)(tw[1] - w1);
+              stats[32 + 3 * j + 2] += (unsigned long long)(tw[2] - w2);
+            }
           }
         }
       } else {
@@ -515,21 +523,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           }
           __syncwarp();
           if (lane == 0) add_release_local(cnt_job + 4 * j);
-        } else if (grp != 0) {
-          // the per-point epilogues below are group 0's
         } else if (epi == EPI_SCORES) {
           // A[i][j] = (KP_i + b0) . (KS_j + b1) / sqrt(128) for i = this job's view; the key embeds of
-          // every view j sit in TMEM (EPI_KEEP jobs).  One thread = one point, no shuffles.
+          // every view j sit in TMEM (EPI_KEEP jobs).  One thread = one point, no shuffles; the two
+          // warps of a lane quadrant take 64 of the 128 key channels each and group 1 hands its
+          // partial sums over through shared memory.
           float sc[TH_MAX_VIEWS];
 #pragma unroll
           for (int jv = 0; jv < TH_MAX_VIEWS; ++jv) sc[jv] = 0.f;
 #pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
+          for (int c0 = 64 * grp; c0 < 64 * grp + 64; c0 += 32) {
             uint32_t kp[32];
             tmem_ld32(taddr + c0, kp);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int e = 0; e < 32; ++e) kp[e] = __float_as_uint(__uint_as_float(kp[e]) + bias_s[c0 + e]);
+            for (int e = 0; e < 32; e += 4) {
+              const float4 bq = *reinterpret_cast<const float4*>(bias_s + c0 + e);
+              kp[e + 0] = __float_as_uint(__uint_as_float(kp[e + 0]) + bq.x);
+              kp[e + 1] = __float_as_uint(__uint_as_float(kp[e + 1]) + bq.y);
+              kp[e + 2] = __float_as_uint(__uint_as_float(kp[e + 2]) + bq.z);
+              kp[e + 3] = __float_as_uint(__uint_as_float(kp[e + 3]) + bq.w);
+            }
 #pragma unroll
             for (int jv = 0; jv < TH_MAX_VIEWS; ++jv)
               if (jv < V) {
@@ -537,10 +551,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
                 tmem_ld32(lane_addr + (((uint32_t)pg.ks_col[jv] + flip) & 511u) + c0, ks);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int e = 0; e < 32; ++e)
-                  sc[jv] = fmaf(__uint_as_float(kp[e]), __uint_as_float(ks[e]) + bias_s[128 + c0 + e], sc[jv]);
+                for (int e = 0; e < 32; e += 4) {
+                  const float4 bq = *reinterpret_cast<const float4*>(bias_s + 128 + c0 + e);
+                  sc[jv] = fmaf(__uint_as_float(kp[e + 0]), __uint_as_float(ks[e + 0]) + bq.x, sc[jv]);
+                  sc[jv] = fmaf(__uint_as_float(kp[e + 1]), __uint_as_float(ks[e + 1]) + bq.y, sc[jv]);
+                  sc[jv] = fmaf(__uint_as_float(kp[e + 2]), __uint_as_float(ks[e + 2]) + bq.z, sc[jv]);
+                  sc[jv] = fmaf(__uint_as_float(kp[e + 3]), __uint_as_float(ks[e + 3]) + bq.w, sc[jv]);
+                }
               }
           }
+          if (grp == 1) {
+#pragma unroll
+            for (int jv = 0; jv < TH_MAX_VIEWS; ++jv) s_part[et * 4 + jv] = sc[jv];
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (grp == 0) {
+#pragma unroll
+          for (int jv = 0; jv < TH_MAX_VIEWS; ++jv) sc[jv] += s_part[et * 4 + jv];
           const int i = jb.view;
 #pragma unroll
           for (int jv = 0; jv < TH_MAX_VIEWS; ++jv)
@@ -562,6 +589,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             __syncwarp();
             if (lane == 0) add_release_local(cnt_scores);
           }
+          }  // grp == 0
+        } else if (grp != 0) {
+          // the per-point head epilogues below are group 0's
         } else if (epi == EPI_ALPHA) {
           // alpha = relu(O) . alpha_fc + b (cross_transformer.py:324-328): O never leaves the SM
           float acc = 0.f;
@@ -816,15 +846,15 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
   pg.dbg = dbg_env ? atoi(dbg_env) : 0;
   static unsigned long long* d_stats = nullptr;
   if (want_stats) {
-    if (!d_stats) TH_CUDA(cudaMalloc(&d_stats, (size_t)num_sms * 32 * 8));
-    TH_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)num_sms * 32 * 8, st));
+    if (!d_stats) TH_CUDA(cudaMalloc(&d_stats, (size_t)num_sms * STATS_PER_CTA * 8));
+    TH_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)num_sms * STATS_PER_CTA * 8, st));
     pg.stats = d_stats;
   }
   k_chain<<<2 * nclusters, NUM_THREADS, SMEM_BYTES, st>>>(pg);
   TH_LAUNCHED();
   if (want_stats) {
     static int printed = 0;
-    std::vector<unsigned long long> hs((size_t)num_sms * 32);
+    std::vector<unsigned long long> hs((size_t)num_sms * STATS_PER_CTA);
     TH_CUDA(cudaMemcpyAsync(hs.data(), d_stats, hs.size() * 8, cudaMemcpyDeviceToHost, st));
     TH_CUDA(cudaStreamSynchronize(st));
     if (printed++ < 4 || (printed % 64) == 0) {
@@ -839,11 +869,21 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
         for (int i = 0; i < 7; ++i) {
           if (names[r][i][0] == '-') continue;
           double lead = 0, peer = 0;
-          for (int c = 0; c < 2 * nclusters; ++c) (c & 1 ? peer : lead) += (double)hs[(size_t)c * 32 + r * 8 + i];
+          for (int c = 0; c < 2 * nclusters; ++c) (c & 1 ? peer : lead) += (double)hs[(size_t)c * STATS_PER_CTA + r * 8 + i];
           fprintf(stderr, " %s=%.0f/%.0f", names[r][i], lead / nclusters / 1e3, peer / nclusters / 1e3);
         }
         fprintf(stderr, "  (kcycles per CTA, leader/peer; units=%d clusters=%d)\n", pg.num_units, nclusters);
       }
+      fprintf(stderr, "[chain stats] MMA waits per job (kcycles per unit: tmem/full/pfull):");
+      for (int j = 0; j < pg.njobs; ++j) {
+        double w[3] = {0, 0, 0};
+        for (int c = 0; c < 2 * nclusters; c += 2)
+          for (int k = 0; k < 3; ++k) w[k] += (double)hs[(size_t)c * STATS_PER_CTA + 32 + 3 * j + k];
+        const double units = (double)pg.num_units;
+        fprintf(stderr, " j%d[N%d K%d]=%.1f/%.1f/%.1f", j, pg.job[j].N, pg.job[j].nkb * 64, w[0] / units / 1e3,
+                w[1] / units / 1e3, w[2] / units / 1e3);
+      }
+      fprintf(stderr, "\n");
     }
   }
   return TH_OK;
