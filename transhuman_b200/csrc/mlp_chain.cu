@@ -139,17 +139,46 @@ __device__ __forceinline__ void st32_keep(void* p, uint4 a, uint4 b) {
                "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(L2_EVICT_LAST)
                : "memory");
 }
-__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __floats2half2_rn(x, y);
-  float2 hf = __half22float2(h);
-  __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+// Packed fp32x2 arithmetic (FADD2 / FFMA2 on sm_100): same rounding as the scalar forms, half the
+// issue slots -- the epilogue and the mix are bound by instruction issue, not by memory.
+__device__ __forceinline__ unsigned long long pk2(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 up2(unsigned long long r) {
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+  return up2(d);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+  return up2(d);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+  return up2(d);
+}
+__device__ __forceinline__ void split2(float2 v, uint32_t& hi, uint32_t& lo) {
+  __half2 h = __floats2half2_rn(v.x, v.y);
+  const float2 r = sub2(v, __half22float2(h));
+  __half2 l = __floats2half2_rn(r.x, r.y);
   hi = *reinterpret_cast<uint32_t*>(&h);
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  split2(make_float2(x, y), hi, lo);
+}
 __device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
-  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-  const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lo));
-  return make_float2(h.x + l.x, h.y + l.y);
+  return add2(__half22float2(*reinterpret_cast<const __half2*>(&hi)),
+              __half22float2(*reinterpret_cast<const __half2*>(&lo)));
 }
 
 constexpr int STATS_PER_CTA = 32 + 3 * MAX_JOBS;  // role totals + per-job MMA waits
@@ -274,15 +303,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  float ox = 0.f, oy = 0.f;
+                  float2 o = make_float2(0.f, 0.f);
 #pragma unroll
                   for (int i = 0; i < CHAIN_MAX_V; ++i)
                     if (i < V) {
                       const float a = A[i * V + j];
-                      ox = fmaf(a, x[i][e].x, ox);
-                      oy = fmaf(a, x[i][e].y, oy);
+                      o = fma2(make_float2(a, a), x[i][e], o);
                     }
-                  split2(ox, oy, hi[e], lo[e]);
+                  split2(o, hi[e], lo[e]);
                 }
                 unsigned char* dst = xbase + (size_t)j * SCR_ACT + off;
                 st16_keep(dst, make_uint4(hi[0], hi[1], hi[2], hi[3]));
@@ -480,19 +508,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
               uint4 hi[2], lo[2];
 #pragma unroll
               for (int cc = 0; cc < 2; ++cc) {
-                float x[8];
                 const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + half * 16 + cc * 8);
                 const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + half * 16 + cc * 8 + 4);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                      make_float2(b1.z, b1.w)};
+                float2 x[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  x[e] = __uint_as_float(v[half * 16 + cc * 8 + e]) + bb[e];
-                  if (relu) x[e] = fmaxf(x[e], 0.f);
+                for (int e = 0; e < 4; ++e) {
+                  x[e] = add2(make_float2(__uint_as_float(v[half * 16 + cc * 8 + 2 * e]),
+                                          __uint_as_float(v[half * 16 + cc * 8 + 2 * e + 1])),
+                              bb[e]);
+                  if (relu) {
+                    x[e].x = fmaxf(x[e].x, 0.f);
+                    x[e].y = fmaxf(x[e].y, 0.f);
+                  }
                 }
-                split2(x[0], x[1], hi[cc].x, lo[cc].x);
-                split2(x[2], x[3], hi[cc].y, lo[cc].y);
-                split2(x[4], x[5], hi[cc].z, lo[cc].z);
-                split2(x[6], x[7], hi[cc].w, lo[cc].w);
+                split2(x[0], hi[cc].x, lo[cc].x);
+                split2(x[1], hi[cc].y, lo[cc].y);
+                split2(x[2], hi[cc].z, lo[cc].z);
+                split2(x[3], hi[cc].w, lo[cc].w);
               }
               // logical chunks (2m, 2m+1) -> physical (2m ^ x, (2m+1) ^ x), x = row & 7: same sector,
               // halves swapped when x is odd
