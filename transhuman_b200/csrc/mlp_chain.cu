@@ -7,16 +7,24 @@
 // through every job of the program -- one job = one layer applied to one view's
 // 128-row tile -- before it moves to the next unit, so that
 //   * activations between layers live in a small per-CTA scratch (768 KB) that is
-//     written by the epilogue's bulk stores and read back by the loader's bulk
-//     copies while it is still in L2 -- no HBM round trip, no second launch;
+//     written by the epilogue warps (32-byte stores straight into the tile image) and
+//     read back by the loader's bulk copies while it is still in L2 -- no second launch,
+//     HBM sees the chunk inputs plus whatever part of the 115 MB of scratch L2 evicts;
 //   * the cross-view attention needs no kernel of its own: the key embeds stay in
 //     TMEM, the 3x3 scores and their softmax are computed by the epilogue threads
-//     (one thread = one point), and the otherwise idle warps 0-7 mix X in place;
+//     (one thread = one point), and the otherwise idle warps 0-5 mix X in place;
 //   * the alpha / rgb heads are dot products inside the fc_3 / fc_4 epilogues.
+// Roles (16 warps = 4 per scheduler, 128 registers each): warps 0-5 mix, 6 loader,
+// 7 MMA issuer (leader CTA) / stage-full relay (peer CTA), 8-15 epilogue (two per
+// TMEM lane quadrant).
 // All synchronisation is CTA- or cluster-local (same rows stay on the same CTA):
 //   stage full/empty mbarriers (loader <-> MMA), tfull mbarriers (MMA -> epilogue),
-//   and monotonic shared-memory counters for epilogue -> MMA (TMEM reuse),
-//   epilogue -> loader (a stored activation may be loaded), scores -> mix -> loader.
+//   and monotonic shared-memory counters for epilogue -> MMA (TMEM reuse, one counter
+//   per CTA of the pair), epilogue -> loader (a stored tile may be loaded: CTA-scope
+//   release by the writers, gpu-scope + proxy fence by the loader after its acquire),
+//   scores -> mix -> loader (one counter per k-block).  Every counter has one
+//   spinning reader; TH_CHAIN_DBG=16|32|64|128 delays the roles at random and the
+//   tests demand bit-identical output under it.
 // The MMA scheme (fp16 hi/lo split, 3 products, cta_group::2, M = 256) and the tile
 // image format are those of mlp_tc.cu.
 #include <stdlib.h>
