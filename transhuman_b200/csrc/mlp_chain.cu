@@ -14,9 +14,10 @@
 //     TMEM, the 3x3 scores and their softmax are computed by the epilogue threads
 //     (one thread = one point), and the otherwise idle warps 0-5 mix X in place;
 //   * the alpha / rgb heads are dot products inside the fc_3 / fc_4 epilogues.
-// Roles (16 warps = 4 per scheduler, 128 registers each): warps 0-5 mix, 6 loader,
-// 7 MMA issuer (leader CTA) / stage-full relay (peer CTA), 8-15 epilogue (two per
-// TMEM lane quadrant).
+// Roles (16 warps = 4 per scheduler, 128 registers each): warps 0-5 mix, 6 loader
+// (2-D TMA copies of tile images; both CTAs' bytes complete on the leader's stage
+// barrier, cta_group::2, so there is no relay between the CTAs), 7 MMA issuer (leader
+// CTA only), 8-15 epilogue (two per TMEM lane quadrant).
 // All synchronisation is CTA- or cluster-local (same rows stay on the same CTA):
 //   stage full/empty mbarriers (loader <-> MMA), tfull mbarriers (MMA -> epilogue),
 //   and monotonic shared-memory counters for epilogue -> MMA (TMEM reuse, one counter
@@ -27,6 +28,7 @@
 //   tests demand bit-identical output under it.
 // The MMA scheme (fp16 hi/lo split, 3 products, cta_group::2, M = 256) and the tile
 // image format are those of mlp_tc.cu.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include <vector>
@@ -71,6 +73,12 @@ struct Job {
   int32_t nseg, nkb, N, relu, epi, tmem_col, wait_back, view;
 };
 struct Program {
+  // TMA descriptors: tile images as rows of 64 fp16 (128 B).  tm_a: box 256 rows (one 32 KB hi|lo
+  // k-block of an A tile) over the chunk workspace; tm_b256 / tm_b128: box N rows (one CTA's [hi | lo]
+  // share of a weight k-block) over the packed weight blob.
+  CUtensorMap tm_a, tm_b256, tm_b128;
+  const unsigned char* a_base;  // first byte tm_a covers
+  const unsigned char* w_base;  // first byte tm_b* cover
   Job job[MAX_JOBS];
   unsigned char* scratch;
   const float *afc_w, *afc_b, *rgb_w, *rgb_b;
@@ -360,6 +368,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           const uint32_t b_bytes = (uint32_t)jb.N * 128u;  // N/2 rows x 128 B x (hi, lo)
           const unsigned char* w = jb.wimg + (size_t)rank * b_bytes;
           const uint32_t w_step = 2u * b_bytes, tx = TILE_IMG + b_bytes;
+          const CUtensorMap* b_map = jb.N == 256 ? &pg.tm_b256 : &pg.tm_b128;
           const int nseg = jb.nseg;
           for (int sgi = 0; sgi < nseg; ++sgi) {
             const Seg& sg = jb.seg[sgi];
@@ -384,10 +393,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
               jitter(pg.dbg, 16);
               TH_TIMED(2, mbar_wait(bar_empty + 8 * s, ph ^ 1));
               const long long t_issue = stats ? clock64() : 0;
-              const uint32_t sa = base + s * STAGE_BYTES, bar = bar_full + 8 * s;
-              mbar_arrive_expect_tx(bar, tx);
-              bulk_g2s_hint(sa, src, TILE_IMG, bar, pol);
-              bulk_g2s_hint(sa + TILE_IMG, w, b_bytes, bar, L2_EVICT_LAST);
+              // both CTAs' bytes are counted by the leader's barrier: the leader arms it for the pair
+              const uint32_t sa = base + s * STAGE_BYTES, bar = (bar_full + 8 * s) & PEER_BIT_MASK;
+              if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * tx);
+              tma2d_pair(sa, &pg.tm_a, 0, (int)((src - pg.a_base) >> 7), bar, pol);
+              tma2d_pair(sa + TILE_IMG, b_map, 0, (int)((w - pg.w_base) >> 7), bar, L2_EVICT_LAST);
               if (stats) tw[3] += clock64() - t_issue;
               src += TILE_IMG;
               w += w_step;
@@ -424,8 +434,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             const uint32_t half_b = (uint32_t)(jb.N / 2) * 128u;
             const int nkb = jb.nkb;
             for (int kb = 0; kb < nkb; ++kb) {
-              TH_TIMED(1, mbar_wait(bar_full + 8 * s, ph));
-              TH_TIMED(2, mbar_wait(bar_pfull + 8 * s, ph));
+              TH_TIMED(1, mbar_wait(bar_full + 8 * s, ph));  // both CTAs' halves of the stage
               tc_fence_after();
               const uint32_t sa = base + s * STAGE_BYTES;
               const uint64_t d_ahi = umma_desc(sa), d_alo = umma_desc(sa + A_TILE_BYTES);
@@ -452,20 +461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           }
         }
       } else {
-        // ===================== relay (peer CTA): forward "stage full" to the leader =====================
-        uint32_t s = 0, ph = 0;
-        for (int u = cluster_id; u < pg.num_units; u += nclusters)
-          for (int j = 0; j < njobs; ++j) {
-            const int nkb = pg.job[j].nkb;
-            for (int kb = 0; kb < nkb; ++kb) {
-              mbar_wait(bar_full + 8 * s, ph);
-              mbar_arrive_remote(bar_pfull + 8 * s, 0);
-              if (++s == NSTAGE) {
-                s = 0;
-                ph ^= 1;
-              }
-            }
-          }
+        // (peer CTA: nothing to do -- its tensor copies complete on the leader's barriers)
       }
     }
   } else {
@@ -773,6 +769,38 @@ size_t chain_scratch_bytes(int64_t P, int V, int num_sms) {
 }
 bool chain_supported(int V) { return V >= 1 && V <= chain::CHAIN_MAX_V; }
 
+namespace chain {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// rows of 64 fp16 over [base, base + bytes), box = 64 x box_rows, no swizzle (the images are pre-swizzled)
+static int make_rows_map(CUtensorMap* m, const void* base, size_t bytes, int box_rows) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+      set_error("mlp_forward_chain: cuTensorMapEncodeTiled is not available");
+      return TH_ECUDA;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t gdim[2] = {64, (cuuint64_t)(bytes / 128)};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("mlp_forward_chain: cuTensorMapEncodeTiled failed (%d) base %p bytes %zu box %d", (int)r, base, bytes,
+              box_rows);
+    return TH_ECUDA;
+  }
+  return TH_OK;
+}
+}  // namespace chain
+
 // The whole per-point network for one chunk in ONE launch.  Inputs (rep, pix, pix_mean, vd)
 // are the tile images the feature kernel wrote; `scratch` holds chain_scratch_bytes().
 int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader& h, unsigned char* scratch,
@@ -856,6 +884,18 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     }
   }
   Program& pg = B.pg;
+  {
+    // A operands: everything from the first chunk input (rep) to the end of the view-direction image
+    // lies in one workspace block (mlp_carve), the scratch included
+    const unsigned char* a0 = reinterpret_cast<const unsigned char*>(b.rep);
+    const unsigned char* a1 = reinterpret_cast<const unsigned char*>(b.vd) + (size_t)Pp * 2 * VD_LD * 4;
+    int rc;
+    if ((rc = make_rows_map(&pg.tm_a, a0, (size_t)(a1 - a0), 256))) return rc;
+    if ((rc = make_rows_map(&pg.tm_b256, run.weights, (size_t)h.total_bytes, 256))) return rc;
+    if ((rc = make_rows_map(&pg.tm_b128, run.weights, (size_t)h.total_bytes, 128))) return rc;
+    pg.a_base = a0;
+    pg.w_base = run.weights;
+  }
   pg.scratch = scratch;
   pg.afc_w = wf(h.afc_w);
   pg.afc_b = wf(h.afc_b);

@@ -71,6 +71,19 @@ __device__ __forceinline__ void bulk_s2g_hint(void* dst, uint32_t src, uint32_t 
                "r"(bytes), "l"(policy)
                : "memory");
 }
+// 2-D tensor copy (TMA) of a CTA pair: each CTA fetches into its OWN shared memory, but the bytes are
+// counted by the barrier of the pair's leader CTA (`bar` with the peer bit cleared), so the thread
+// that issues tcgen05.mma.cta_group::2 waits on one barrier for both halves -- no relay between
+// the CTAs.  The non-tensor cp.async.bulk has no such form (its barrier must be local).
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // shared::cluster address: bit 24 = CTA rank within the pair
+__device__ __forceinline__ void tma2d_pair(uint32_t dst, const void* tmap, int c0, int c1, uint32_t leader_bar,
+                                           uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
