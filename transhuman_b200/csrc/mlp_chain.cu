@@ -99,6 +99,12 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(uint32_t addr) {
   asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+// for opportunistic reads that a fence.acq_rel follows (relaxed load + fence = acquire)
+__device__ __forceinline__ uint32_t ld_relaxed_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.relaxed.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 // `nap` nanoseconds between polls: a spinning single thread otherwise competes for issue slots with
 // the epilogue warp that shares its scheduler.
 __device__ __forceinline__ void wait_counter(uint32_t addr, uint32_t target, int what, unsigned nap = 32) {
@@ -363,6 +369,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         const int64_t ptile = 2 * (int64_t)u + rank;
         const uint32_t done_target = (uint32_t)EPI_WARPS * (uint32_t)(it + 1);
         const uint32_t mix_target = (uint32_t)(MIX_THREADS / 32) * (uint32_t)(it + 1);
+        // What this thread's fences already cover in this unit: bit j = the tile job j stored, bit kb = the
+        // mix of k-block kb.  A fence executed after a counter was seen complete orders those stores before
+        // every later copy, so each dependency costs one wait + fence per unit, not one per reader -- a
+        // fence is ~1-2 kcycles here and sits between "tile stored" and the dependent job's first copy.
+        uint32_t dep_seen = 0, mix_seen = 0;
         for (int j = 0; j < njobs; ++j) {
           const Job& jb = pg.job[j];
           const uint32_t b_bytes = (uint32_t)jb.N * 128u;  // N/2 rows x 128 B x (hi, lo)
@@ -379,15 +390,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             // chunk inputs stream through L2 once (evict first); scratch tiles and weights are the
             // working set that should stay resident (evict last)
             const uint64_t pol = from_chunk ? L2_EVICT_FIRST : L2_EVICT_LAST;
-            if (sg.dep >= 0) {
+            if (sg.dep >= 0 && !((dep_seen >> sg.dep) & 1u)) {
               TH_TIMED(0, wait_counter(cnt_job + 4 * sg.dep, done_target, 2));
-              // cumulative: covers the epilogue warps' stores observed through the counter
+              // whatever else is stored by now rides on the same fence
+              for (int j2 = 0; j2 < njobs; ++j2)
+                if ((int32_t)(ld_relaxed_u32(cnt_job + 4 * j2) - done_target) >= 0) dep_seen |= 1u << j2;
+              // cumulative: covers the epilogue warps' stores observed through the counters
               TH_TIMED(4, __threadfence(); fence_proxy_async_all());
             }
             for (int kk = 0; kk < kbs; ++kk) {
-              if (dep_mix) {
+              if (dep_mix && !((mix_seen >> kk) & 1u)) {
                 // one counter per k-block: the mix warps are not in lockstep
                 TH_TIMED(1, wait_counter(cnt_mix + 4 * kk, mix_target, 3));
+                for (int k2 = kk; k2 < 4; ++k2)
+                  if ((int32_t)(ld_relaxed_u32(cnt_mix + 4 * k2) - mix_target) >= 0) mix_seen |= 1u << k2;
                 TH_TIMED(4, __threadfence(); fence_proxy_async_all());
               }
               jitter(pg.dbg, 16);
