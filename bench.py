@@ -320,7 +320,7 @@ def main():
                 "l2_bytes_per_launch": l2_bytes,
                 "l2_tbs_live": (l2_bytes * (gemm_launches // args.steps) / (gemm_ms_step * 1e-3) / 1e12
                                 if l2_bytes and gemm_ms_step > 0 else None),
-                "binding": "job-pipeline latency (epilogue ~ MMA time per job, serial attention sections); L2->SM at ~80 % of its practical cap" if chain else "HBM (K=256 layers) / tensor (K>=512)",
+                "binding": "job-pipeline latency (epilogue ~ MMA time per job; the attention mix, 768 KB per unit and CTA, runs at the ~20 B/clk of SM<->L2 bandwidth the operand stream leaves it); L2->SM at ~80 % of its practical cap" if chain else "HBM (K=256 layers) / tensor (K>=512)",
                 "hbm_algorithmic_gbs": BYTES_PER_RAY * N_rays / (ms_step * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
     breakdown = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
