@@ -1,6 +1,7 @@
 #!/bin/bash
-# A/B of the feature kernel's schedules on one GPU box: prints rays/s and the per-category split.
-# usage: tools/feat_ab.sh <tag> "<env assignments>" ...
+# A/B of environment settings (TH_CHAIN_*, TH_CHUNK_PTS, ...) on one GPU box: one short bench run per
+# setting, prints rays/s and the per-category split.
+# usage: tools/env_ab.sh <tag> "<env assignments>" ...
 tag=$1; shift
 mkdir -p gpurun_out
 i=0
