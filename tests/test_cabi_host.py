@@ -63,8 +63,8 @@ def test_pack_weights_folds_layers(lib):
         assert lib.th_pack_weights(C.byref(wstruct), V, blob.ctypes.data, 16) == -2
         assert b"need" in lib.th_last_error()
         magic, nviews, total = struct.unpack_from("<IiQ", blob, 0)
-        assert magic == 0x33574854 and nviews == V and total == pw_bytes
-        offs = struct.unpack_from("<43Q", blob, 16)
+        assert magic == 0x34574854 and nviews == V and total == pw_bytes
+        offs = struct.unpack_from("<54Q", blob, 16)
         f32 = lambda off, n: blob[off:off + 4 * n].view(np.float32)
         # fc_0: K padded 255 -> 256 with a zero column
         fc0 = f32(offs[0], 256 * 256).reshape(256, 256)
@@ -113,6 +113,96 @@ def test_pack_weights_folds_layers(lib):
         rec = np.concatenate([np.take_along_axis(img[kb, 0], col, 1) + np.take_along_axis(img[kb, 1], col, 1)
                               for kb in range(4)], axis=1)
         assert np.abs(rec - fc0).max() <= 2.0 ** -21 * np.abs(fc0).max()
+
+
+def _pack(lib, w, V):
+    wstruct = _lib.ThWeightsF32()
+    keep = []
+    for cname, rname in _lib.WEIGHT_FIELDS:
+        for suf, key in (("w", rname + ".weight"), ("b", rname + ".bias")):
+            a = np.ascontiguousarray(w[key].reshape(-1))
+            keep.append(a)
+            setattr(wstruct, f"{cname}_{suf}", a.ctypes.data)
+    blob = np.zeros(lib.th_packed_weights_bytes(V), dtype=np.uint8)
+    assert lib.th_pack_weights(C.byref(wstruct), V, blob.ctypes.data, blob.size) == 0
+    return blob
+
+
+# order of the (w, b) offset pairs in PackedHeader (kernels.cuh), then the image offsets
+_MATS = ["fc0", "ar0", "k0", "k1", "v", "fc1", "fc2", "fc3m", "afc", "f", "view", "t", "rgb", "fc1f", "gvf",
+         "pre", "gvfp", "tp", "xid"]
+
+
+def _matrices(blob, V):
+    offs = struct.unpack_from("<54Q", blob, 16)
+    # the image offsets of the first 13 matrices sit between gvf and pre in the header
+    pair = {name: (offs[2 * i], offs[2 * i + 1]) for i, name in enumerate(_MATS[:15])}
+    pair.update({name: (offs[43 + 2 * i], offs[43 + 2 * i + 1]) for i, name in enumerate(_MATS[15:])})
+    shapes = {"fc0": (256, 256), "ar0": (256, 384), "k0": (128, 256), "k1": (128, 256), "v": (256, 512),
+              "fc1": (256, 256), "fc2": (256, 256), "fc3m": (256, 256 * V), "afc": (1, 256), "f": (256, 640),
+              "view": (128, 320), "t": (128, 128 * V + 384), "rgb": (3, 128), "fc1f": (256, 512), "gvf": (128, 704),
+              "pre": (512, 384), "gvfp": (128, 448), "tp": (128, 128 * V + 128), "xid": (256, 256)}
+    out = {}
+    for name, (ow, ob) in pair.items():
+        n, k = shapes[name]
+        out[name] = (torch.from_numpy(blob[ow:ow + 4 * n * k].view(np.float32).reshape(n, k).astype(np.float64)),
+                     torch.from_numpy(blob[ob:ob + 4 * n].view(np.float32).astype(np.float64)))
+    return out
+
+
+@pytest.mark.parametrize("V", [1, 3])
+def test_packed_programs_reproduce_the_network(lib, V):
+    """The layer programs the tensor-core schedules run, evaluated in float64 straight from the packed blob
+    -- the default one (folded fc_1' and view_fc') and the pre-mapped one (DESIGN.md section 5, round-2 item 1:
+    alpha_res_0 / rgb_res_0 / rgb_res_1 applied to the maps, identity blocks in view_fc' and fc_4') --
+    against the oracle's MLP in float64.  Checks every fold, transpose, 1/V and bias of th_pack_weights."""
+    from oracle import transhuman_oracle as orc
+    w = synth.make_weights(seed=7)
+    m = _matrices(_pack(lib, w, V), V)
+    g = torch.Generator().manual_seed(3)
+    P = 64
+    rep = torch.randn((V, 255, P), generator=g, dtype=torch.float64)
+    pix = torch.randn((V, 384, P), generator=g, dtype=torch.float64)
+    vd = torch.randn((1, P, 27), generator=g, dtype=torch.float64)
+    w64 = {k: torch.from_numpy(np.asarray(v)).double() for k, v in w.items()}
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        want = orc.mlp_forward(w64, rep, pix, vd, progressive=False)[0]            # (P,4) = rgb, alpha
+    finally:
+        torch.set_default_dtype(old)
+
+    lin = lambda name, x: x @ m[name][0].T + m[name][1]                          # x (rows, K)
+    relu = torch.relu
+    rep_r = torch.cat([rep.permute(0, 2, 1), torch.zeros((V, P, 1), dtype=torch.float64)], -1)   # (V,P,256)
+    pix_r = pix.permute(0, 2, 1)                                                   # (V,P,384)
+    vd_r = torch.cat([vd[0], torch.zeros((P, 37), dtype=torch.float64)], -1)       # (P,64)
+
+    def program(premapped):
+        S = relu(lin("fc0", rep_r))
+        if premapped:
+            pre = lin("pre", pix_r)                                                # what the blended pre-mapped map holds
+            X = lin("xid", relu(pre[..., :256]))
+            P2, R = pre[..., 256:384], pre[..., 384:].sum(0)
+        else:
+            X = relu(lin("ar0", pix_r))
+        KP, KS = lin("k0", X), lin("k1", S)
+        A = torch.softmax(torch.einsum("ipc,jpc->pij", KP, KS) / np.sqrt(128.0), dim=1)   # over i
+        XT = torch.einsum("pij,ipc->jpc", A, X)
+        inter = relu(lin("fc2", relu(lin("fc1f", torch.cat([S, XT], -1)))))
+        alpha = lin("afc", relu(lin("fc3m", torch.cat(list(inter), -1))))
+        if premapped:
+            G = relu(lin("gvfp", torch.cat([inter, P2, vd_r.expand(V, P, 64)], -1)))
+            T = relu(lin("tp", torch.cat(list(G) + [R], -1)))
+        else:
+            G = relu(lin("gvf", torch.cat([inter, pix_r, vd_r.expand(V, P, 64)], -1)))
+            T = relu(lin("t", torch.cat(list(G) + [pix_r.mean(0)], -1)))
+        return torch.cat([lin("rgb", T), alpha], -1)
+
+    scale = want.abs().max().item()
+    for premapped in (False, True):
+        got = program(premapped)
+        assert (got - want).abs().max().item() <= 2e-6 * max(1.0, scale), premapped
 
 
 def test_workspace_bytes(lib):

@@ -97,6 +97,10 @@ static std::vector<MatSpec> mat_specs(int V) {
       {&H::rgb_w, &H::rgb_b, nullptr, 3, 128},
       {&H::fc1f_w, &H::fc1f_b, &H::h_fc1f, 256, 512},
       {&H::gvf_w, &H::gvf_b, &H::h_gvf, 128, 704},
+      {&H::pre_w, &H::pre_b, nullptr, 512, 384},
+      {&H::gvfp_w, &H::gvfp_b, &H::h_gvfp, 128, 448},
+      {&H::tp_w, &H::tp_b, &H::h_tp, 128, 128 * V + 128},
+      {&H::xid_w, &H::xid_b, &H::h_xid, 256, 256},
   };
 }
 
@@ -283,6 +287,26 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
   }
   memcpy(W(h.rgb_w), w->rgb_fc_w, 3 * 128 * 4);
   memcpy(W(h.rgb_b), w->rgb_fc_b, 3 * 4);
+  // pre-mapped feature maps (kernels.cuh): built from the folded matrices above
+  {
+    const int ldt = 128 * V + 384, ldp = 128 * V + 128;
+    memcpy(W(h.pre_w), W(h.ar0_w), (size_t)256 * 384 * 4);
+    memcpy(W(h.pre_b), W(h.ar0_b), 256 * 4);  // rows 256..511 keep a zero bias
+    for (int n = 0; n < 128; ++n) {
+      for (int k = 0; k < 384; ++k) {
+        W(h.pre_w)[(size_t)(256 + n) * 384 + k] = W(h.gvf_w)[(size_t)n * 704 + 256 + k];
+        W(h.pre_w)[(size_t)(384 + n) * 384 + k] = (float)((double)W(h.t_w)[(size_t)n * ldt + 128 * V + k] / V);
+      }
+      for (int k = 0; k < 256; ++k) W(h.gvfp_w)[(size_t)n * 448 + k] = W(h.gvf_w)[(size_t)n * 704 + k];
+      W(h.gvfp_w)[(size_t)n * 448 + 256 + n] = 1.0f;
+      for (int k = 0; k < 64; ++k) W(h.gvfp_w)[(size_t)n * 448 + 384 + k] = W(h.gvf_w)[(size_t)n * 704 + 640 + k];
+      W(h.gvfp_b)[n] = W(h.gvf_b)[n];
+      for (int k = 0; k < 128 * V; ++k) W(h.tp_w)[(size_t)n * ldp + k] = W(h.t_w)[(size_t)n * ldt + k];
+      W(h.tp_w)[(size_t)n * ldp + 128 * V + n] = 1.0f;
+      W(h.tp_b)[n] = W(h.t_b)[n];
+    }
+    for (int n = 0; n < 256; ++n) W(h.xid_w)[(size_t)n * 256 + n] = 1.0f;
+  }
   // fp16 hi/lo split of the GEMM matrices, stored as shared-memory tile images for
   // the tensor-core path: per 64-wide k-block and per half of the N rows (one half per CTA of a
   // cta_group::2 pair) [hi image | lo image], each N/2 rows of 128 bytes, K-major with the 128-byte

@@ -82,7 +82,7 @@ int launch_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w
 //   W_gvf  = [V1 @ feature_fc | V1 @ rgb_res_0 | view_fc[:, 256:283] | 0(37)]  (K = 704)
 //            with V1 = view_fc[:, :256];  b = V1 @ b_f + b_view
 struct PackedHeader {
-  uint32_t magic;      // 'THW3'
+  uint32_t magic;      // 'THW4'
   int32_t n_views;
   uint64_t total_bytes;
   // fp32 matrices, row-major (N, K) with K contiguous; offsets in bytes from blob start
@@ -103,8 +103,22 @@ struct PackedHeader {
   uint64_t gvf_w, gvf_b;        // (128,704)
   // fp16 hi/lo tile images for the tensor-core path (see th_pack_weights)
   uint64_t h_fc0, h_ar0, h_k0, h_k1, h_v, h_fc1, h_fc2, h_fc3m, h_f, h_view, h_t, h_fc1f, h_gvf;
+  // Pre-mapped feature maps (packed, not yet consumed by a kernel):
+  // the three 1x1 convolutions that read the bilinear blend of the feature maps commute with the
+  // blend, so they can be applied once per frame to the (V,H,W,384) maps instead of once per point:
+  //   W_pre = [alpha_res_0 ; V1 @ rgb_res_0 ; fc_4 @ rgb_res_1 / V]  (512,384), b_pre = [b_ar0 ; 0 ; 0]
+  //           (the other two biases already sit in b_gvf and b_t; bilinear weights sum to 1)
+  //   W_gvfp = [V1 @ feature_fc | I_128 | view_fc[:, 256:283] | 0(37)]  (K = 448): the blended rows
+  //            256..383 of the pre-mapped map enter view_fc' through an identity block
+  //   W_tp   = [fc_4/V | ... | fc_4/V | I_128]  (K = 128 V + 128): the view sum of rows 384..511
+  //   W_xid  = I_256: copies the blended, rectified rows 0..255 (= X_v) into the chain kernel's scratch
+  uint64_t pre_w, pre_b;        // (512,384), (512)
+  uint64_t gvfp_w, gvfp_b;      // (128,448)
+  uint64_t tp_w, tp_b;          // (128,128*V+128)
+  uint64_t xid_w, xid_b;        // (256,256), zero bias
+  uint64_t h_gvfp, h_tp, h_xid;
 };
-constexpr uint32_t PACK_MAGIC = 0x33574854u;
+constexpr uint32_t PACK_MAGIC = 0x34574854u;
 
 // Byte offset of the hi element (row, col) of a (rows, C) activation in tile-image
 // format; the lo element sits 16384 bytes further.
