@@ -58,6 +58,11 @@ extern "C" {
 #define TH_FLAG_WHITE_BKGD 1u /* cfg.white_bkgd, nerf_net_utils.py:56-57 */
 #define TH_FLAG_SIMT_MLP 2u   /* force the fp32 CUDA-core GEMM path (debug / parity) */
 #define TH_FLAG_LAYERWISE 4u  /* tcgen05 GEMMs one layer per launch instead of the layer-chained kernel (cross-check) */
+/* EXPERIMENTAL (not yet validated on a GPU, off by default):
+ * `feat` holds the PRE-MAPPED maps (V, H, W, 512) written by th_premap_features -- alpha_res_0,
+ * rgb_res_0 and rgb_res_1 (cross_transformer.py:315, 333, 343) applied to the maps once per frame
+ * instead of to every blended sample.  Layer-chained tensor-core schedule only (V <= 3, k = 7). */
+#define TH_FLAG_PREMAPPED 8u
 
 /* Per-frame state: the outputs of the (out-of-scope, torch) prologue that the
  * query path consumes.  Built once per frame by the Python Renderer. */
@@ -214,6 +219,12 @@ int th_integrate(const float* raw, const float* z_vals, const float* ray_d, int6
                  void* stream);
 /* layout helper: (V,C,H,W) -> (V,H,W,C). */
 int th_nchw_to_nhwc(const float* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
+/* EXPERIMENTAL, with TH_FLAG_PREMAPPED: encoder output `pixel_feat_map` (V,384,H,W) NCHW
+ * (encoder.py:133-146) -> pre-mapped maps (V,H,W,512) channel-last =
+ * [alpha_res_0 F + b | view_fc[:, :256] rgb_res_0 F | fc_4 rgb_res_1 F / V], weights from the packed
+ * blob (device pointer, th_pack_weights).  Replaces th_nchw_to_nhwc for such a frame. */
+int th_premap_features(const float* feat_nchw, const void* packed_weights, int32_t n_views, int32_t h, int32_t w,
+                       float* out, void* stream);
 
 /* Optional device-time profile: between start and stop every kernel launch is
  * bracketed by CUDA events on its stream; stop synchronises the device and

@@ -1,0 +1,66 @@
+"""OPT-IN (TH_TEST_PREMAP=1) GPU tests of the experimental pre-mapped feature-map path
+(TH_FLAG_PREMAPPED).  The path was written at the end of
+round 1 without GPU time left to run it, so it is off by default and these tests are skipped unless
+asked for; the packed matrices it uses ARE checked on the CPU (tests/test_cabi_host.py)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import transhuman_oracle as orc
+from tests.gpu_util import frame_to_device
+from transhuman_b200 import ops, synth
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("TH_TEST_PREMAP") != "1", reason="experimental path: TH_TEST_PREMAP=1")]
+DEV = "cuda:0"
+
+
+def _frame(**kw):
+    fr = synth.make_frame(H=20, W=20, n_class=300, V=3, feat_hw=28, seed=21, alpha_bias_shift=-12.0, **kw)
+    tf = orc.to_torch_frame(fr)
+    return fr, tf, orc.build_tokens(tf)
+
+
+def test_premap_kernel_matches_conv():
+    fr, tf, _ = _frame()
+    wts = ops.PackedWeights(fr["weights"], 3, device=DEV)
+    offs = struct.unpack_from("<54Q", wts.host, 16)
+    w_pre = torch.from_numpy(wts.host[offs[43]:offs[43] + 4 * 512 * 384].view(np.float32).reshape(512, 384).copy())
+    b_pre = torch.from_numpy(wts.host[offs[44]:offs[44] + 4 * 512].view(np.float32).copy())
+    fmap = tf["pixel_feat_map"]
+    got = ops.premap_features(fmap.to(DEV), wts).cpu()
+    want = torch.nn.functional.conv2d(fmap.double(), w_pre.double()[:, :, None, None], b_pre.double()).permute(0, 2, 3, 1)
+    assert (got.double() - want).abs().max().item() <= 2e-5 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("mode", ["dense", "culled"])
+def test_premapped_render_matches_oracle_and_default_path(mode):
+    fr, tf, tokens = _frame()
+    S = 16
+    want = orc.render(tf, S, tokens=tokens) if mode == "dense" else \
+        orc.render_fast(tf, S, tokens=tokens, train_branch_max_rays=0)
+    m = ops.TH_RENDER_DENSE if mode == "dense" else ops.TH_RENDER_MASKED
+    f0, rays = frame_to_device(fr, tokens, DEV)
+    f1, _ = frame_to_device(fr, tokens, DEV, premapped=True)
+    base = ops.render_rays(f0, *rays, S, mode=m, want_raw=True)
+    got = ops.render_rays(f1, *rays, S, mode=m, want_raw=True)
+    torch.cuda.synchronize()
+    assert (got["rgb_map"].cpu() - want["rgb_map"][0]).abs().max().item() <= 1e-4
+    assert (got["acc_map"].cpu() - want["acc_map"][0]).abs().max().item() <= 1e-4
+    scale = max(1.0, base["raw"].abs().max().item())
+    assert (got["raw"] - base["raw"]).abs().max().item() <= 1e-5 * scale
+
+
+def test_premapped_density_query():
+    fr, tf, tokens = _frame()
+    f0, _ = frame_to_device(fr, tokens, DEV)
+    f1, _ = frame_to_device(fr, tokens, DEV, premapped=True)
+    v = torch.from_numpy(fr["tar_smpl_vertice"]).to(DEV)
+    pts = (v[::7] + 0.02 * torch.randn((v[::7].shape[0], 3), device=DEV, generator=torch.Generator(DEV).manual_seed(1)))
+    a0, m0 = ops.query_density(f0, pts.contiguous())
+    a1, m1 = ops.query_density(f1, pts.contiguous())
+    assert torch.equal(m0, m1)
+    assert (a0 - a1).abs().max().item() <= 1e-5 * max(1.0, a0.abs().max().item())

@@ -18,6 +18,7 @@ TH_MAX_KNN = 16
 TH_FLAG_WHITE_BKGD = 1
 TH_FLAG_SIMT_MLP = 2
 TH_FLAG_LAYERWISE = 4
+TH_FLAG_PREMAPPED = 8  # experimental, see include/transhuman_b200.h
 TH_RENDER_DENSE, TH_RENDER_MASKED, TH_RENDER_FAST = 0, 1, 2
 TH_TRAIN_BRANCH_MAX_RAYS = 2400
 
@@ -86,6 +87,7 @@ SIGNATURES = {
     "th_mlp_raw": (C.c_int, [C.POINTER(ThFrame), _fp, _fp, _fp, _fp, C.c_int64, _fp, _fp, C.c_size_t, _fp]),
     "th_integrate": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp]),
     "th_nchw_to_nhwc": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp]),
+    "th_premap_features": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp, _fp]),
 }
 
 _lib = None

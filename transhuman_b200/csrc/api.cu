@@ -465,6 +465,11 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
     fo.do_vd = alpha_only ? 0 : 1;
     fo.rep_pad = 1;
     const int use_tc = (f->flags & TH_FLAG_SIMT_MLP) ? 0 : 1;
+    const bool premapped = (f->flags & TH_FLAG_PREMAPPED) != 0;
+    if (premapped && !(use_tc && !(f->flags & TH_FLAG_LAYERWISE) && chain_supported(V) && fr.K == 7)) {
+      set_error("TH_FLAG_PREMAPPED needs the layer-chained tensor-core schedule (V <= 3, k = 7, no SIMT/LAYERWISE flag)");
+      return TH_EUNSUPPORTED;
+    }
     if (use_tc) {  // the feature kernel writes the GEMM operands directly as fp16 hi/lo tile images
       fo.rep_img = reinterpret_cast<unsigned char*>(b.rep);
       fo.pix_img = reinterpret_cast<unsigned char*>(b.pix);
@@ -472,10 +477,12 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
       fo.vd_img = reinterpret_cast<unsigned char*>(b.vd);
       fo.img_view_rows = Pp;
       fo.pix_mean = nullptr;
+      if (premapped)  // pix block = [X (V*Pp,256) | P2 (V*Pp,128)], pix_mean block = R (Pp,128): see k_features PRE
+        fo.pix = alpha_only ? nullptr : b.pix + (size_t)V * Pp * 256;
     }
     src.ids = ids;
     src.first = first;
-    int rc = launch_features(fr, src, P, fo, st);
+    int rc = launch_features(fr, src, P, fo, st, premapped);
     if (rc) return rc;
     MlpRun run{};
     run.weights = static_cast<const unsigned char*>(f->weights);
@@ -489,6 +496,7 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
     run.zero_rgb_if_transparent = zero_rgb;
     run.use_tensor_cores = use_tc;
     run.inputs_are_images = use_tc;
+    run.premapped = premapped ? 1 : 0;
     // one layer-chained launch per chunk (mlp_chain.cu) unless TH_CHAIN=0 asks for the
     // layer-at-a-time schedule; its scratch is the (otherwise unused) S/X/XT/NET/KP/KS block
     static const int use_chain = [] {
@@ -502,11 +510,15 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
       TH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const size_t scratch_room = (size_t)Pp * V * (256 * 4 + 128 * 2) * 4;  // b.s ... b.ks are contiguous
-    if (use_tc && use_chain && !(f->flags & TH_FLAG_LAYERWISE) && chain_supported(V) &&
-        chain_scratch_bytes(P, V, num_sms) <= scratch_room)
+    if (use_tc && (use_chain || premapped) && !(f->flags & TH_FLAG_LAYERWISE) && chain_supported(V) &&
+        chain_scratch_bytes(P, V, num_sms) <= scratch_room) {
       rc = mlp_forward_chain(run, b, hdr, reinterpret_cast<unsigned char*>(b.s), nullptr, st);
-    else
+    } else if (premapped) {
+      set_error("TH_FLAG_PREMAPPED: the layer-chained schedule is not available for this chunk");
+      rc = TH_EUNSUPPORTED;
+    } else {
       rc = mlp_forward(run, b, hdr, st);
+    }
     if (rc) return rc;
   }
   return TH_OK;
@@ -760,6 +772,23 @@ int th_integrate(const float* raw, const float* z_vals, const float* ray_d, int6
   PointSource src{};
   return launch_integrate(raw, nullptr, src, z_vals, ray_d, n_rays, n_samples, white_bkgd, rgb_map, acc_map,
                           depth_map, static_cast<cudaStream_t>(stream));
+}
+
+int th_premap_features(const float* feat_nchw, const void* packed_weights, int32_t n_views, int32_t h, int32_t w,
+                       float* out, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TH_CHECK_ARG(feat_nchw && packed_weights && out, "null pointer");
+  TH_CHECK_ARG(n_views >= 1 && n_views <= TH_MAX_VIEWS && h >= 1 && w >= 1, "bad argument");
+  PackedHeader hdr;
+  TH_CUDA(cudaMemcpyAsync(&hdr, packed_weights, sizeof(PackedHeader), cudaMemcpyDeviceToHost, st));
+  TH_CUDA(cudaStreamSynchronize(st));
+  if (hdr.magic != PACK_MAGIC) {
+    set_error("th_premap_features: bad weights blob");
+    return TH_EINVAL;
+  }
+  const unsigned char* blob = static_cast<const unsigned char*>(packed_weights);
+  return launch_premap(feat_nchw, reinterpret_cast<const float*>(blob + hdr.pre_w),
+                       reinterpret_cast<const float*>(blob + hdr.pre_b), out, n_views, h, w, st);
 }
 
 int th_nchw_to_nhwc(const float* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w, void* stream) {

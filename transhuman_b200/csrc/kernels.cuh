@@ -61,7 +61,9 @@ int launch_expand_rays(const uint8_t* ray_any, int64_t n_points, int S, uint8_t*
 int launch_world2smpl(const float* pts, int64_t n, const float* Rh, const float* Th, float* out, cudaStream_t st);
 int launch_view_embed(const float* ray_d, int64_t n_rays, float* out, cudaStream_t st);
 int launch_features(const FrameDev& fr, const PointSource& src, int64_t n_points, const FeatOut& out,
-                    cudaStream_t st);
+                    cudaStream_t st, bool premapped = false);
+int launch_premap(const float* src_nchw, const float* w_pre, const float* b_pre, float* dst, int n_views, int h, int w,
+                  cudaStream_t st);
 int launch_integrate(const float* raw, const uint8_t* mask, const PointSource& src, const float* z_vals,
                      const float* ray_d, int64_t n_rays, int S, int white_bkgd, float* rgb, float* acc,
                      float* depth, cudaStream_t st);
@@ -163,6 +165,9 @@ struct MlpRun {
   int zero_rgb_if_transparent;
   int use_tensor_cores;
   int inputs_are_images;  // rep / pix / pix_mean / vd buffers hold tile images (fused path)
+  // experimental (TH_FLAG_PREMAPPED, chain schedule only): the pix block holds the images
+  // [X (V*Pp,256) | P2 (V*Pp,128)] and pix_mean the image R (Pp,128) -- see k_features PRE
+  int premapped;
 };
 // Pp = pad_points(P): view stride of every buffer in `b`.
 int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& hdr_host, cudaStream_t st);

@@ -833,9 +833,16 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
   auto wf = [&](uint64_t off) { return reinterpret_cast<const float*>(run.weights + off); };
   Builder B(V, Pp);
   int j_s[TH_MAX_VIEWS], j_x[TH_MAX_VIEWS], j_n1[TH_MAX_VIEWS], j_int[TH_MAX_VIEWS], j_g[TH_MAX_VIEWS];
+  // Pre-mapped inputs (experimental): the feature kernel has already blended alpha_res_0 F + b, so X_v
+  // arrives as a 256-wide image and is only copied into the scratch (identity weights, exact: hi + lo
+  // of the operand times 1.0); P2_v (128 wide, behind X in the pix block) and R (128 wide, in the
+  // pix_mean block) enter view_fc' / fc_4' through identity blocks of W_gvfp / W_tp.
+  const bool pre = run.premapped != 0;
+  const float* p2_img = b.pix + (size_t)V * Pp * 256;
   // front: X_v = relu(alpha_res_0 pix_v) -> slot B ; S_v = relu(fc_0 rep_v) -> slot A
   for (int v = 0; v < V; ++v)
-    j_x[v] = B.add({B.in_view(b.pix, PIX_LD, v)}, wimg(h.h_ar0), wf(h.ar0_b), 256, 1, EPI_IMG, B.slotB(v));
+    j_x[v] = pre ? B.add({B.in_view(b.pix, 256, v)}, wimg(h.h_xid), nullptr, 256, 1, EPI_IMG, B.slotB(v))
+                 : B.add({B.in_view(b.pix, PIX_LD, v)}, wimg(h.h_ar0), wf(h.ar0_b), 256, 1, EPI_IMG, B.slotB(v));
   for (int v = 0; v < V; ++v)
     j_s[v] = B.add({B.in_view(b.rep, REP_LD, v)}, wimg(h.h_fc0), wf(h.fc0_b), 256, 1, EPI_IMG, B.slotA(v));
   // key embeds: KS_v = key_embed_1 S_v stays in TMEM; KP_v = key_embed_0 X_v is consumed by the score epilogue
@@ -874,8 +881,11 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     add_fc3();
   } else {
     auto add_gvf = [&](int v) {
-      j_g[v] = B.add({Builder::scr(B.slotA(v), 256, j_int[v]), B.in_view(b.pix, PIX_LD, v), B.in_point(b.vd, 64)},
-                     wimg(h.h_gvf), wf(h.gvf_b), 128, 1, EPI_IMG, B.slotB(v));
+      j_g[v] = pre ? B.add({Builder::scr(B.slotA(v), 256, j_int[v]), B.in_view(p2_img, 128, v), B.in_point(b.vd, 64)},
+                           wimg(h.h_gvfp), wf(h.gvfp_b), 128, 1, EPI_IMG, B.slotB(v))
+                   : B.add({Builder::scr(B.slotA(v), 256, j_int[v]), B.in_view(b.pix, PIX_LD, v),
+                            B.in_point(b.vd, 64)},
+                           wimg(h.h_gvf), wf(h.gvf_b), 128, 1, EPI_IMG, B.slotB(v));
     };
     for (int v = 0; v + 1 < V; ++v) add_gvf(v);
     add_fc3();
@@ -888,10 +898,11 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
         jb.seg[jb.nseg++] = Builder::scr(B.slotB(v), 128, j_g[v]);
         jb.nkb += 2;
       }
-      jb.seg[jb.nseg++] = B.in_point(b.pix_mean, PIX_LD);
-      jb.nkb += PIX_LD / 64;
-      jb.wimg = wimg(h.h_t);
-      jb.bias = wf(h.t_b);
+      const int c_tail = pre ? 128 : PIX_LD;  // R (pre-mapped) or the view mean of pix
+      jb.seg[jb.nseg++] = B.in_point(b.pix_mean, c_tail);
+      jb.nkb += c_tail / 64;
+      jb.wimg = wimg(pre ? h.h_tp : h.h_t);
+      jb.bias = wf(pre ? h.tp_b : h.t_b);
       jb.N = 128;
       jb.relu = 1;
       jb.epi = EPI_RGB;

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (TH_FLAG_LAYERWISE, TH_FLAG_SIMT_MLP, TH_FLAG_WHITE_BKGD, TH_RENDER_DENSE, TH_RENDER_FAST, TH_RENDER_MASKED,
+from ._lib import (TH_FLAG_LAYERWISE, TH_FLAG_PREMAPPED, TH_FLAG_SIMT_MLP, TH_FLAG_WHITE_BKGD, TH_RENDER_DENSE, TH_RENDER_FAST, TH_RENDER_MASKED,
                    ThFrame, ThOut, ThRays, ThWeightsF32)
 
 __all__ = ["PackedWeights", "Frame", "render_rays", "query_density", "sample_points", "cull_knn1", "cull_grid",
@@ -110,7 +110,7 @@ class Frame:
     def __init__(self, *, holder, tok_xyz, tok_rot, verts, feat_nhwc, cam_R, cam_T, cam_K, Rh, Th,
                  weights: PackedWeights, uv_scale, knn: int = 7, knn_dist_alpha: float = 0.5,
                  cull_radius: float = 0.1, white_bkgd: bool = False, simt_mlp: bool = False,
-                 layerwise: bool = False):
+                 layerwise: bool = False, premapped: bool = False):
         self.holder = _f32(holder, "holder")
         V, n_tok, c = self.holder.shape
         assert c == 192, "token width must be 192"
@@ -118,7 +118,8 @@ class Frame:
         self.tok_rot = _f32(tok_rot, "tok_rot").view(n_tok, 3, 3)
         self.verts = _f32(verts, "verts").view(-1, 3)
         self.feat = _f32(feat_nhwc, "feat_nhwc")
-        assert self.feat.dim() == 4 and self.feat.shape[0] == V and self.feat.shape[3] == 384, \
+        # premapped (experimental): ``feat_nhwc`` is the output of ``premap_features`` (512 channels)
+        assert self.feat.dim() == 4 and self.feat.shape[0] == V and self.feat.shape[3] == (512 if premapped else 384), \
             "feature maps must be (V,H,W,384) channel-last"
         self.cam_R = _f32(cam_R, "cam_R").view(V, 3, 3)
         self.cam_T = _f32(cam_T, "cam_T").view(V, 3)
@@ -140,7 +141,7 @@ class Frame:
         f.uv_scale_x, f.uv_scale_y = float(uv_scale[0]), float(uv_scale[1])
         f.knn_dist_alpha, f.cull_radius = knn_dist_alpha, cull_radius
         f.flags = ((TH_FLAG_WHITE_BKGD if white_bkgd else 0) | (TH_FLAG_SIMT_MLP if simt_mlp else 0) |
-                   (TH_FLAG_LAYERWISE if layerwise else 0))
+                   (TH_FLAG_LAYERWISE if layerwise else 0) | (TH_FLAG_PREMAPPED if premapped else 0))
         self.c = f
 
     @property
@@ -326,4 +327,17 @@ def nchw_to_nhwc(x):
     n, c, h, w = x.shape
     out = torch.empty((n, h, w, c), device=x.device)
     _lib.check(lib.th_nchw_to_nhwc(_ptr(x), _ptr(out), n, c, h, w, _stream()), "th_nchw_to_nhwc")
+    return out
+
+
+def premap_features(x, weights: PackedWeights):
+    """EXPERIMENTAL (``TH_FLAG_PREMAPPED``): encoder maps (V,384,H,W) -> pre-mapped maps (V,H,W,512) with
+    ``alpha_res_0`` / ``rgb_res_0`` / ``rgb_res_1`` already applied (``th_premap_features``)."""
+    lib = _lib.load()
+    x = _f32(x, "x")
+    n, c, h, w = x.shape
+    assert c == 384 and n == weights.n_views
+    out = torch.empty((n, h, w, 512), device=x.device)
+    _lib.check(lib.th_premap_features(_ptr(x), weights.blob.data_ptr(), n, h, w, _ptr(out), _stream()),
+               "th_premap_features")
     return out
