@@ -49,6 +49,10 @@ CASES = {
                               signed=True),
     "c1_64x64x32": dict(frame=dict(H=64, W=64, n_class=300, V=3, feat_hw=64, seed=0), S=32, mode="culled",
                         signed=True),
+    # token counts of BASELINE configs[2] (kmeans_dict_1500) and configs[4] (6000 tokens), small ray sets
+    "tokens1500_dense": dict(frame=dict(H=12, W=12, n_class=1500, V=3, feat_hw=24, seed=6), S=32, mode="dense"),
+    "tokens6000_culled": dict(frame=dict(H=14, W=14, n_class=6000, V=3, feat_hw=24, seed=7), S=16, mode="culled",
+                              signed=True),
 }
 
 

@@ -17,6 +17,11 @@ if ROOT not in sys.path:
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["tiny_dense", "tiny_culled", "tiny_rotated", "oneshot_v1", "c1_64x64x32",
                 "culled_144x144x24"]
+# Token counts of BASELINE configs[2] / configs[4] (1500 / 6000 tokens) through the genuine reference.  Generated
+# after the round's last GPU minute: the CPU oracle is pinned to them now; the GPU golden test takes them in once
+# they have run on a B200 (the CUDA path is checked against the oracle at these token counts in
+# tests/test_gpu_fullsize.py).
+GOLDEN_CASES_MANY_TOKENS = ["tokens1500_dense", "tokens6000_culled"]
 
 
 def pytest_configure(config):

@@ -5,12 +5,12 @@ import numpy as np
 import pytest
 import torch
 
-from tests.conftest import GOLDEN_CASES, load_golden
+from tests.conftest import GOLDEN_CASES, GOLDEN_CASES_MANY_TOKENS, load_golden
 from oracle import transhuman_oracle as orc
 from transhuman_b200 import synth
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + GOLDEN_CASES_MANY_TOKENS)
 def test_oracle_matches_reference_golden(name):
     kw, S, mode, g = load_golden(name)
     if name == "c1_64x64x32":
@@ -29,7 +29,7 @@ def test_oracle_matches_reference_golden(name):
     np.testing.assert_allclose(out["depth_map"][0].numpy(), g["depth_map"], atol=1e-5, rtol=0)
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES[:4])
+@pytest.mark.parametrize("name", GOLDEN_CASES[:4] + GOLDEN_CASES_MANY_TOKENS)
 def test_oracle_stages_match_reference_golden(name):
     kw, S, mode, g = load_golden(name)
     frame = synth.make_frame(**kw)
