@@ -10,7 +10,7 @@ import sys
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import transhuman_oracle as orc  # noqa: E402  (checker only)
 from transhuman_b200 import synth  # noqa: E402

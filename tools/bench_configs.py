@@ -22,12 +22,13 @@ def c3():
 def c5(n=256, tokens=6000):
     import __graft_entry__ as entry
     entry.build()
-    from oracle import transhuman_oracle as orc
     from tests.gpu_util import frame_to_device
     from transhuman_b200 import ops, synth
+    from transhuman_b200.renderer import segment_mean
     fr = synth.make_frame(H=8, W=8, n_class=tokens, V=3, feat_hw=128, seed=5)
-    tf = orc.to_torch_frame(fr)
-    tokens_t = orc.build_tokens(tf)
+    pc2 = torch.from_numpy(fr["pc2voxel_ind"]).long()
+    tokens_t = (segment_mean(torch.from_numpy(fr["tar_smpl_vertice_smplcoord"]), pc2, tokens).float(),
+                segment_mean(torch.from_numpy(fr["blend_mtx"]), pc2, tokens))
     frame, _ = frame_to_device(fr, tokens_t, "cuda:0")
     v = fr["tar_smpl_vertice"]
     lo, hi = v.min(0) - 0.05, v.max(0) + 0.05
