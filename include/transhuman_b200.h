@@ -235,6 +235,13 @@ int th_premap_features(const float* feat_nchw, const void* packed_weights, int32
 int th_profile_start(void);
 int th_profile_stop(double* ms_per_category_host, int64_t* launches_per_category_host, int32_t n);
 
+/* Host-only test hook (needs no device): the job program the layer-chained kernel would run for a chunk
+ * of n_points, as a table of int64 (layout documented at the definition in csrc/mlp_chain.cu), so that a
+ * CPU test can interpret it against the oracle.  packed_host = the HOST copy of the th_pack_weights blob.
+ * Returns the number of words written, or a negative TH_E* code. */
+int64_t th_debug_chain_program(const void* packed_host, int32_t n_views, int64_t n_points, int32_t alpha_only,
+                               int32_t premapped, int64_t* table, int64_t capacity);
+
 /* Number of kernels this library launched on the calling thread since the last
  * reset (bench.py reports it as gpu_launches). */
 int64_t th_launch_count(int32_t reset);

@@ -1,0 +1,188 @@
+"""CPU check of the job program the layer-chained kernel runs (csrc/mlp_chain.cu).
+
+``th_debug_chain_program`` returns the program ``mlp_forward_chain`` builds -- jobs, their operand segments
+(scratch slots / chunk images), weight k-blocks, epilogue kinds, TMEM columns -- without touching a device.
+This test (1) checks its static invariants: segment and weight k-block counts add up, every scratch operand
+was stored by the job it names, TMEM columns are never overwritten while an epilogue may still read them;
+(2) INTERPRETS the program in float64 with the matrices of the packed blob and compares the result with the
+oracle's MLP.  It covers the default program, the density-only program and the experimental pre-mapped one,
+so a wiring mistake in a new program variant shows up here before it costs GPU time."""
+import ctypes as C
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from tests.test_cabi_host import _matrices, _pack, lib  # noqa: F401  (fixture)
+from transhuman_b200 import synth
+
+EPI_IMG, EPI_KEEP, EPI_SCORES, EPI_ALPHA, EPI_RGB = 0, 2, 3, 4, 5
+MAX_SEG = 5
+IMG_NAMES = ["fc0", "ar0", "k0", "k1", "v", "fc1", "fc2", "fc3m", "f", "view", "t", "fc1f", "gvf"]
+
+
+def _program(lib, blob, V, P, alpha_only, premapped):
+    cap = 8 + 28 * (16 + 6 * MAX_SEG)
+    table = np.zeros(cap, dtype=np.int64)
+    n = lib.th_debug_chain_program(blob.ctypes.data, V, P, alpha_only, premapped, table.ctypes.data, cap)
+    assert n > 0, n
+    head = table[:8]
+    jobs = []
+    for j in range(int(head[0])):
+        t = table[8 + j * (16 + 6 * MAX_SEG):8 + (j + 1) * (16 + 6 * MAX_SEG)]
+        keys = ["N", "relu", "epi", "out_off", "tmem_col", "wait_back", "view", "nseg", "nkb", "wimg", "bias", "bias2"]
+        job = {k: int(t[i]) for i, k in enumerate(keys)}
+        job["segs"] = [dict(zip(["chunk", "off", "tile_off", "kbs", "dep", "dep_mix"], map(int, t[16 + 6 * s:22 + 6 * s])))
+                       for s in range(job["nseg"])]
+        jobs.append(job)
+    return {"njobs": int(head[0]), "V": int(head[1]), "has_mix": int(head[2]), "alpha_only": int(head[3]),
+            "Pp": int(head[4]), "scr_act": int(head[5]), "tile_img": int(head[6])}, jobs
+
+
+def _images(blob, V):
+    offs = struct.unpack_from("<54Q", blob, 16)
+    shapes = {"fc0": (256, 256), "ar0": (256, 384), "k0": (128, 256), "k1": (128, 256), "v": (256, 512),
+              "fc1": (256, 256), "fc2": (256, 256), "fc3m": (256, 256 * V), "f": (256, 640), "view": (128, 320),
+              "t": (128, 128 * V + 384), "fc1f": (256, 512), "gvf": (128, 704), "gvfp": (128, 448),
+              "tp": (128, 128 * V + 128), "xid": (256, 256)}
+    img = {n: offs[30 + i] for i, n in enumerate(IMG_NAMES)}
+    img.update({"gvfp": offs[51], "tp": offs[52], "xid": offs[53]})
+    return {n: (o, shapes[n]) for n, o in img.items()}
+
+
+def _check_tmem(head, jobs):
+    """No job's MMAs may overwrite TMEM columns that an earlier epilogue can still read: job G starts after
+    the epilogue of job G - wait_back; kept key embeds are read by every score epilogue."""
+    n = head["njobs"]
+    flip_on = 256 if n & 1 else 0
+    last_scores = max((j for j, jb in enumerate(jobs) if jb["epi"] == EPI_SCORES), default=-1)
+    seq = []
+    for unit in range(3):
+        for j, jb in enumerate(jobs):
+            col = (jb["tmem_col"] + (flip_on if unit & 1 else 0)) & 511
+            assert col + jb["N"] <= 512
+            last_reader = unit * n + (last_scores if jb["epi"] == EPI_KEEP else j)
+            seq.append((col, col + jb["N"], last_reader, jb["wait_back"]))
+    for g, (c0, c1, _, wb) in enumerate(seq):
+        for a in range(g):
+            a0, a1, reader, _ = seq[a]
+            if a0 < c1 and c0 < a1:
+                assert g - wb >= reader, f"job {g} (wait_back {wb}) overwrites columns job {a} is read from until {reader}"
+
+
+def _interpret(blob, head, jobs, data):
+    """data: chunk buffers by name, each (views or 1, P, C) float64.  Returns raw (P,4) or alpha (P)."""
+    V, Pp, scr = head["V"], head["Pp"], head["scr_act"]
+    mats = _matrices(blob, V)
+    images = _images(blob, V)
+    f32 = lambda off, n: torch.from_numpy(blob[off:off + 4 * n].view(np.float32).astype(np.float64))
+    # chunk block (mlp_carve): byte offsets from the first buffer
+    o_pix = V * Pp * 256 * 4
+    o_pm = o_pix + V * Pp * 384 * 4 + 4 * V * Pp * 256 * 4 + 2 * V * Pp * 128 * 4
+    chunk = {0: "rep", o_pix: "pix", o_pix + V * Pp * 256 * 4: "p2", o_pm: "pix_mean", o_pm + Pp * 384 * 4: "vd"}
+    slots, written_by = {}, {}
+    KS, scores, alpha, out_final = {}, {}, None, None
+    for j, jb in enumerate(jobs):
+        parts = []
+        for sg in jb["segs"]:
+            C_ = sg["kbs"] * 64
+            if sg["chunk"]:
+                name = chunk[sg["off"]]
+                view = sg["tile_off"] // (Pp // 128)
+                assert sg["tile_off"] % (Pp // 128) == 0 and sg["dep"] == -1
+                buf = data[name]
+                assert buf.shape[-1] == C_, (j, name, buf.shape, C_)
+                parts.append(buf[view if buf.shape[0] > 1 else 0])
+            else:
+                assert sg["off"] % scr == 0
+                slot = sg["off"] // scr
+                assert slot in slots, f"job {j} reads scratch slot {slot} before anything stored it"
+                if sg["dep"] >= 0:
+                    assert written_by[slot] == sg["dep"] < j, (j, slot, written_by[slot], sg["dep"])
+                assert bool(sg["dep_mix"]) == (head["has_mix"] == 1 and slot >= V and jobs[written_by[slot]]["epi"] == EPI_IMG
+                                               and jb["epi"] == EPI_IMG and jb["N"] == 256 and len(jb["segs"]) == 2)
+                parts.append(slots[slot][:, :C_])
+        A = torch.cat(parts, -1)
+        assert A.shape[1] == jb["nkb"] * 64
+        name = next(n for n, (o, (N, K)) in images.items() if o <= jb["wimg"] < o + N * K * 4)
+        o, (N, K) = images[name]
+        assert N == jb["N"] and (jb["wimg"] - o) % (N * 256) == 0
+        kb0 = (jb["wimg"] - o) // (N * 256)
+        W = mats[name][0][:, kb0 * 64:kb0 * 64 + A.shape[1]]
+        assert W.shape[1] == A.shape[1], (j, name, kb0)
+        out = A @ W.T
+        bias = f32(jb["bias"], N) if jb["bias"] >= 0 else None
+        if jb["epi"] == EPI_IMG:
+            out = out + bias if bias is not None else out
+            out = torch.relu(out) if jb["relu"] else out
+            slot = jb["out_off"] // scr
+            assert jb["out_off"] % scr == 0
+            full = torch.zeros((out.shape[0], 256), dtype=torch.float64)
+            full[:, :N] = out
+            slots[slot], written_by[slot] = full, j
+        elif jb["epi"] == EPI_KEEP:
+            assert bias is None
+            KS[jb["view"]] = out
+        elif jb["epi"] == EPI_SCORES:
+            kp = out + bias
+            b2 = f32(jb["bias2"], 128)
+            for jv in range(V):
+                scores[(jb["view"], jv)] = (kp * (KS[jv] + b2)).sum(-1) / np.sqrt(128.0)
+            if jb["view"] == V - 1:
+                S_ = torch.stack([torch.stack([scores[(i, jv)] for jv in range(V)], -1) for i in range(V)], 1)  # (P,i,j)
+                Aw = torch.softmax(S_, dim=1)
+                if head["has_mix"] == 1:
+                    X = torch.stack([slots[V + i] for i in range(V)], 0)                      # (i,P,256)
+                    XT = torch.einsum("pij,ipc->jpc", Aw, X)
+                    for jv in range(V):
+                        slots[V + jv] = XT[jv]
+        elif jb["epi"] == EPI_ALPHA:
+            O = torch.relu(out + bias)
+            alpha = O @ mats["afc"][0][0] + mats["afc"][1][0]
+        elif jb["epi"] == EPI_RGB:
+            T = torch.relu(out + bias)
+            out_final = T @ mats["rgb"][0].T + mats["rgb"][1]
+        else:
+            raise AssertionError(f"job {j}: unknown epilogue {jb['epi']}")
+    return alpha if head["alpha_only"] else torch.cat([out_final, alpha[:, None]], -1)
+
+
+@pytest.mark.parametrize("V", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["default", "alpha_only", "premapped", "premapped_alpha_only"])
+def test_chain_program(lib, V, variant):
+    from oracle import transhuman_oracle as orc
+    w = synth.make_weights(seed=9)
+    blob = _pack(lib, w, V)
+    P = 200
+    premapped, alpha_only = variant.startswith("premapped"), variant.endswith("alpha_only")
+    head, jobs = _program(lib, blob, V, P, int(alpha_only), int(premapped))
+    assert head["V"] == V and head["Pp"] == 256 and head["njobs"] == len(jobs) <= 28
+    _check_tmem(head, jobs)
+
+    g = torch.Generator().manual_seed(4)
+    rep = torch.randn((V, 255, P), generator=g, dtype=torch.float64)
+    pix = torch.randn((V, 384, P), generator=g, dtype=torch.float64)
+    vd = torch.randn((1, P, 27), generator=g, dtype=torch.float64) * (0.0 if alpha_only else 1.0)
+    w64 = {k: torch.from_numpy(np.asarray(v)).double() for k, v in w.items()}
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        want = orc.mlp_forward(w64, rep, pix, vd, progressive=False)[0]
+    finally:
+        torch.set_default_dtype(old)
+    mats = _matrices(blob, V)
+    pix_r = pix.permute(0, 2, 1)
+    data = {"rep": torch.cat([rep.permute(0, 2, 1), torch.zeros((V, P, 1), dtype=torch.float64)], -1),
+            "vd": torch.cat([vd[0], torch.zeros((P, 37), dtype=torch.float64)], -1)[None]}
+    if premapped:  # what k_features PRE blends out of the pre-mapped maps
+        pre = pix_r @ mats["pre"][0].T + mats["pre"][1]
+        data["pix"] = torch.relu(pre[..., :256])
+        data["p2"] = pre[..., 256:384]
+        data["pix_mean"] = pre[..., 384:].sum(0)[None]
+    else:
+        data["pix"] = pix_r
+        data["pix_mean"] = pix_r.mean(0)[None]
+    got = _interpret(blob, head, jobs, data)
+    ref = want[:, 3] if alpha_only else want
+    assert (got - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())

@@ -88,6 +88,7 @@ SIGNATURES = {
     "th_integrate": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp]),
     "th_nchw_to_nhwc": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "th_premap_features": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp, _fp]),
+    "th_debug_chain_program": (C.c_int64, [_fp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _fp, C.c_int64]),
 }
 
 _lib = None

@@ -168,6 +168,9 @@ struct MlpRun {
   // experimental (TH_FLAG_PREMAPPED, chain schedule only): the pix block holds the images
   // [X (V*Pp,256) | P2 (V*Pp,128)] and pix_mean the image R (Pp,128) -- see k_features PRE
   int premapped;
+  // test hook (th_debug_chain_program): mlp_forward_chain copies its job program here and returns
+  // before touching the device
+  void* program_dump;
 };
 // Pp = pad_points(P): view stride of every buffer in `b`.
 int mlp_forward(const MlpRun& run, const MlpBuffers& b, const PackedHeader& hdr_host, cudaStream_t st);

@@ -911,6 +911,16 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     }
   }
   Program& pg = B.pg;
+  if (run.program_dump) {  // host-side test hook: the program as built, nothing launched
+    pg.afc_w = wf(h.afc_w);
+    pg.afc_b = wf(h.afc_b);
+    pg.rgb_w = wf(h.rgb_w);
+    pg.rgb_b = wf(h.rgb_b);
+    pg.alpha_only = run.alpha_only;
+    pg.num_units = (int)(Pp / 256);
+    *static_cast<Program*>(run.program_dump) = pg;
+    return TH_OK;
+  }
   {
     // A operands: everything from the first chunk input (rep) to the end of the view-direction image
     // lies in one workspace block (mlp_carve), the scratch included
@@ -999,3 +1009,61 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
 }
 
 }  // namespace th
+
+// Host-only test hook (no device needed): the job program mlp_forward_chain builds for a chunk of
+// n_points, as a table of int64 so that a CPU test can interpret it against the oracle
+// (tests/test_chain_program.py).  Addresses are reported relative to a fictitious workspace base
+// (the chunk block of mlp_carve) and to the start of the packed weight blob.
+//   header: [njobs, V, has_mix, alpha_only, Pp, scr_act_bytes, tile_img_bytes, 0]
+//   job (16 + 6 * MAX_SEG words): N, relu, epi, out_off, tmem_col, wait_back, view, nseg, nkb, wimg_off,
+//        bias_off (-1 = none), bias2_off (-1 = none), 0, 0, 0, 0, then per segment:
+//        kind (0 scratch / 1 chunk image), offset (scratch bytes / image byte offset from the chunk base),
+//        tile_off, kbs, dep, dep_mix
+extern "C" int64_t th_debug_chain_program(const void* packed_host, int32_t n_views, int64_t n_points,
+                                          int32_t alpha_only, int32_t premapped, int64_t* table, int64_t capacity) {
+  using namespace th;
+  using namespace th::chain;
+  if (!packed_host || !table || n_points < 1 || !chain_supported(n_views)) return TH_EINVAL;
+  PackedHeader h;
+  memcpy(&h, packed_host, sizeof(h));
+  if (h.magic != PACK_MAGIC || h.n_views != n_views) return TH_EINVAL;
+  float* base = reinterpret_cast<float*>(uintptr_t(1) << 32);  // never dereferenced
+  MlpBuffers b;
+  mlp_carve(base, n_points, n_views, &b);
+  MlpRun run{};
+  run.weights = static_cast<const unsigned char*>(packed_host);
+  run.P = n_points;
+  run.V = n_views;
+  run.alpha_only = alpha_only;
+  run.premapped = premapped;
+  run.use_tensor_cores = 1;
+  run.inputs_are_images = 1;
+  Program pg{};
+  run.program_dump = &pg;
+  const int rc = mlp_forward_chain(run, b, h, reinterpret_cast<unsigned char*>(b.s), nullptr, nullptr);
+  if (rc) return rc;
+  const int64_t words = 8 + (int64_t)pg.njobs * (16 + 6 * MAX_SEG);
+  if (capacity < words) return TH_EWORKSPACE;
+  const unsigned char* wbase = run.weights;
+  const unsigned char* cbase = reinterpret_cast<const unsigned char*>(b.rep);
+  auto woff = [&](const void* p) { return p ? (int64_t)(static_cast<const unsigned char*>(p) - wbase) : (int64_t)-1; };
+  int64_t* t = table;
+  t[0] = pg.njobs; t[1] = pg.V; t[2] = pg.has_mix; t[3] = pg.alpha_only; t[4] = pad_points(n_points);
+  t[5] = SCR_ACT; t[6] = TILE_IMG; t[7] = 0;
+  t += 8;
+  for (int j = 0; j < pg.njobs; ++j) {
+    const Job& jb = pg.job[j];
+    t[0] = jb.N; t[1] = jb.relu; t[2] = jb.epi; t[3] = jb.out_off; t[4] = jb.tmem_col; t[5] = jb.wait_back;
+    t[6] = jb.view; t[7] = jb.nseg; t[8] = jb.nkb; t[9] = woff(jb.wimg); t[10] = woff(jb.bias); t[11] = woff(jb.bias2);
+    t[12] = t[13] = t[14] = t[15] = 0;
+    for (int sgi = 0; sgi < MAX_SEG; ++sgi) {
+      const Seg& sg = jb.seg[sgi];
+      int64_t* q = t + 16 + 6 * sgi;
+      q[0] = sg.img ? 1 : 0;
+      q[1] = sg.img ? (int64_t)(sg.img - cbase) : (int64_t)sg.scratch_off;
+      q[2] = sg.tile_off; q[3] = sg.kbs; q[4] = sg.dep; q[5] = sg.dep_mix;
+    }
+    t += 16 + 6 * MAX_SEG;
+  }
+  return words;
+}
