@@ -108,7 +108,8 @@ def build_workload(args, rank: int, device):
         return torch.from_numpy(np.ascontiguousarray(a)).to(device)
 
     g = torch.Generator(device=device).manual_seed(1234)
-    feat = torch.randn((args.views, H, H, 384), generator=g, device=device)          # NHWC, 1.2 GB at 512^2
+    premapped = getattr(args, "premapped", False)
+    feat = torch.randn((args.views, H, H, 512 if premapped else 384), generator=g, device=device)  # NHWC, 1.2 GB at 512^2
     pc2 = t(fr["pc2voxel_ind"]).long()
     tok_xyz = segment_mean(t(fr["tar_smpl_vertice_smplcoord"]), pc2, args.tokens).float()
     tok_rot = segment_mean(t(fr["blend_mtx"]), pc2, args.tokens)[:, :3, :3].float().contiguous()
@@ -116,7 +117,7 @@ def build_workload(args, rank: int, device):
     frame = ops.Frame(holder=t(fr["holder"]), tok_xyz=tok_xyz, tok_rot=tok_rot, verts=t(fr["tar_smpl_vertice"]),
                       feat_nhwc=feat, cam_R=t(fr["input_R"]), cam_T=t(fr["input_T"]).reshape(args.views, 3),
                       cam_K=t(fr["input_K"]), Rh=t(fr["Rh"]), Th=t(fr["Th"]).reshape(3), weights=weights,
-                      uv_scale=ops.uv_scale_for(H, H, H, H), simt_mlp=args.simt)
+                      uv_scale=ops.uv_scale_for(H, H, H, H), simt_mlp=args.simt, premapped=premapped)
     host_rays = tuple(torch.from_numpy(fr[k]).pin_memory() for k in ("ray_o", "ray_d", "near", "far"))
     return fr, frame, host_rays
 
@@ -166,6 +167,8 @@ def main():
     ap.add_argument("--tokens", type=int, default=300)
     ap.add_argument("--views", type=int, default=3)
     ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core GEMM path")
+    ap.add_argument("--premapped", action="store_true",
+                    help="EXPERIMENTAL (TH_FLAG_PREMAPPED): time the query path on pre-mapped 512-channel feature maps")
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-culled", action="store_true", help="skip the extra culled-mode measurement")
@@ -347,7 +350,8 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "l2": "inputs larger than L2 (1.2 GB feature maps per frame)",
                            "sharding": "one 512x512 target view per rank, NCCL all_gather of the images",
-                           "mlp": "fp32 CUDA cores" if args.simt else "tcgen05 fp16x3 split, fp32 accumulate" + (", layer-chained" if chain else "")},
+                           "mlp": "fp32 CUDA cores" if args.simt else "tcgen05 fp16x3 split, fp32 accumulate" + (", layer-chained" if chain else "")
+                                  + (", EXPERIMENTAL pre-mapped feature maps" if args.premapped else "")},
                 "clocks": clk,
                 "e2e": {"value": world * N_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
