@@ -40,12 +40,16 @@ def flops_per_point(V: int) -> int:
     return 2 * (740_480 * V + 384 * V * V + 82_560) + 126
 
 
-def executed_macs_per_point(V: int) -> int:
+def executed_macs_per_point(V: int, premapped: bool = True) -> int:
     """Tensor-core MACs the tcgen05 schedule really issues per point (before the x3 of the fp16
     split): value embeds folded into fc_1, feature_fc/rgb_res_0 folded into view_fc, K padded to 64
-    (DESIGN.md section 3).  Per view row: fc_0 256x256, alpha_res_0 256x384, two key embeds
+    (DESIGN.md section 3).  Plain maps, per view row: fc_0 256x256, alpha_res_0 256x384, two key embeds
     128x256, fc_1' 256x512, fc_2 256x256, view_fc' 128x704; per point: fc_3 256x(256 V),
-    fc_4' 128x(128 V + 384)."""
+    fc_4' 128x(128 V + 384).  Pre-mapped maps: no alpha_res_0, view_fc' 128x448, fc_4' 128x(128 V + 128)
+    (the per-pixel pre-map GEMM is counted separately: it is per map pixel, not per point)."""
+    if premapped:
+        per_view = 256 * 256 + 2 * 128 * 256 + 256 * 512 + 256 * 256 + 128 * 448
+        return V * per_view + 256 * 256 * V + 128 * (128 * V + 128)
     per_view = 256 * 256 + 256 * 384 + 2 * 128 * 256 + 256 * 512 + 256 * 256 + 128 * 704
     return V * per_view + 256 * 256 * V + 128 * (128 * V + 384)
 
@@ -108,17 +112,20 @@ def build_workload(args, rank: int, device):
         return torch.from_numpy(np.ascontiguousarray(a)).to(device)
 
     g = torch.Generator(device=device).manual_seed(1234)
-    premapped = getattr(args, "premapped", False)
-    feat = torch.randn((args.views, H, H, 512 if premapped else 384), generator=g, device=device)  # NHWC, 1.2 GB at 512^2
+    premapped = not args.plain_maps and not args.simt and args.views <= 3
+    # the encoder's output layout (V,384,H,W) NCHW, 1.2 GB at 512^2: the step's input
+    feat_nchw = torch.randn((args.views, 384, H, H), generator=g, device=device)
     pc2 = t(fr["pc2voxel_ind"]).long()
     tok_xyz = segment_mean(t(fr["tar_smpl_vertice_smplcoord"]), pc2, args.tokens).float()
     tok_rot = segment_mean(t(fr["blend_mtx"]), pc2, args.tokens)[:, :3, :3].float().contiguous()
     weights = ops.PackedWeights(fr["weights"], args.views, device=device)
+    feat = ops.premap_features(feat_nchw, weights) if premapped else ops.nchw_to_nhwc(feat_nchw)
     frame = ops.Frame(holder=t(fr["holder"]), tok_xyz=tok_xyz, tok_rot=tok_rot, verts=t(fr["tar_smpl_vertice"]),
                       feat_nhwc=feat, cam_R=t(fr["input_R"]), cam_T=t(fr["input_T"]).reshape(args.views, 3),
                       cam_K=t(fr["input_K"]), Rh=t(fr["Rh"]), Th=t(fr["Th"]).reshape(3), weights=weights,
                       uv_scale=ops.uv_scale_for(H, H, H, H), simt_mlp=args.simt, premapped=premapped)
     host_rays = tuple(torch.from_numpy(fr[k]).pin_memory() for k in ("ray_o", "ray_d", "near", "far"))
+    frame.feat_nchw = feat_nchw
     return fr, frame, host_rays
 
 
@@ -167,8 +174,8 @@ def main():
     ap.add_argument("--tokens", type=int, default=300)
     ap.add_argument("--views", type=int, default=3)
     ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core GEMM path")
-    ap.add_argument("--premapped", action="store_true",
-                    help="EXPERIMENTAL (TH_FLAG_PREMAPPED): time the query path on pre-mapped 512-channel feature maps")
+    ap.add_argument("--plain-maps", action="store_true",
+                    help="round-1 path: plain channel-last 384-channel maps (no pre-map GEMM, alpha_res_0 per point)")
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-culled", action="store_true", help="skip the extra culled-mode measurement")
@@ -217,7 +224,13 @@ def main():
     S = args.samples
     gathered = torch.empty((world, N_rays, 5), device=device) if world > 1 else None
 
+    premapped = bool(frame.c.flags & ops.TH_FLAG_PREMAPPED)
+
     def step(rays, mode=ops.TH_RENDER_DENSE):
+        # one pass of the hot path from the encoder's output: the pre-map GEMM over the (V,384,H,W) maps
+        # (alpha_res_0 / rgb_res_0 / rgb_res_1 once per map pixel instead of once per sample) is part of the step
+        if premapped:
+            ops.premap_features(frame.feat_nchw, frame.weights, out=frame.feat)
         out = ops.render_rays(frame, *rays, S, mode=mode)
         img = torch.cat([out["rgb_map"], out["acc_map"][:, None], out["depth_map"][:, None]], dim=1)
         if world > 1:  # the final image gather over NVLink
@@ -292,7 +305,9 @@ def main():
     peaks = measured_peaks()
     P_step = N_rays * S
     gemm_ms, gemm_launches = prof["gemm"]
-    gemm_ms_step = gemm_ms / args.steps
+    # the pre-map GEMM does part of the same algorithmic work (alpha_res_0 / rgb_res_* once per map pixel):
+    # its time belongs in the denominator of the algorithmic rate
+    gemm_ms_step = (gemm_ms + prof["premap"][0]) / args.steps
     flops_step = flops_per_point(args.views) * P_step
     achieved = flops_step / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else 0.0
     traffic = l2_bytes = None
@@ -314,9 +329,9 @@ def main():
                 "tensor_products_per_mac": 1 if args.simt else 3,
                 # what the tensor pipe really executes: folded layers, 3 fp16 products per MAC
                 "executed_tensor_tflops": (0.0 if args.simt or gemm_ms_step <= 0 else
-                                           6 * executed_macs_per_point(args.views) * P_step / (gemm_ms_step * 1e-3) / 1e12),
+                                           6 * executed_macs_per_point(args.views, premapped) * P_step / (gemm_ms_step * 1e-3) / 1e12),
                 "issued_tensor_frac": (achieved / peaks["bf16_tflops"] if args.simt or gemm_ms_step <= 0 else
-                                       6 * executed_macs_per_point(args.views) * P_step / (gemm_ms_step * 1e-3) / 1e12
+                                       6 * executed_macs_per_point(args.views, premapped) * P_step / (gemm_ms_step * 1e-3) / 1e12
                                        / peaks["bf16_tflops"]),
                 # ncu: bytes through L2 per launch; live rate = that / the launch's live duration
                 # (practical L2 cap ~6300 B/clk)
@@ -351,7 +366,7 @@ def main():
                 "config": {"workload": workload, "l2": "inputs larger than L2 (1.2 GB feature maps per frame)",
                            "sharding": "one 512x512 target view per rank, NCCL all_gather of the images",
                            "mlp": "fp32 CUDA cores" if args.simt else "tcgen05 fp16x3 split, fp32 accumulate" + (", layer-chained" if chain else "")
-                                  + (", EXPERIMENTAL pre-mapped feature maps" if args.premapped else "")},
+                                  + (", pre-mapped feature maps (pre-map GEMM inside the step)" if premapped else "")},
                 "clocks": clk,
                 "e2e": {"value": world * N_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},

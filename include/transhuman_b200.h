@@ -58,10 +58,12 @@ extern "C" {
 #define TH_FLAG_WHITE_BKGD 1u /* cfg.white_bkgd, nerf_net_utils.py:56-57 */
 #define TH_FLAG_SIMT_MLP 2u   /* force the fp32 CUDA-core GEMM path (debug / parity) */
 #define TH_FLAG_LAYERWISE 4u  /* tcgen05 GEMMs one layer per launch instead of the layer-chained kernel (cross-check) */
-/* EXPERIMENTAL (not yet validated on a GPU, off by default):
- * `feat` holds the PRE-MAPPED maps (V, H, W, 512) written by th_premap_features -- alpha_res_0,
- * rgb_res_0 and rgb_res_1 (cross_transformer.py:315, 333, 343) applied to the maps once per frame
- * instead of to every blended sample.  Layer-chained tensor-core schedule only (V <= 3, k = 7). */
+/* `feat` holds the PRE-MAPPED maps (V, H, W, 512) written by th_premap_features -- alpha_res_0,
+ * rgb_res_0 and rgb_res_1 (cross_transformer.py:315, 333, 343; linear maps that the reference applies
+ * to the bilinear blend of the feature maps) applied to the maps once per frame instead of to every
+ * blended sample: blend and map commute exactly in real arithmetic.  This is the path the Renderer
+ * plugin uses (23 % fewer tensor MACs per point, no alpha_res_0 jobs).  Layer-chained tensor-core
+ * schedule only (V <= 3); without the flag `feat` is the plain channel-last map (V, H, W, 384). */
 #define TH_FLAG_PREMAPPED 8u
 
 /* Per-frame state: the outputs of the (out-of-scope, torch) prologue that the
@@ -219,10 +221,11 @@ int th_integrate(const float* raw, const float* z_vals, const float* ray_d, int6
                  void* stream);
 /* layout helper: (V,C,H,W) -> (V,H,W,C). */
 int th_nchw_to_nhwc(const float* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
-/* EXPERIMENTAL, with TH_FLAG_PREMAPPED: encoder output `pixel_feat_map` (V,384,H,W) NCHW
- * (encoder.py:133-146) -> pre-mapped maps (V,H,W,512) channel-last =
+/* With TH_FLAG_PREMAPPED: encoder output `pixel_feat_map` (V,384,H,W) NCHW (encoder.py:133-146) ->
+ * pre-mapped maps (V,H,W,512) channel-last =
  * [alpha_res_0 F + b | view_fc[:, :256] rgb_res_0 F | fc_4 rgb_res_1 F / V], weights from the packed
- * blob (device pointer, th_pack_weights).  Replaces th_nchw_to_nhwc for such a frame. */
+ * blob (device pointer, th_pack_weights).  Two tcgen05 GEMM launches per view reading the NCHW map as a
+ * channel-major operand (no transpose pass).  Replaces th_nchw_to_nhwc for such a frame. */
 int th_premap_features(const float* feat_nchw, const void* packed_weights, int32_t n_views, int32_t h, int32_t w,
                        float* out, void* stream);
 
@@ -230,8 +233,9 @@ int th_premap_features(const float* feat_nchw, const void* packed_weights, int32
  * bracketed by CUDA events on its stream; stop synchronises the device and
  * returns, per category, the summed elapsed milliseconds and launch counts.
  * Categories: 0 cull, 1 features (sampler + k-NN/DPaRF + pixel gather),
- * 2 GEMM layers, 3 point-wise (attention mix, heads), 4 integration. */
-#define TH_PROF_NCAT 5
+ * 2 GEMM layers, 3 point-wise (attention mix, heads), 4 integration,
+ * 5 pre-map GEMM (th_premap_features), 6 token prologue (paint / group / ray kernels). */
+#define TH_PROF_NCAT 7
 int th_profile_start(void);
 int th_profile_stop(double* ms_per_category_host, int64_t* launches_per_category_host, int32_t n);
 

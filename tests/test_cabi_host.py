@@ -63,7 +63,7 @@ def test_pack_weights_folds_layers(lib):
         assert lib.th_pack_weights(C.byref(wstruct), V, blob.ctypes.data, 16) == -2
         assert b"need" in lib.th_last_error()
         magic, nviews, total = struct.unpack_from("<IiQ", blob, 0)
-        assert magic == 0x34574854 and nviews == V and total == pw_bytes
+        assert magic == 0x35574854 and nviews == V and total == pw_bytes
         offs = struct.unpack_from("<54Q", blob, 16)
         f32 = lambda off, n: blob[off:off + 4 * n].view(np.float32)
         # fc_0: K padded 255 -> 256 with a zero column

@@ -83,6 +83,8 @@ def _interpret(blob, head, jobs, data):
     chunk = {0: "rep", o_pix: "pix", o_pix + V * Pp * 256 * 4: "p2", o_pm: "pix_mean", o_pm + Pp * 384 * 4: "vd"}
     slots, written_by = {}, {}
     KS, scores, alpha, out_final = {}, {}, None, None
+    data = dict(data)
+    mixed_in_chunk = False
     for j, jb in enumerate(jobs):
         parts = []
         for sg in jb["segs"]:
@@ -91,6 +93,7 @@ def _interpret(blob, head, jobs, data):
                 name = chunk[sg["off"]]
                 view = sg["tile_off"] // (Pp // 128)
                 assert sg["tile_off"] % (Pp // 128) == 0 and sg["dep"] == -1
+                assert not sg["dep_mix"] or (name == "pix" and mixed_in_chunk), (j, name)
                 buf = data[name]
                 assert buf.shape[-1] == C_, (j, name, buf.shape, C_)
                 parts.append(buf[view if buf.shape[0] > 1 else 0])
@@ -132,11 +135,14 @@ def _interpret(blob, head, jobs, data):
             if jb["view"] == V - 1:
                 S_ = torch.stack([torch.stack([scores[(i, jv)] for jv in range(V)], -1) for i in range(V)], 1)  # (P,i,j)
                 Aw = torch.softmax(S_, dim=1)
-                if head["has_mix"] == 1:
+                if head["has_mix"] == 1 and (V in slots):
                     X = torch.stack([slots[V + i] for i in range(V)], 0)                      # (i,P,256)
                     XT = torch.einsum("pij,ipc->jpc", Aw, X)
                     for jv in range(V):
                         slots[V + jv] = XT[jv]
+                elif head["has_mix"] == 1:  # no X jobs: the mix works on the X tiles of the chunk image
+                    data["pix"] = torch.einsum("pij,ipc->jpc", Aw, data["pix"])
+                    mixed_in_chunk = True
         elif jb["epi"] == EPI_ALPHA:
             O = torch.relu(out + bias)
             alpha = O @ mats["afc"][0][0] + mats["afc"][1][0]

@@ -9,19 +9,25 @@ import pytest
 import torch
 
 from oracle import transhuman_oracle as orc
-from tests.gpu_util import frame_to_device
+from tests.gpu_util import assert_maps_close, frame_to_device
 from transhuman_b200 import ops, synth
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _frame(n_class, H, feat_hw, seed=0, shift=-15.0):
+def _frame(n_class, H, feat_hw, seed=0, shift=-15.0, premapped=None):
     fr = synth.make_frame(H=H, W=H, n_class=n_class, V=3, feat_hw=feat_hw, seed=seed, alpha_bias_shift=shift)
     tf = orc.to_torch_frame(fr)
     tokens = orc.build_tokens(tf)
-    frame, rays = frame_to_device(fr, tokens, DEV)
+    frame, rays = frame_to_device(fr, tokens, DEV, premapped=premapped)     # default: the pre-mapped path
     return fr, tf, tokens, frame, rays
+
+
+def _check(got_sel, want, sub_tf, S, name):
+    _, z = orc.get_sampling_points(sub_tf["ray_o"][None], sub_tf["ray_d"][None], sub_tf["near"][None],
+                                   sub_tf["far"][None], S)
+    assert_maps_close(got_sel, want, want["raw"], z[0], sub_tf["ray_d"], S, 3.5, name)
 
 
 def _oracle_on_rays(tf, tokens, sel, S, culled):
@@ -29,8 +35,8 @@ def _oracle_on_rays(tf, tokens, sel, S, culled):
     for k in ("ray_o", "ray_d", "near", "far"):
         sub[k] = tf[k][sel]
     if culled:
-        return orc.render_fast(sub, S, tokens=tokens, train_branch_max_rays=0)
-    return orc.render(sub, S, tokens=tokens)
+        return orc.render_fast(sub, S, tokens=tokens, train_branch_max_rays=0), sub
+    return orc.render(sub, S, tokens=tokens), sub
 
 
 @pytest.mark.parametrize("n_class,S", [(300, 64), (1500, 128)])
@@ -39,7 +45,7 @@ def test_config_512_sampled_parity(n_class, S):
     full-size culled + a dense band, spot-checked against the oracle."""
     fr, tf, tokens, frame, rays = _frame(n_class, 512, 128)     # 128x128 input views keep host memory small
     N = 512 * 512
-    got = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_MASKED, want_mask=True)
+    got = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_MASKED, want_mask=True, want_raw=True)
     n_in, n_rays, n_eval = got["counters"]
     assert 0.005 < n_in / (N * S) < 0.2 and n_eval == n_in
     pm = got["pts_mask"].bool()                      # uint8.any() stays uint8 and ~ would be a bitwise not
@@ -49,39 +55,41 @@ def test_config_512_sampled_parity(n_class, S):
     assert torch.all(got["rgb_map"][dead] == 0) and torch.all(got["acc_map"][dead] == 0)
     g = torch.Generator().manual_seed(0)
     sel = alive[torch.randperm(len(alive), generator=g)[:96]]
-    want = _oracle_on_rays(tf, tokens, sel, S, culled=True)
+    want, sub = _oracle_on_rays(tf, tokens, sel, S, culled=True)
     assert torch.equal(got["pts_mask"][sel.to(DEV)].cpu().bool(), want["valid_pts_mask"][0])   # exact cull
-    last = want["raw"][:, -1, 3]
-    keep = ~((last.abs() < 1e-3) & (last != 0))
-    err = (got["rgb_map"][sel.to(DEV)].cpu() - want["rgb_map"][0])[keep].abs().max().item()
-    assert err <= 1e-4, err
-    assert (got["acc_map"][sel.to(DEV)].cpu() - want["acc_map"][0])[keep].abs().max().item() <= 1e-4
-    assert (got["depth_map"][sel.to(DEV)].cpu() - want["depth_map"][0])[keep].abs().max().item() <= 1e-4 * 3.5
+    _check({k: got[k][sel.to(DEV)] for k in ("rgb_map", "acc_map", "depth_map", "raw")}, want, sub, S,
+           f"512^2 culled, {n_class} tokens")
+    del got
     # dense band of 2048 rays: sampled parity + chunk independence against the same rays alone
     band = slice(N // 2, N // 2 + 2048)
-    dense = ops.render_rays(frame, *(r[band] for r in rays), S, mode=ops.TH_RENDER_DENSE)
+    dense = ops.render_rays(frame, *(r[band] for r in rays), S, mode=ops.TH_RENDER_DENSE, want_raw=True)
     sel2 = torch.arange(0, 2048, 64)
-    want2 = _oracle_on_rays(tf, tokens, torch.arange(N // 2, N // 2 + 2048)[sel2], S, culled=False)
-    last = want2["raw"][:, -1, 3]
-    keep = ~(last.abs() < 1e-3)
-    assert (dense["rgb_map"][sel2.to(DEV)].cpu() - want2["rgb_map"][0])[keep].abs().max().item() <= 1e-4
+    want2, sub2 = _oracle_on_rays(tf, tokens, torch.arange(N // 2, N // 2 + 2048)[sel2], S, culled=False)
+    _check({k: dense[k][sel2.to(DEV)] for k in ("rgb_map", "acc_map", "depth_map", "raw")}, want2, sub2, S,
+           f"512^2 dense band, {n_class} tokens")
     part = ops.render_rays(frame, *(r[N // 2 + 512:N // 2 + 1024] for r in rays), S, mode=ops.TH_RENDER_DENSE)
     assert torch.equal(part["rgb_map"], dense["rgb_map"][512:1024])
 
 
 def test_simt_and_tensor_core_paths_agree_at_size():
-    fr, tf, tokens, frame, rays = _frame(300, 256, 64, seed=2)
+    """Three independent evaluations of the per-point network on 524,288 points: fp32 CUDA cores with the
+    UNFOLDED layers, tcgen05 with the folded layers on the plain maps, tcgen05 on the pre-mapped maps."""
+    fr, tf, tokens, frame_pre, rays = _frame(300, 256, 64, seed=2)
+    frame, _ = frame_to_device(fr, tokens, DEV, premapped=False, weights=frame_pre.weights)
     S = 64
     sel = slice(30000, 30000 + 8192)
+    p = ops.render_rays(frame_pre, *(r[sel] for r in rays), S, mode=ops.TH_RENDER_DENSE, want_raw=True)
     a = ops.render_rays(frame, *(r[sel] for r in rays), S, mode=ops.TH_RENDER_DENSE, want_raw=True)
     frame.set_flag(ops.TH_FLAG_SIMT_MLP, True)
     b = ops.render_rays(frame, *(r[sel] for r in rays), S, mode=ops.TH_RENDER_DENSE, want_raw=True)
     frame.set_flag(ops.TH_FLAG_SIMT_MLP, False)
-    scale = b["raw"].abs().max().item()
-    assert (a["raw"] - b["raw"]).abs().max().item() <= 2e-5 * max(1.0, scale)
+    scale = max(1.0, b["raw"].abs().max().item())
     last = b["raw"][:, -1, 3]
-    keep = ~(last.abs() < 1e-3)
-    assert (a["rgb_map"] - b["rgb_map"])[keep].abs().max().item() <= 1e-4
+    keep = ~(last.abs() < 2e-5 * scale)
+    print(f"[simt vs tc] {int((~keep).sum())} of {keep.numel()} rays on the alpha_S step excluded")
+    for name, x in (("tc", a), ("premapped", p)):
+        assert (x["raw"] - b["raw"]).abs().max().item() <= 2e-5 * scale, name
+        assert (x["rgb_map"] - b["rgb_map"])[keep].abs().max().item() <= 1e-4, name
 
 
 def test_chain_kernel_is_insensitive_to_role_timing(monkeypatch):

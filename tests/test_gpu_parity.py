@@ -8,9 +8,9 @@ import numpy as np
 import pytest
 import torch
 
-from tests.conftest import GOLDEN_CASES, load_golden
+from tests.conftest import GOLDEN_CASES, GOLDEN_CASES_MANY_TOKENS, load_golden
 from oracle import transhuman_oracle as orc
-from tests.gpu_util import frame_to_device
+from tests.gpu_util import assert_maps_close, frame_to_device
 from transhuman_b200 import ops, synth
 
 pytestmark = pytest.mark.gpu
@@ -24,16 +24,28 @@ def small():
     fr = synth.make_frame(H=20, W=20, n_class=300, V=3, feat_hw=28, seed=21, alpha_bias_shift=-12.0)
     tf = orc.to_torch_frame(fr)
     tokens = orc.build_tokens(tf)
-    frame, rays = frame_to_device(fr, tokens, DEV)
+    # the staged entry points (pixel_gather) read the plain channel-last maps; the fused-path tests below
+    # take the pre-mapped frame from `small_pre` as well
+    frame, rays = frame_to_device(fr, tokens, DEV, premapped=False)
     return fr, tf, tokens, frame, rays
 
 
-def _knife_edge_rays(raw, S, eps=1e-3):
-    """Rays whose last-sample alpha_raw is within eps of 0: dist = 1e10 makes
-    alpha_S a step function of sign(raw) (nerf_net_utils.py:31-34), so these are
-    excluded-and-counted (hard parts)."""
-    a = raw.reshape(-1, S, 4)[:, -1, 3]
-    return (a.abs() < eps) & (a != 0)     # raw == 0 exactly is a masked-out sample, not an edge
+@pytest.fixture(scope="module")
+def small_pre(small):
+    fr, tf, tokens, frame, rays = small
+    frame_pre, _ = frame_to_device(fr, tokens, DEV, premapped=True, weights=frame.weights)
+    return frame_pre
+
+
+def _z_and_d(tf, S):
+    _, z = orc.get_sampling_points(tf["ray_o"][None], tf["ray_d"][None], tf["near"][None], tf["far"][None], S)
+    return z[0], tf["ray_d"]
+
+
+def _compare(got, want, tf, S, far, name, white=False):
+    """Maps against the oracle's; knife-edge rays verified under the flipped alpha_S hypothesis (gpu_util)."""
+    z, d = _z_and_d(tf, S)
+    return assert_maps_close(got, want, want["raw"], z, d, S, far, name, white_bkgd=white, tol=RGB_TOL)
 
 
 # ---------------------------------------------------------------- staged, exact
@@ -200,33 +212,38 @@ def test_mlp_raw_stage(small, simt):
 
 
 # ---------------------------------------------------------------- fused path
-def _compare_maps(got, want, far, name, exclude=None):
-    keep = slice(None) if exclude is None else ~exclude
-    e_rgb = (got["rgb_map"].cpu() - want["rgb_map"][0])[keep].abs().max().item()
-    e_acc = (got["acc_map"].cpu() - want["acc_map"][0])[keep].abs().max().item()
-    e_dep = (got["depth_map"].cpu() - want["depth_map"][0])[keep].abs().max().item()
-    assert e_rgb <= RGB_TOL, f"{name}: rgb {e_rgb}"
-    assert e_acc <= RGB_TOL, f"{name}: acc {e_acc}"
-    assert e_dep <= RGB_TOL * far, f"{name}: depth {e_dep}"
+_ORACLE_FOR_GOLDEN = {}
 
 
-@pytest.mark.parametrize("simt", [True, False])
-@pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_render_matches_reference_golden(name, simt):
+def _oracle_for_golden(name, tf, tokens, S, mode):
+    """The oracle's own render of a golden frame (for the knife-edge set and its step hypotheses only:
+    the maps are compared with the GOLDEN, i.e. the genuine reference's outputs)."""
+    if name not in _ORACLE_FOR_GOLDEN:
+        _ORACLE_FOR_GOLDEN[name] = orc.render(tf, S, tokens=tokens) if mode == "dense" else \
+            orc.render_fast(tf, S, tokens=tokens)
+    return _ORACLE_FOR_GOLDEN[name]
+
+
+@pytest.mark.parametrize("path", ["simt", "tc", "premapped"])
+@pytest.mark.parametrize("name", GOLDEN_CASES + GOLDEN_CASES_MANY_TOKENS)
+def test_render_matches_reference_golden(name, path):
     """End to end against outputs of the reference's own Renderer.render /
-    render_fast (fixtures from oracle/make_golden.py)."""
+    render_fast (fixtures from oracle/make_golden.py), on all three schedules: fp32 CUDA cores,
+    tcgen05 on the plain maps, tcgen05 on the pre-mapped maps (what the Renderer plugin runs)."""
     kw, S, mode, g = load_golden(name)
     fr = synth.make_frame(**kw)
+    if path == "premapped" and fr["V"] > 3:
+        pytest.skip("the layer-chained schedule holds at most 3 key embeds in TMEM")
     tf = orc.to_torch_frame(fr)
     tokens = orc.build_tokens(tf)
-    frame, rays = frame_to_device(fr, tokens, DEV, simt_mlp=simt)
+    frame, rays = frame_to_device(fr, tokens, DEV, simt_mlp=path == "simt", premapped=path == "premapped")
     m = ops.TH_RENDER_DENSE if mode == "dense" else ops.TH_RENDER_FAST
     got = ops.render_rays(frame, *rays, S, mode=m, want_raw=True, want_mask=True)
     want = {k: torch.from_numpy(g[k])[None] for k in ("rgb_map", "acc_map", "depth_map")}
-    # exclude-and-count rays sitting on the last-sample step function
-    ex = _knife_edge_rays(got["raw"].cpu(), S)
-    assert ex.float().mean().item() < 0.02
-    _compare_maps(got, want, float(fr["far"].max()), name, exclude=ex)
+    ref = _oracle_for_golden(name, tf, tokens, S, mode)
+    z, d = _z_and_d(tf, S)
+    n_edge = assert_maps_close(got, want, ref["raw"], z, d, S, float(fr["far"].max()), f"{name}/{path}")
+    assert n_edge <= 0.02 * want["rgb_map"].shape[1]
     if mode != "dense":
         mask = np.unpackbits(g["cull_mask"])[: got["pts_mask"].numel()].astype(bool)
         assert np.array_equal(got["pts_mask"].cpu().numpy().reshape(-1).astype(bool), mask)   # exact cull
@@ -236,9 +253,12 @@ def test_render_matches_reference_golden(name, simt):
             assert got["counters"][2] == got["counters"][1] * S
 
 
+@pytest.mark.parametrize("pre", [False, True])
 @pytest.mark.parametrize("mode", ["dense", "masked", "fast"])
-def test_render_matches_oracle(small, mode):
+def test_render_matches_oracle(small, small_pre, mode, pre):
     fr, tf, tokens, frame, rays = small
+    if pre:
+        frame = small_pre
     S = 24
     if mode == "dense":
         want = orc.render(tf, S, tokens=tokens)
@@ -249,8 +269,9 @@ def test_render_matches_oracle(small, mode):
     else:
         want = orc.render_fast(tf, S, tokens=tokens)
         got = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_FAST, want_raw=True, want_mask=True)
-    ex = _knife_edge_rays(want["raw"], S)
-    _compare_maps(got, want, float(fr["far"].max()), mode, exclude=ex)
+    _compare(got, want, tf, S, float(fr["far"].max()), f"{mode}/pre={pre}")
+    # raw against the oracle's, relative to the frame's raw scale (the fp32 reference itself sits ~1e-6 x scale
+    # from a float64 evaluation)
     raw_err = (got["raw"].cpu() - want["raw"]).abs().max().item()
     assert raw_err <= 2e-5 * max(1.0, want["raw"].abs().max().item())
     if mode != "dense":
@@ -283,16 +304,76 @@ def test_rotated_rh_indices_explained(small):
     assert bad.float().mean().item() < 1e-3
 
 
-def test_white_background(small):
+@pytest.mark.parametrize("pre", [False, True])
+@pytest.mark.parametrize("mode", ["dense", "masked", "fast"])
+def test_white_background(small, small_pre, mode, pre):
+    """cfg.white_bkgd (nerf_net_utils.py:56-57).  In the culled modes the reference composites the SURVIVING
+    rays only and scatters them into zero-filled maps (if_clight_renderer.py:468-476): a culled ray stays 0,
+    it does not turn white."""
     fr, tf, tokens, frame, rays = small
+    if pre:
+        frame = small_pre
+    S = 12
     frame.set_flag(ops.TH_FLAG_WHITE_BKGD, True)
     try:
-        got = ops.render_rays(frame, *rays, 12, mode=ops.TH_RENDER_DENSE)
-        want = orc.render(tf, 12, tokens=tokens, white_bkgd=True)
-        ex = _knife_edge_rays(want["raw"], 12)
-        _compare_maps(got, want, float(fr["far"].max()), "white", exclude=ex)
+        if mode == "dense":
+            got = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_DENSE, want_raw=True)
+            want = orc.render(tf, S, tokens=tokens, white_bkgd=True)
+        else:
+            m = ops.TH_RENDER_MASKED if mode == "masked" else ops.TH_RENDER_FAST
+            got = ops.render_rays(frame, *rays, S, mode=m, want_raw=True)
+            want = orc.render_fast(tf, S, tokens=tokens, white_bkgd=True,
+                                   **({"train_branch_max_rays": 0} if mode == "masked" else {}))
+            dead = ~want["valid_pts_mask"][0].any(dim=1)
+            assert dead.any() and (~dead).any()
+            assert torch.all(got["rgb_map"].cpu()[dead] == 0) and torch.all(got["acc_map"].cpu()[dead] == 0)
+            # a surviving ray with little density is (nearly) white
+            assert got["rgb_map"].cpu()[~dead].max().item() > 0.9
+        _compare(got, want, tf, S, float(fr["far"].max()), f"white/{mode}/pre={pre}", white=True)
     finally:
         frame.set_flag(ops.TH_FLAG_WHITE_BKGD, False)
+
+
+def test_split_operands_saturate_instead_of_nan(small):
+    """The fp16 hi/lo operand split saturates (common.cuh): activations beyond the fp16 range give finite,
+    sign-correct results instead of inf - inf = NaN, and activations up to 2 x 65504 stay accurate."""
+    fr, tf, tokens, frame, rays = small
+    P = 512
+    g = torch.Generator().manual_seed(11)
+    rep = torch.randn((3, 255, P), generator=g)
+    pix = torch.randn((3, 384, P), generator=g)
+    vd = torch.zeros((P, 27))
+    base = ops.mlp_raw(frame, rep.to(DEV), pix.to(DEV), vd.to(DEV))
+    assert torch.isfinite(base).all()
+    # inputs scaled into (65504, 131008): hi saturates, lo carries the rest; the network is positively
+    # homogeneous in its inputs up to the biases, so raw grows ~linearly -- compare with the fp32 CUDA-core path
+    big = 9.0e4 / float(max(rep.abs().max(), pix.abs().max()))
+    got = ops.mlp_raw(frame, (rep * big).to(DEV), (pix * big).to(DEV), vd.to(DEV))
+    frame.set_flag(ops.TH_FLAG_SIMT_MLP, True)
+    try:
+        ref = ops.mlp_raw(frame, (rep * big).to(DEV), (pix * big).to(DEV), vd.to(DEV))
+    finally:
+        frame.set_flag(ops.TH_FLAG_SIMT_MLP, False)
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    # far beyond the range: clamped, finite, never NaN
+    huge = ops.mlp_raw(frame, (rep * 1e8).to(DEV), (pix * 1e8).to(DEV), vd.to(DEV))
+    assert not torch.isnan(huge).any()
+
+
+def test_non_finite_ray_does_not_fault(small_pre, small):
+    """A NaN ray (bad near/far) must not index tokens out of bounds: its own pixel is NaN like the
+    reference's, every other ray is untouched."""
+    fr, tf, tokens, frame, rays = small
+    o, d, n, f = (r.clone() for r in rays)
+    n[5] = float("nan")
+    good = ops.render_rays(small_pre, *rays, 16, mode=ops.TH_RENDER_DENSE)
+    bad = ops.render_rays(small_pre, o, d, n, f, 16, mode=ops.TH_RENDER_DENSE)
+    torch.cuda.synchronize()
+    keep = torch.ones(o.shape[0], dtype=torch.bool, device=DEV)
+    keep[5] = False
+    assert torch.equal(good["rgb_map"][keep], bad["rgb_map"][keep])
+    assert torch.isnan(bad["rgb_map"][5]).any()
 
 
 def test_query_density(small):
@@ -335,9 +416,9 @@ def test_one_shot_single_view():
     tf = orc.to_torch_frame(fr)
     tokens = orc.build_tokens(tf)
     frame, rays = frame_to_device(fr, tokens, DEV)
-    got = ops.render_rays(frame, *rays, 16, mode=ops.TH_RENDER_DENSE)
+    got = ops.render_rays(frame, *rays, 16, mode=ops.TH_RENDER_DENSE, want_raw=True)
     want = orc.render(tf, 16, tokens=tokens)
-    _compare_maps(got, want, float(fr["far"].max()), "V=1", exclude=_knife_edge_rays(want["raw"], 16))
+    _compare(got, want, tf, 16, float(fr["far"].max()), "V=1")
 
 
 @pytest.mark.parametrize("V", [2, 4])
@@ -348,9 +429,9 @@ def test_other_view_counts(V):
     tf = orc.to_torch_frame(fr)
     tokens = orc.build_tokens(tf)
     frame, rays = frame_to_device(fr, tokens, DEV)
-    got = ops.render_rays(frame, *rays, 16, mode=ops.TH_RENDER_DENSE)
+    got = ops.render_rays(frame, *rays, 16, mode=ops.TH_RENDER_DENSE, want_raw=True)
     want = orc.render(tf, 16, tokens=tokens)
-    _compare_maps(got, want, float(fr["far"].max()), f"V={V}", exclude=_knife_edge_rays(want["raw"], 16))
+    _compare(got, want, tf, 16, float(fr["far"].max()), f"V={V}")
 
 
 def test_layerwise_schedule_agrees_with_chain(small):

@@ -22,6 +22,21 @@ void set_error(const char* fmt, ...) {
 }
 int64_t& launch_counter() { return g_launches; }
 
+int device_sm_count(int* out) {
+  static int cache[64] = {0};  // benign race: every writer stores the same value
+  int dev = 0;
+  TH_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !cache[dev]) {
+    int n = 0;
+    TH_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < 64) cache[dev] = n;
+    *out = n;
+    return TH_OK;
+  }
+  *out = cache[dev];
+  return TH_OK;
+}
+
 // ---- profiler: CUDA events around every launch of a category, summed at stop ----
 struct ProfState {
   bool on = false;
@@ -101,6 +116,7 @@ static std::vector<MatSpec> mat_specs(int V) {
       {&H::gvfp_w, &H::gvfp_b, &H::h_gvfp, 128, 448},
       {&H::tp_w, &H::tp_b, &H::h_tp, 128, 128 * V + 128},
       {&H::xid_w, &H::xid_b, &H::h_xid, 256, 256},
+      {&H::preb_w, &H::preb_b, &H::h_preb, 256, 384},
   };
 }
 
@@ -306,6 +322,8 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
       W(h.tp_b)[n] = W(h.t_b)[n];
     }
     for (int n = 0; n < 256; ++n) W(h.xid_w)[(size_t)n * 256 + n] = 1.0f;
+    // rows 256..511 of W_pre as a matrix of their own (the second launch of the pre-map GEMM; zero bias)
+    memcpy(W(h.preb_w), W(h.pre_w) + (size_t)256 * 384, (size_t)256 * 384 * 4);
   }
   // fp16 hi/lo split of the GEMM matrices, stored as shared-memory tile images for
   // the tensor-core path: per 64-wide k-block and per half of the N rows (one half per CTA of a
@@ -319,8 +337,10 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
       for (int n = 0; n < m.N; ++n)
         for (int kk = 0; kk < 64; ++kk) {
           const float x = src[(size_t)n * m.K + kb * 64 + kk];
-          const __half a = __float2half_rn(x);
-          const __half b = __float2half_rn(x - __half2float(a));
+          // saturating like the device-side split (common.cuh): no inf planes from a huge weight
+          auto sat = [](float f) { return f > 65504.f ? 65504.f : (f < -65504.f ? -65504.f : f); };
+          const __half a = __float2half_rn(sat(x));
+          const __half b = __float2half_rn(sat(x - __half2float(a)));
           const size_t off = (size_t)n * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
           const int half_rows = m.N / 2, r = n / half_rows;
           unsigned char* tile = img + (size_t)kb * (2 * m.N * 128) + (size_t)r * (m.N * 128);  // this half: [hi | lo]
@@ -466,8 +486,8 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
     fo.rep_pad = 1;
     const int use_tc = (f->flags & TH_FLAG_SIMT_MLP) ? 0 : 1;
     const bool premapped = (f->flags & TH_FLAG_PREMAPPED) != 0;
-    if (premapped && !(use_tc && !(f->flags & TH_FLAG_LAYERWISE) && chain_supported(V) && fr.K == 7)) {
-      set_error("TH_FLAG_PREMAPPED needs the layer-chained tensor-core schedule (V <= 3, k = 7, no SIMT/LAYERWISE flag)");
+    if (premapped && !(use_tc && !(f->flags & TH_FLAG_LAYERWISE) && chain_supported(V))) {
+      set_error("TH_FLAG_PREMAPPED needs the layer-chained tensor-core schedule (V <= 3, no SIMT/LAYERWISE flag)");
       return TH_EUNSUPPORTED;
     }
     if (use_tc) {  // the feature kernel writes the GEMM operands directly as fp16 hi/lo tile images
@@ -503,12 +523,8 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
       const char* e = getenv("TH_CHAIN");
       return e ? atoi(e) : 1;
     }();
-    static int num_sms = 0;
-    if (!num_sms) {
-      int dev = 0;
-      TH_CUDA(cudaGetDevice(&dev));
-      TH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int num_sms = 0;
+    if (device_sm_count(&num_sms)) return TH_ECUDA;
     const size_t scratch_room = (size_t)Pp * V * (256 * 4 + 128 * 2) * 4;  // b.s ... b.ks are contiguous
     if (use_tc && (use_chain || premapped) && !(f->flags & TH_FLAG_LAYERWISE) && chain_supported(V) &&
         chain_scratch_bytes(P, V, num_sms) <= scratch_room) {
@@ -605,7 +621,8 @@ int th_render_rays(const ThFrame* f, const ThRays* r, ThOut* o, int32_t culled, 
     if ((rc = run_points(f, fr, hdr, src, ws.ids, n_eval, ws, raw, nullptr, 0, zero_rgb, st))) return rc;
     mask = integ_mask;
   }
-  return launch_integrate(raw, mask, src, nullptr, r->ray_d, N, S, white, o->rgb_map, o->acc_map, o->depth_map, st);
+  return launch_integrate(raw, mask, culled ? ws.ray_any : nullptr, src, nullptr, r->ray_d, N, S, white, o->rgb_map,
+                          o->acc_map, o->depth_map, st);
 }
 
 int th_query_density(const ThFrame* f, const float* pts, int64_t n_points, float* alpha_raw, uint8_t* mask_out,
@@ -770,7 +787,7 @@ int th_integrate(const float* raw, const float* z_vals, const float* ray_d, int6
   TH_CHECK_ARG(raw && z_vals && ray_d && rgb_map && acc_map && depth_map, "null pointer");
   TH_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "bad counts");
   PointSource src{};
-  return launch_integrate(raw, nullptr, src, z_vals, ray_d, n_rays, n_samples, white_bkgd, rgb_map, acc_map,
+  return launch_integrate(raw, nullptr, nullptr, src, z_vals, ray_d, n_rays, n_samples, white_bkgd, rgb_map, acc_map,
                           depth_map, static_cast<cudaStream_t>(stream));
 }
 
@@ -786,9 +803,7 @@ int th_premap_features(const float* feat_nchw, const void* packed_weights, int32
     set_error("th_premap_features: bad weights blob");
     return TH_EINVAL;
   }
-  const unsigned char* blob = static_cast<const unsigned char*>(packed_weights);
-  return launch_premap(feat_nchw, reinterpret_cast<const float*>(blob + hdr.pre_w),
-                       reinterpret_cast<const float*>(blob + hdr.pre_b), out, n_views, h, w, st);
+  return launch_premap(feat_nchw, static_cast<const unsigned char*>(packed_weights), hdr, out, n_views, h, w, st);
 }
 
 int th_nchw_to_nhwc(const float* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w, void* stream) {

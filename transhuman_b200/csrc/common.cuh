@@ -41,7 +41,7 @@ int64_t& launch_counter();
   } while (0)
 
 // ---- optional per-category device timing (th_profile_start/stop) -------------
-enum ProfCat { PROF_CULL = 0, PROF_FEATURES = 1, PROF_GEMM = 2, PROF_POINTWISE = 3, PROF_INTEGRATE = 4, PROF_NCAT = 5 };
+enum ProfCat { PROF_CULL = 0, PROF_FEATURES = 1, PROF_GEMM = 2, PROF_POINTWISE = 3, PROF_INTEGRATE = 4, PROF_PREMAP = 5, PROF_PROLOGUE = 6, PROF_NCAT = 7 };
 void prof_begin(int cat, cudaStream_t st);
 void prof_end(int cat, cudaStream_t st);
 struct ProfScope {
@@ -50,6 +50,9 @@ struct ProfScope {
   ProfScope(int c, cudaStream_t s) : cat(c), st(s) { prof_begin(cat, st); }
   ~ProfScope() { prof_end(cat, st); }
 };
+
+// SM count of the CURRENT device (cached per device id: a process may render on several devices)
+int device_sm_count(int* out);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -104,6 +107,31 @@ __device__ __forceinline__ float3 world2smpl(float3 p, const float* Rh, const fl
 // torch.norm over 3 components: sqrt(fma(z,z,fma(y,y,x*x))) on the CPU path.
 __device__ __forceinline__ float norm3(float x, float y, float z) {
   return __fsqrt_rn(__fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
+}
+
+// ---- fp32 -> fp16 hi/lo operand split of the tensor-core path ------------------------------
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits while |x| < 65504.  Both conversions
+// SATURATE (cvt.satfinite): a plain conversion turns |x| > 65504 into hi = inf, lo = -inf and the three-product
+// GEMM into inf - inf = NaN, where the fp32 reference just carries a large number.  Saturated, the pair
+// represents x exactly-to-fp16 up to 2 x 65504 and clamps (finite, sign-correct) beyond.  Residuals below
+// the fp16 subnormal step (6e-8) flush to zero: an absolute operand error of <= 3e-8.  NaN stays NaN.
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float lo_half, float hi_half) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
+  return r;
+}
+__device__ __forceinline__ float2 f16x2_to_f32(uint32_t h) {
+  float2 f;
+  asm("{\n\t.reg .f16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}"
+      : "=f"(f.x), "=f"(f.y)
+      : "r"(h));
+  return f;
+}
+// two adjacent values -> packed hi pair and packed lo pair
+__device__ __forceinline__ void split_hl2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_f16x2_sat(x, y);
+  const float2 hf = f16x2_to_f32(hi);
+  lo = cvt_f16x2_sat(x - hf.x, y - hf.y);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

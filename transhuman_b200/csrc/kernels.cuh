@@ -62,11 +62,9 @@ int launch_world2smpl(const float* pts, int64_t n, const float* Rh, const float*
 int launch_view_embed(const float* ray_d, int64_t n_rays, float* out, cudaStream_t st);
 int launch_features(const FrameDev& fr, const PointSource& src, int64_t n_points, const FeatOut& out,
                     cudaStream_t st, bool premapped = false);
-int launch_premap(const float* src_nchw, const float* w_pre, const float* b_pre, float* dst, int n_views, int h, int w,
-                  cudaStream_t st);
-int launch_integrate(const float* raw, const uint8_t* mask, const PointSource& src, const float* z_vals,
-                     const float* ray_d, int64_t n_rays, int S, int white_bkgd, float* rgb, float* acc,
-                     float* depth, cudaStream_t st);
+int launch_integrate(const float* raw, const uint8_t* mask, const uint8_t* ray_alive, const PointSource& src,
+                     const float* z_vals, const float* ray_d, int64_t n_rays, int S, int white_bkgd, float* rgb,
+                     float* acc, float* depth, cudaStream_t st);
 int launch_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, cudaStream_t st);
 
 // ---- packed weights (api.cu writes, mlp_*.cu read) --------------------------------
@@ -84,7 +82,7 @@ int launch_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w
 //   W_gvf  = [V1 @ feature_fc | V1 @ rgb_res_0 | view_fc[:, 256:283] | 0(37)]  (K = 704)
 //            with V1 = view_fc[:, :256];  b = V1 @ b_f + b_view
 struct PackedHeader {
-  uint32_t magic;      // 'THW4'
+  uint32_t magic;      // 'THW5'
   int32_t n_views;
   uint64_t total_bytes;
   // fp32 matrices, row-major (N, K) with K contiguous; offsets in bytes from blob start
@@ -119,8 +117,12 @@ struct PackedHeader {
   uint64_t tp_w, tp_b;          // (128,128*V+128)
   uint64_t xid_w, xid_b;        // (256,256), zero bias
   uint64_t h_gvfp, h_tp, h_xid;
+  // second half of W_pre as a GEMM matrix of its own ([V1 @ rgb_res_0 ; fc_4 @ rgb_res_1 / V], zero bias): the
+  // pre-map GEMM (th_premap_features) runs as two N = 256 tcgen05 launches, h_ar0 / ar0_b and h_preb / preb_b
+  uint64_t preb_w, preb_b;      // (256,384), (256)
+  uint64_t h_preb;
 };
-constexpr uint32_t PACK_MAGIC = 0x34574854u;
+constexpr uint32_t PACK_MAGIC = 0x35574854u;
 
 // Byte offset of the hi element (row, col) of a (rows, C) activation in tile-image
 // format; the lo element sits 16384 bytes further.
@@ -196,6 +198,10 @@ struct GemmSeg {
   int64_t row_mod;  // rows wrap modulo this (0 = no wrap)
   const unsigned char* img;
   int64_t img_tile_mod;  // image segments: row tiles wrap modulo this (0 = no wrap)
+  // fp32 segments, tensor-core path: non-zero = the operand is stored K-MAJOR-OUTER ("channel-major"):
+  // element (row m, column k) sits at ptr[k * col_stride + m] -- an NCHW feature map read as a
+  // (pixels, channels) matrix without a transpose pass (th_premap_features)
+  int64_t col_stride;
 };
 struct GemmArgs {
   GemmSeg seg[TH_MAX_VIEWS + 1];
@@ -211,7 +217,12 @@ struct GemmArgs {
   int relu;
 };
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
-int launch_gemm_tc(const GemmArgs& a, const void* w_hi_lo, cudaStream_t st);
+int launch_gemm_tc(const GemmArgs& a, const void* w_hi_lo, cudaStream_t st, int prof_cat = PROF_GEMM);
+// mlp_tc.cu: pre-mapped feature maps.  dst[v][hw][n] = b[n] + sum_k W_pre[n][k] src[v][k][hw]: (V,384,H,W) NCHW in (the
+// encoder's layout, encoder.py:133-146), (V,H,W,512) channel-last out -- the layout change of th_nchw_to_nhwc and the
+// three 1x1 convolutions that read the blended maps, as tcgen05 GEMMs over the maps (2 launches of N = 256 per view).
+int launch_premap(const float* src_nchw, const unsigned char* weights, const PackedHeader& hdr, float* dst, int n_views,
+                  int h, int w, cudaStream_t st);
 int launch_pack_inputs(const float* human_rep, const float* pixel_feat, const float* viewdir, int64_t P, int V,
                        const MlpBuffers& b, cudaStream_t st);
 

@@ -87,6 +87,10 @@ struct Program {
   float* alpha_out;
   const int32_t* dst_ids;
   int64_t first, P;
+  // pre-mapped inputs without the X copy jobs: the mix works on the X tiles of the chunk image in place
+  // (x_img = first X tile of view 0, x_view_stride = bytes between the views); nullptr = slot B of the scratch
+  unsigned char* x_img;
+  int64_t x_view_stride;
   int32_t njobs, num_units, V, has_mix, zero_rgb, alpha_only, kp_col;
   int32_t ks_col[TH_MAX_VIEWS];
   int32_t dbg;  // TH_CHAIN_DBG: timing experiments only, 1 = skip the mix, 2 = skip the store fences (results wrong); 16/32/64/128 = random delays in the loader / MMA / epilogue / mix role, 512 = writer-side fences as well (results valid)
@@ -189,11 +193,9 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   return up2(d);
 }
 __device__ __forceinline__ void split2(float2 v, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __floats2half2_rn(v.x, v.y);
-  const float2 r = sub2(v, __half22float2(h));
-  __half2 l = __floats2half2_rn(r.x, r.y);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = *reinterpret_cast<uint32_t*>(&l);
+  hi = cvt_f16x2_sat(v.x, v.y);  // saturating: see common.cuh
+  const float2 r = sub2(v, __half22float2(*reinterpret_cast<const __half2*>(&hi)));
+  lo = cvt_f16x2_sat(r.x, r.y);
 }
 __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
   split2(make_float2(x, y), hi, lo);
@@ -277,8 +279,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     // elementwise over 16-byte chunks: position = (row, physical chunk); a thread owns 4 rows.
     if (pg.has_mix) {
       unsigned char* xbase = scratch + (size_t)V * SCR_ACT;  // slot B: X_v at v * SCR_ACT
+      size_t xstride = SCR_ACT;
       int it = 0;
       for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
+        if (pg.x_img) {  // this CTA's 128-row tile of every view's X image (4 k-blocks per tile)
+          xbase = pg.x_img + (size_t)(2 * (int64_t)u + rank) * 4 * TILE_IMG;
+          xstride = (size_t)pg.x_view_stride;
+        }
         TH_TIMED(0, if (lane == 0) wait_counter(cnt_scores, 4u * (uint32_t)(it + 1), 1, 256); __syncwarp());
         const long long t_mix = clock64();
         fence_proxy_async_all();
@@ -298,8 +305,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
             for (int i = 0; i < CHAIN_MAX_V; ++i)
               if (i < V) {
-                h[i] = ldcg16(xbase + (size_t)i * SCR_ACT + off);
-                l[i] = ldcg16(xbase + (size_t)i * SCR_ACT + off + A_TILE_BYTES);
+                h[i] = ldcg16(xbase + (size_t)i * xstride + off);
+                l[i] = ldcg16(xbase + (size_t)i * xstride + off + A_TILE_BYTES);
               }
           };
           fetch(tid, ch, cl);
@@ -334,7 +341,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
                     }
                   split2(o, hi[e], lo[e]);
                 }
-                unsigned char* dst = xbase + (size_t)j * SCR_ACT + off;
+                unsigned char* dst = xbase + (size_t)j * xstride + off;
                 st16_keep(dst, make_uint4(hi[0], hi[1], hi[2], hi[3]));
                 st16_keep(dst + A_TILE_BYTES, make_uint4(lo[0], lo[1], lo[2], lo[3]));
               }
@@ -840,24 +847,35 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
   const bool pre = run.premapped != 0;
   const float* p2_img = b.pix + (size_t)V * Pp * 256;
   // front: X_v = relu(alpha_res_0 pix_v) -> slot B ; S_v = relu(fc_0 rep_v) -> slot A
+  // TH_PREMAP_COPY=1 keeps the first form of the pre-mapped program (X copied into slot B by identity jobs)
+  static const bool pre_copy = getenv("TH_PREMAP_COPY") && atoi(getenv("TH_PREMAP_COPY"));
+  const bool x_in_chunk = pre && !pre_copy;
   for (int v = 0; v < V; ++v)
-    j_x[v] = pre ? B.add({B.in_view(b.pix, 256, v)}, wimg(h.h_xid), nullptr, 256, 1, EPI_IMG, B.slotB(v))
-                 : B.add({B.in_view(b.pix, PIX_LD, v)}, wimg(h.h_ar0), wf(h.ar0_b), 256, 1, EPI_IMG, B.slotB(v));
+    j_x[v] = x_in_chunk ? -1
+             : pre      ? B.add({B.in_view(b.pix, 256, v)}, wimg(h.h_xid), nullptr, 256, 1, EPI_IMG, B.slotB(v))
+                        : B.add({B.in_view(b.pix, PIX_LD, v)}, wimg(h.h_ar0), wf(h.ar0_b), 256, 1, EPI_IMG, B.slotB(v));
   for (int v = 0; v < V; ++v)
     j_s[v] = B.add({B.in_view(b.rep, REP_LD, v)}, wimg(h.h_fc0), wf(h.fc0_b), 256, 1, EPI_IMG, B.slotA(v));
   // key embeds: KS_v = key_embed_1 S_v stays in TMEM; KP_v = key_embed_0 X_v is consumed by the score epilogue
   for (int v = 0; v < V; ++v)
     B.add({Builder::scr(B.slotA(v), 256, j_s[v])}, wimg(h.h_k1), nullptr, 128, 0, EPI_KEEP, 0, v, 128 * v, 2);
   for (int v = 0; v < V; ++v) {
-    const int j = B.add({Builder::scr(B.slotB(v), 256, j_x[v])}, wimg(h.h_k0), wf(h.k0_b), 128, 0, EPI_SCORES,
-                        0, v, 128 * V, v == 0 ? 2 : 1);
+    const int j = B.add({x_in_chunk ? B.in_view(b.pix, 256, v) : Builder::scr(B.slotB(v), 256, j_x[v])}, wimg(h.h_k0),
+                        wf(h.k0_b), 128, 0, EPI_SCORES, 0, v, 128 * V, v == 0 ? 2 : 1);
     B.pg.job[j].bias2 = wf(h.k1_b);
   }
   B.pg.has_mix = 1;
   // N1_v = relu([S_v | XT_v] W_fc1f^T) in place of S_v; INTER_v = relu(fc_2 N1_v) in place again
-  for (int v = 0; v < V; ++v)
-    j_n1[v] = B.add({Builder::scr(B.slotA(v), 256, -1), Builder::scr(B.slotB(v), 256, -1, 1)},
-                    wimg(h.h_fc1f), wf(h.fc1f_b), 256, 1, EPI_IMG, B.slotA(v), v, -1, v == 0 ? 1 : 2);
+  for (int v = 0; v < V; ++v) {
+    Seg xt = x_in_chunk ? B.in_view(b.pix, 256, v) : Builder::scr(B.slotB(v), 256, -1, 1);
+    xt.dep_mix = 1;  // mixed in place (scratch slot B, or the chunk image), released per k-block
+    j_n1[v] = B.add({Builder::scr(B.slotA(v), 256, -1), xt}, wimg(h.h_fc1f), wf(h.fc1f_b), 256, 1, EPI_IMG,
+                    B.slotA(v), v, -1, v == 0 ? 1 : 2);
+  }
+  if (x_in_chunk) {
+    B.pg.x_img = reinterpret_cast<unsigned char*>(const_cast<float*>(b.pix));
+    B.pg.x_view_stride = (int64_t)(Pp / 128) * 4 * TILE_IMG;
+  }
   for (int v = 0; v < V; ++v)
     j_int[v] = B.add({Builder::scr(B.slotA(v), 256, j_n1[v])}, wimg(h.h_fc2), wf(h.fc2_b), 256, 1, EPI_IMG,
                      B.slotA(v));
@@ -911,6 +929,32 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     }
   }
   Program& pg = B.pg;
+  if (x_in_chunk) {
+    // Without the X jobs the hand-set TMEM waits above no longer match the job parity: derive them.
+    // Job G may start once the epilogue of job G - wait_back is done, so wait_back = G - (the last job
+    // whose epilogue still reads columns that G overwrites); kept key embeds are read by every score job.
+    const int n = pg.njobs;
+    const uint32_t flip_on_h = (n & 1) ? 256u : 0u;
+    int last_scores = -1;
+    for (int j = 0; j < n; ++j)
+      if (pg.job[j].epi == EPI_SCORES) last_scores = j;
+    for (int j = 0; j < n; ++j) {
+      int wb = n;  // nothing to wait for
+      for (int u = 1; u <= 2; ++u) {  // steady state: two consecutive units with their column flips
+        const int G = u * n + j;
+        const uint32_t c0 = ((uint32_t)pg.job[j].tmem_col + ((u & 1) ? flip_on_h : 0u)) & 511u, c1 = c0 + pg.job[j].N;
+        for (int A = 0; A < G; ++A) {
+          const int ja = A % n, ua = A / n;
+          const uint32_t a0 = ((uint32_t)pg.job[ja].tmem_col + ((ua & 1) ? flip_on_h : 0u)) & 511u, a1 = a0 + pg.job[ja].N;
+          if (a0 < c1 && c0 < a1) {
+            const int reader = ua * n + (pg.job[ja].epi == EPI_KEEP ? last_scores : ja);
+            if (G - reader < wb) wb = G - reader;
+          }
+        }
+      }
+      pg.job[j].wait_back = wb < 1 ? 1 : wb;
+    }
+  }
   if (run.program_dump) {  // host-side test hook: the program as built, nothing launched
     pg.afc_w = wf(h.afc_w);
     pg.afc_b = wf(h.afc_b);
@@ -948,24 +992,22 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
   pg.alpha_only = run.alpha_only;
   pg.num_units = (int)(Pp / 256);
 
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    TH_CUDA(cudaGetDevice(&dev));
-    TH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  static bool cfg = false;
-  if (!cfg) {
-    TH_CUDA(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    cfg = true;
-  }
+  int num_sms = 0;
+  if (device_sm_count(&num_sms)) return TH_ECUDA;
+  // per-device attribute: set on every launch (cheap) rather than caching a process-global flag
+  TH_CUDA(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const int nclusters = pg.num_units < num_sms / 2 ? pg.num_units : num_sms / 2;
   static const bool want_stats = getenv("TH_CHAIN_STATS") != nullptr;
   const char* dbg_env = getenv("TH_CHAIN_DBG");  // read per launch so that a test can toggle it
   pg.dbg = dbg_env ? atoi(dbg_env) : 0;
-  static unsigned long long* d_stats = nullptr;
+  static unsigned long long* d_stats_dev[64] = {nullptr};  // debug only (TH_CHAIN_STATS), one buffer per device
+  unsigned long long* d_stats = nullptr;
   if (want_stats) {
-    if (!d_stats) TH_CUDA(cudaMalloc(&d_stats, (size_t)num_sms * STATS_PER_CTA * 8));
+    int dev = 0;
+    TH_CUDA(cudaGetDevice(&dev));
+    dev &= 63;
+    if (!d_stats_dev[dev]) TH_CUDA(cudaMalloc(&d_stats_dev[dev], (size_t)num_sms * STATS_PER_CTA * 8));
+    d_stats = d_stats_dev[dev];
     TH_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)num_sms * STATS_PER_CTA * 8, st));
     pg.stats = d_stats;
   }

@@ -223,13 +223,12 @@ __global__ void __launch_bounds__(256) k_attn_mix(const float* __restrict__ kp, 
             o.w = fmaf(A[i][j], xv[i].w, o.w);
           }
         if (IMG) {
-          __half2 ha = __floats2half2_rn(o.x, o.y), hb = __floats2half2_rn(o.z, o.w);
-          const float2 fa = __half22float2(ha), fb = __half22float2(hb);
-          __half2 la = __floats2half2_rn(o.x - fa.x, o.y - fa.y), lb = __floats2half2_rn(o.z - fb.x, o.w - fb.y);
+          uint32_t ha, la, hb, lb;
+          split_hl2(o.x, o.y, ha, la);
+          split_hl2(o.z, o.w, hb, lb);
           unsigned char* q = reinterpret_cast<unsigned char*>(xt) + img_offset(j * Pp + p, c, 256);
-          *reinterpret_cast<uint2*>(q) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
-          *reinterpret_cast<uint2*>(q + 16384) =
-              make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+          *reinterpret_cast<uint2*>(q) = make_uint2(ha, hb);
+          *reinterpret_cast<uint2*>(q + 16384) = make_uint2(la, lb);
         } else {
           *reinterpret_cast<float4*>(xt + (j * Pp + p) * 256 + c) = o;
         }

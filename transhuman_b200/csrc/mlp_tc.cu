@@ -132,8 +132,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
     // 8*i + 4*(lane&1); the 8-byte swizzled stores of a half-warp hit 8 distinct 16-byte chunks.
     const int grp = warp >> 2, wq = warp & 3;
     float4 v[2][8];
+    // channel-major fp32 operand (GemmSeg::col_stride != 0, the pre-map GEMM over an NCHW map): a warp owns 32
+    // consecutive rows (pixels, lane = row) and all 64 columns of the k-block, so that every load instruction
+    // is one coalesced 128-byte line and a thread holds whole 16-byte chunks of its row
+    auto load_block_cm = [&](int st, int sgi, int kin) {
+      const GemmSeg sg = a.g.seg[sgi];
+      const int64_t m = (int64_t)st * (2 * BM) + rank * BM + wq * 32 + lane;
+      const bool row_ok = m < M;
+      const float* src = sg.ptr + (int64_t)kin * sg.col_stride + (row_ok ? m : 0);
+      float* vf = reinterpret_cast<float*>(&v[0][0]);
+#pragma unroll
+      for (int c = 0; c < 64; ++c)
+        vf[c] = (row_ok && kin + c < sg.K) ? __ldg(src + (int64_t)c * sg.col_stride) : 0.f;
+    };
     auto load_block = [&](int st, int sgi, int kin) {
       const GemmSeg sg = a.g.seg[sgi];
+      if (sg.col_stride) {
+        load_block_cm(st, sgi, kin);
+        return;
+      }
       const int64_t m0 = (int64_t)st * (2 * BM) + rank * BM;
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
@@ -175,17 +192,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
       if (!is_img) {
         unsigned char* a_hi = base_ptr + s * STAGE_BYTES;
         unsigned char* a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const int r = pass * 64 + wq * 16 + (lane >> 1);
+        if (a.g.seg[sgi].col_stride) {
+          const float* vf = reinterpret_cast<const float*>(&v[0][0]);
+          const int r = wq * 32 + lane;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            uint2 hi, lo;
-            split2(v[pass][i].x, v[pass][i].y, hi.x, lo.x);
-            split2(v[pass][i].z, v[pass][i].w, hi.y, lo.y);
-            const int off = r * 128 + ((i ^ (r & 7)) << 4) + ((lane & 1) << 3);
-            *reinterpret_cast<uint2*>(a_hi + off) = hi;
-            *reinterpret_cast<uint2*>(a_lo + off) = lo;
+            uint4 hi, lo;
+            split2(vf[8 * i + 0], vf[8 * i + 1], hi.x, lo.x);
+            split2(vf[8 * i + 2], vf[8 * i + 3], hi.y, lo.y);
+            split2(vf[8 * i + 4], vf[8 * i + 5], hi.z, lo.z);
+            split2(vf[8 * i + 6], vf[8 * i + 7], hi.w, lo.w);
+            const int off = r * 128 + ((i ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(a_hi + off) = hi;
+            *reinterpret_cast<uint4*>(a_lo + off) = lo;
+          }
+        } else {
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const int r = pass * 64 + wq * 16 + (lane >> 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint2 hi, lo;
+              split2(v[pass][i].x, v[pass][i].y, hi.x, lo.x);
+              split2(v[pass][i].z, v[pass][i].w, hi.y, lo.y);
+              const int off = r * 128 + ((i ^ (r & 7)) << 4) + ((lane & 1) << 3);
+              *reinterpret_cast<uint2*>(a_hi + off) = hi;
+              *reinterpret_cast<uint2*>(a_lo + off) = lo;
+            }
           }
         }
         fence_proxy_async();
@@ -386,8 +419,8 @@ int tc_image_kblocks(const GemmArgs& a) {
   return n;
 }
 
-int launch_gemm_tc(const GemmArgs& a, const void* w_image, cudaStream_t st) {
-  ProfScope prof_(PROF_GEMM, st);
+int launch_gemm_tc(const GemmArgs& a, const void* w_image, cudaStream_t st, int prof_cat) {
+  ProfScope prof_(prof_cat, st);
   if (a.M <= 0) return TH_OK;
   if (a.N != 128 && a.N != 256) {
     set_error("gemm_tc: N=%d unsupported (128 or 256)", a.N);
@@ -407,12 +440,8 @@ int launch_gemm_tc(const GemmArgs& a, const void* w_image, cudaStream_t st) {
     set_error("gemm_tc: exactly one of C / C_img, image output needs M %% 256 == 0");
     return TH_EINVAL;
   }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    TH_CUDA(cudaGetDevice(&dev));
-    TH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  if (device_sm_count(&num_sms)) return TH_ECUDA;
   tc::TcArgs t;
   t.g = a;
   t.wimg = static_cast<const unsigned char*>(w_image);
@@ -420,24 +449,43 @@ int launch_gemm_tc(const GemmArgs& a, const void* w_image, cudaStream_t st) {
   t.num_tiles = (int)cdiv(a.M, tc::BM);
   const int num_super = (t.num_tiles + 1) / 2;
   const int nclusters = num_super < num_sms / 2 ? num_super : num_sms / 2;
+  // function attributes are per device: set them on every launch (cheap) instead of caching a flag
   if (a.N == 256) {
-    static bool cfg = false;
-    if (!cfg) {
-      TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)tc::Cfg2<256>::SMEM));
-      cfg = true;
-    }
+    TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)tc::Cfg2<256>::SMEM));
     tc::k_gemm_tc2<256><<<2 * nclusters, tc::NUM_THREADS, tc::Cfg2<256>::SMEM, st>>>(t);
   } else {
-    static bool cfg = false;
-    if (!cfg) {
-      TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)tc::Cfg2<128>::SMEM));
-      cfg = true;
-    }
+    TH_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)tc::Cfg2<128>::SMEM));
     tc::k_gemm_tc2<128><<<2 * nclusters, tc::NUM_THREADS, tc::Cfg2<128>::SMEM, st>>>(t);
   }
   TH_LAUNCHED();
+  return TH_OK;
+}
+
+// Pre-mapped feature maps (kernels.cuh): per view two N = 256 GEMMs over the (H*W, 384) channel-major map,
+// [alpha_res_0 + b] -> channels 0..255 and [V1 rgb_res_0 ; fc_4 rgb_res_1 / V] -> channels 256..511 of the
+// channel-last output.  0.31 TFLOP per 512 x 512 x 3 frame; bound by reading the map twice and writing 1.6 GB.
+int launch_premap(const float* src_nchw, const unsigned char* weights, const PackedHeader& hdr, float* dst, int n_views,
+                  int h, int w, cudaStream_t st) {
+  const int64_t HW = (int64_t)h * w;
+  for (int v = 0; v < n_views; ++v)
+    for (int half = 0; half < 2; ++half) {
+      GemmArgs g{};
+      g.nseg = 1;
+      g.seg[0].ptr = src_nchw + (int64_t)v * TH_C_PIX * HW;
+      g.seg[0].K = TH_C_PIX;
+      g.seg[0].ld = 4;  // unused in channel-major mode (must pass the alignment check)
+      g.seg[0].col_stride = HW;
+      g.bias = reinterpret_cast<const float*>(weights + (half ? hdr.preb_b : hdr.ar0_b));
+      g.C = dst + (int64_t)v * HW * 512 + half * 256;
+      g.ldc = 512;
+      g.M = HW;
+      g.N = 256;
+      g.relu = 0;
+      int rc = launch_gemm_tc(g, weights + (half ? hdr.h_preb : hdr.h_ar0), st, PROF_PREMAP);
+      if (rc) return rc;
+    }
   return TH_OK;
 }
 

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include "common.cuh"
+
 namespace th {
 namespace tc {
 
@@ -133,14 +135,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-// split two floats into packed fp16 hi and lo pairs
-__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __floats2half2_rn(x, y);
-  float2 hf = __half22float2(h);
-  __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = *reinterpret_cast<uint32_t*>(&l);
-}
+// split two floats into packed fp16 hi and lo pairs (saturating, see common.cuh)
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) { split_hl2(x, y, hi, lo); }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -58,7 +58,7 @@ def launch_count(reset: bool = False) -> int:
     return int(_lib.load().th_launch_count(1 if reset else 0))
 
 
-PROFILE_CATEGORIES = ("cull", "features", "gemm", "pointwise", "integrate")
+PROFILE_CATEGORIES = ("cull", "features", "gemm", "pointwise", "integrate", "premap", "prologue")
 
 
 def profile_start():
@@ -67,9 +67,10 @@ def profile_start():
 
 def profile_stop() -> dict:
     """-> {category: (milliseconds, launches)} summed since profile_start()."""
-    ms = (C.c_double * 5)()
-    n = (C.c_int64 * 5)()
-    _lib.check(_lib.load().th_profile_stop(ms, n, 5), "th_profile_stop")
+    ncat = len(PROFILE_CATEGORIES)
+    ms = (C.c_double * ncat)()
+    n = (C.c_int64 * ncat)()
+    _lib.check(_lib.load().th_profile_stop(ms, n, ncat), "th_profile_stop")
     return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(PROFILE_CATEGORIES)}
 
 
@@ -118,7 +119,7 @@ class Frame:
         self.tok_rot = _f32(tok_rot, "tok_rot").view(n_tok, 3, 3)
         self.verts = _f32(verts, "verts").view(-1, 3)
         self.feat = _f32(feat_nhwc, "feat_nhwc")
-        # premapped (experimental): ``feat_nhwc`` is the output of ``premap_features`` (512 channels)
+        # premapped: ``feat_nhwc`` is the output of ``premap_features`` (512 channels)
         assert self.feat.dim() == 4 and self.feat.shape[0] == V and self.feat.shape[3] == (512 if premapped else 384), \
             "feature maps must be (V,H,W,384) channel-last"
         self.cam_R = _f32(cam_R, "cam_R").view(V, 3, 3)
@@ -330,14 +331,16 @@ def nchw_to_nhwc(x):
     return out
 
 
-def premap_features(x, weights: PackedWeights):
-    """EXPERIMENTAL (``TH_FLAG_PREMAPPED``): encoder maps (V,384,H,W) -> pre-mapped maps (V,H,W,512) with
-    ``alpha_res_0`` / ``rgb_res_0`` / ``rgb_res_1`` already applied (``th_premap_features``)."""
+def premap_features(x, weights: PackedWeights, out=None):
+    """``TH_FLAG_PREMAPPED``: encoder maps (V,384,H,W) -> pre-mapped maps (V,H,W,512) with ``alpha_res_0`` /
+    ``rgb_res_0`` / ``rgb_res_1`` already applied (``th_premap_features``, tcgen05 GEMM over the NCHW maps)."""
     lib = _lib.load()
     x = _f32(x, "x")
     n, c, h, w = x.shape
     assert c == 384 and n == weights.n_views
-    out = torch.empty((n, h, w, 512), device=x.device)
+    if out is None:
+        out = torch.empty((n, h, w, 512), device=x.device)
+    assert out.shape == (n, h, w, 512) and out.is_contiguous() and out.dtype == torch.float32
     _lib.check(lib.th_premap_features(_ptr(x), weights.blob.data_ptr(), n, h, w, _ptr(out), _stream()),
                "th_premap_features")
     return out

@@ -150,11 +150,16 @@ class Renderer:
         image_shape = batch['input_imgs'][0].shape[-2:]
         fs = np.asarray(pixel_scale, dtype=np.float64)
         sc = fs / np.array(image_shape)
+        weights = self._packed_weights(V, dev)
+        # pre-mapped maps (alpha_res_0 / rgb_res_0 / rgb_res_1 applied to the maps once per frame, tcgen05 GEMM over
+        # the encoder's NCHW output) wherever the layer-chained schedule exists; plain channel-last maps otherwise
+        premapped = V <= 3
+        feat = ops.premap_features(pixel_map, weights) if premapped else ops.nchw_to_nhwc(pixel_map)
         return ops.Frame(
             holder=holder, tok_xyz=tok_xyz, tok_rot=tok_rot, verts=batch['tar_smpl_vertice'][0],
-            feat_nhwc=ops.nchw_to_nhwc(pixel_map), cam_R=batch['input_R'][0].reshape(-1, 3, 3),
+            feat_nhwc=feat, premapped=premapped, cam_R=batch['input_R'][0].reshape(-1, 3, 3),
             cam_T=batch['input_T'][0].reshape(-1, 3), cam_K=batch['input_K'][0].reshape(-1, 3, 3),
-            Rh=batch['Rh'][0], Th=batch['Th'][0].reshape(3), weights=self._packed_weights(V, dev),
+            Rh=batch['Rh'][0], Th=batch['Th'][0].reshape(3), weights=weights,
             uv_scale=(np.float32(sc[0]), np.float32(sc[1])), knn=int(self.cfg.KNN),
             knn_dist_alpha=float(self.cfg.KNN_DIST_ALPHA), white_bkgd=bool(self.cfg.white_bkgd))
 
