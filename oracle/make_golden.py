@@ -85,15 +85,17 @@ class _FakeViT(nn.Module):
         return self.holder
 
 
-def build_reference(frame: dict, S: int):
+def build_reference(frame: dict, S: int, device: str = "cpu", knn=None, fake_prologue: bool = True):
     """Instantiate the genuine reference ``Network`` + ``Renderer`` for a
-    synthetic frame.  Returns ``(ns, net, renderer, batch)``."""
+    synthetic frame.  Returns ``(ns, net, renderer, batch)``.  ``device="cuda"`` runs the reference in
+    torch-CUDA (GPU box, from the copy under baseline/_ref); ``fake_prologue=False`` keeps the genuine
+    encoder + ViT (random init) and feeds them ``frame["input_imgs"]``."""
     cwd = ref_shim.make_scratch_cwd(
         smpl_pkl={"v_template": synth.make_body(0), "f": np.zeros((1, 3), dtype=np.int64)},
         kmeans={frame["n_class"]: frame["pc2voxel_ind"]})
-    ns = ref_shim.load_reference(orc.knn_points, cwd,
+    ns = ref_shim.load_reference(knn or orc.knn_points, cwd,
                                  opts=dict(N_samples=S, num_class=frame["n_class"], perturb=0,
-                                           rasterize=True))
+                                           rasterize=True), device=device)
     tf = orc.to_torch_frame(frame)
     torch.manual_seed(0)
     net = ns.cross_transformer.Network()
@@ -101,11 +103,15 @@ def build_reference(frame: dict, S: int):
     for name, arr in tf["weights"].items():
         assert name in sd, name
         sd[name].copy_(arr.view(sd[name].shape))
-    net.encoder = _FakeEncoder(tf["pixel_feat_map"])
-    net.ViT = _FakeViT(tf["holder"])
+    dev = torch.device(device)
+    if fake_prologue:
+        net.encoder = _FakeEncoder(tf["pixel_feat_map"].to(dev))
+        net.ViT = _FakeViT(tf["holder"].to(dev))
+    net.to(dev)
     net.train()  # run.py:29 -- inference runs with net.training == True
     renderer = ns.renderer_mod.Renderer(net)
     V, hw = frame["V"], frame["feat_hw"]
+    imgs = tf["input_imgs"][None] if "input_imgs" in tf else torch.zeros((1, V, 3, hw, hw))
     batch = {
         "ray_o": tf["ray_o"][None], "ray_d": tf["ray_d"][None],
         "near": tf["near"][None], "far": tf["far"][None],
@@ -113,13 +119,15 @@ def build_reference(frame: dict, S: int):
         "tar_smpl_vertice_smplcoord": tf["tar_smpl_vertice_smplcoord"][None],
         "Rh": tf["Rh"][None], "Th": tf["Th"][None],
         "blend_mtx": tf["blend_mtx"][None],
-        "input_imgs": [torch.zeros((1, V, 3, hw, hw))],
+        "input_imgs": [imgs],
         "input_R": [tf["input_R"][None]], "input_T": [tf["input_T"][None]], "input_K": [tf["input_K"][None]],
         "input_smpl_vertice": [tf["tar_smpl_vertice"][None]],
         "input_vizmaps": [torch.ones((1, V, synth.N_VERTS), dtype=torch.bool)],
         "input_blend_mtx": [tf["blend_mtx"][None]],
         "input_smpl_vertice_smplcoord": [tf["tar_smpl_vertice_smplcoord"][None]],
     }
+    if device != "cpu":
+        batch = {k: ([x.to(dev) for x in v] if isinstance(v, list) else v.to(dev)) for k, v in batch.items()}
     return ns, net, renderer, batch
 
 

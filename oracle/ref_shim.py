@@ -45,7 +45,18 @@ import types
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get("TRANSHUMAN_REFERENCE", "/root/reference")
+def _find_reference_root() -> str:
+    """``$TRANSHUMAN_REFERENCE``, else ``/root/reference`` (build container), else the unmodified copy that
+    ``oracle/install_ref.py`` ships to the GPU box under the git-ignored ``baseline/_ref/``."""
+    env = os.environ.get("TRANSHUMAN_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/lib/networks"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+REFERENCE_ROOT = _find_reference_root()
 _STATE: dict = {}
 _STUBBED: set = set()
 
@@ -187,11 +198,13 @@ def make_scratch_cwd(smpl_pkl: dict | None = None, kmeans: dict | None = None) -
     return d
 
 
-def load_reference(knn_points, cwd: str, opts: dict | None = None):
+def load_reference(knn_points, cwd: str, opts: dict | None = None, device: str = "cpu"):
     """Import the reference modules.  Returns a namespace with
     ``cfg, cross_transformer, renderer_mod, mesh_renderer_mod, nerf_net_utils,
     embedder, vision_transformer``.  Can only be done once per process (the
-    reference keeps a global ``cfg``); later calls update ``cfg`` in place."""
+    reference keeps a global ``cfg``); later calls update ``cfg`` in place.
+    ``device="cuda"`` leaves ``.cuda()`` alone (the reference in torch-CUDA on the GPU box); the default makes
+    it an identity so the CUDA-only prologue runs on the CPU."""
     if not reference_available():
         raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
     os.chdir(cwd)
@@ -211,8 +224,9 @@ def load_reference(knn_points, cwd: str, opts: dict | None = None):
     sys.argv = ["ref_shim", "--cfg_file", "configs/train_or_eval.yaml",
                 "pretrained", "False", "gpus", "[0]"]
     try:
-        torch.Tensor.cuda = lambda self, *a, **k: self  # CPU only
-        torch.cuda.current_device = lambda: "cpu"
+        if device == "cpu":
+            torch.Tensor.cuda = lambda self, *a, **k: self  # CPU only
+            torch.cuda.current_device = lambda: "cpu"
         cfg = importlib.import_module("lib.config").cfg
     finally:
         sys.argv = argv
@@ -225,5 +239,6 @@ def load_reference(knn_points, cwd: str, opts: dict | None = None):
     ns.nerf_net_utils = importlib.import_module("lib.networks.renderer.nerf_net_utils")
     ns.embedder = importlib.import_module("lib.networks.embedder")
     ns.vision_transformer = importlib.import_module("lib.networks.vision_transformer")
+    ns.make_renderer = importlib.import_module("lib.networks.renderer.make_renderer")
     _STATE["ns"] = ns
     return ns

@@ -67,8 +67,8 @@ def knn_points(p1: torch.Tensor, p2: torch.Tensor, K: int = 1, return_nn: bool =
     assert p1.dtype == torch.float32 and p2.dtype == torch.float32
     B, P, _ = p1.shape
     N = p2.shape[1]
-    dists = torch.empty((B, P, K), dtype=torch.float32)
-    idx = torch.empty((B, P, K), dtype=torch.int64)
+    dists = torch.empty((B, P, K), dtype=torch.float32, device=p1.device)
+    idx = torch.empty((B, P, K), dtype=torch.int64, device=p1.device)
     for b in range(B):
         for s in range(0, P, chunk):
             d2 = pairwise_d2(p1[b, s:s + chunk], p2[b])

@@ -112,7 +112,19 @@ def test_pack_weights_folds_layers(lib):
         col = (((kk >> 3) ^ (n & 7)) << 3) + (kk & 7)          # position of element kk inside the swizzled row
         rec = np.concatenate([np.take_along_axis(img[kb, 0], col, 1) + np.take_along_axis(img[kb, 1], col, 1)
                               for kb in range(4)], axis=1)
-        assert np.abs(rec - fc0).max() <= 2.0 ** -21 * np.abs(fc0).max()
+        # the image holds W * 2^e, max|W| 2^e in (2^13, 2^14]; the header lists (image offset, 2^-e) per matrix
+        hdr_tail = 16 + 57 * 8
+        img_off = struct.unpack_from("<24Q", blob, hdr_tail)
+        inv_scale = struct.unpack_from("<24f", blob, hdr_tail + 24 * 8)
+        n_img = struct.unpack_from("<i", blob, hdr_tail + 24 * 8 + 24 * 4)[0]
+        assert 16 <= n_img <= 24 and h_fc0 in img_off[:n_img]
+        inv = inv_scale[img_off.index(h_fc0)]
+        assert 2.0 ** 13 < np.abs(fc0).max() / inv <= 2.0 ** 14 and np.log2(inv) == np.round(np.log2(inv))
+        assert np.abs(rec * inv - fc0).max() <= 2.0 ** -21 * np.abs(fc0).max()
+        # ... and keeps 22 bits for SMALL weights too (unscaled, the fp16 lo plane flushes below 6e-8)
+        small = np.abs(fc0) < 1e-3 * np.abs(fc0).max()
+        small &= fc0 != 0
+        assert small.any() and np.all(np.abs(rec * inv - fc0)[small] <= 2.0 ** -20 * np.abs(fc0[small]) + 2.0 ** -38)
 
 
 def _pack(lib, w, V):

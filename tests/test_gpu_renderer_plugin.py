@@ -107,7 +107,10 @@ def _oracle_frame(fr, renderer, batch):
     frame = renderer.prepare_frame(batch)
     tf = orc.to_torch_frame(fr)
     tf["holder"] = frame.holder.cpu()
-    tf["pixel_feat_map"] = frame.feat.permute(0, 3, 1, 2).contiguous().cpu()
+    # the plugin keeps only the PRE-MAPPED maps; the oracle takes the encoder's own output
+    with torch.no_grad():
+        images = batch["input_imgs"][0].reshape(-1, *batch["input_imgs"][0].shape[2:])
+        tf["pixel_feat_map"] = renderer.net.encoder(images)[2].contiguous().cpu()
     tokens = (frame.tok_xyz.cpu(), torch.cat([frame.tok_rot.cpu().double(), torch.zeros(300, 3, 1, dtype=torch.float64)],
                                              dim=2))
     tok_blend = torch.zeros((300, 4, 4), dtype=torch.float64)

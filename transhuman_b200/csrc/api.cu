@@ -2,6 +2,7 @@
 // weight packing, workspace planning and the kernel schedule of the fused path.
 #include <cuda_fp16.h>
 #include <stdarg.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -333,10 +334,28 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
     if (!m.h) continue;
     const float* src = W(h.*(m.w));
     unsigned char* img = blob + h.*(m.h);
+    // power-of-two scale (PackedHeader::img_inv_scale): max|w| 2^e in (2^13, 2^14]
+    float wmax = 0.f;
+    for (size_t i = 0; i < (size_t)m.N * m.K; ++i) wmax = fmaxf(wmax, fabsf(src[i]));
+    int e = 0;
+    if (wmax > 0.f && isfinite(wmax)) {
+      int ex = 0;
+      frexpf(wmax, &ex);  // wmax = f * 2^ex, f in [0.5, 1)
+      e = 14 - ex;
+      if (e > 60) e = 60;
+      if (e < -60) e = -60;
+    }
+    const float up = ldexpf(1.0f, e);
+    PackedHeader* hb = reinterpret_cast<PackedHeader*>(blob);
+    if (hb->n_img < 24) {
+      hb->img_off[hb->n_img] = h.*(m.h);
+      hb->img_inv_scale[hb->n_img] = ldexpf(1.0f, -e);
+      ++hb->n_img;
+    }
     for (int kb = 0; kb < m.K / 64; ++kb)
       for (int n = 0; n < m.N; ++n)
         for (int kk = 0; kk < 64; ++kk) {
-          const float x = src[(size_t)n * m.K + kb * 64 + kk];
+          const float x = src[(size_t)n * m.K + kb * 64 + kk] * up;
           // saturating like the device-side split (common.cuh): no inf planes from a huge weight
           auto sat = [](float f) { return f > 65504.f ? 65504.f : (f < -65504.f ? -65504.f : f); };
           const __half a = __float2half_rn(sat(x));

@@ -121,7 +121,19 @@ struct PackedHeader {
   // pre-map GEMM (th_premap_features) runs as two N = 256 tcgen05 launches, h_ar0 / ar0_b and h_preb / preb_b
   uint64_t preb_w, preb_b;      // (256,384), (256)
   uint64_t h_preb;
+  // Per-matrix power-of-two scale of the fp16 hi/lo images: the image holds W * 2^e with e chosen so that
+  // max|W| 2^e lies in (2^13, 2^14]; every epilogue multiplies its accumulator by 2^-e (exact) before the bias.
+  // The fp16 lo plane is subnormal below 6.1e-5 (absolute step 6e-8): unscaled, a weight of 1e-3 would keep
+  // 15 instead of 22 significant bits and weights below 6e-5 almost none of the lo half.
+  uint64_t img_off[24];
+  float img_inv_scale[24];
+  int32_t n_img, pad_;
 };
+inline float img_inv_scale_of(const PackedHeader& h, uint64_t off) {
+  for (int i = 0; i < h.n_img && i < 24; ++i)
+    if (h.img_off[i] == off) return h.img_inv_scale[i];
+  return 1.0f;
+}
 constexpr uint32_t PACK_MAGIC = 0x35574854u;
 
 // Byte offset of the hi element (row, col) of a (rows, C) activation in tile-image
@@ -215,6 +227,7 @@ struct GemmArgs {
   int64_t M;
   int N;  // multiple of 128
   int relu;
+  float acc_scale;  // tensor-core path: the accumulator is multiplied by this before the bias (img_inv_scale_of); 0 = 1
 };
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& a, const void* w_hi_lo, cudaStream_t st, int prof_cat = PROF_GEMM);

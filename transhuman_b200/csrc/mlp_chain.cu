@@ -71,6 +71,8 @@ struct Job {
   const float* bias2;       // EPI_SCORES: bias of the kept key embed
   uint32_t out_off;         // EPI_IMG: destination inside the CTA's scratch
   int32_t nseg, nkb, N, relu, epi, tmem_col, wait_back, view;
+  float acc_scale;          // 2^-e of this job's weight image (PackedHeader::img_inv_scale): acc * scale + bias
+  float acc_scale2;         // EPI_SCORES: the scale of the kept key embeds' weight image
 };
 struct Program {
   // TMA descriptors: tile images as rows of 64 fp16 (128 B).  tm_a: box 256 rows (one 32 KB hi|lo
@@ -527,6 +529,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           const int ncol = N >> 1, cbeg = grp * ncol;
           const bool swap = (et & 1) != 0;
           const bool relu = jb.relu != 0;
+          const float2 sc2 = make_float2(jb.acc_scale, jb.acc_scale);
           // 32 accumulator columns -> 2 x (hi sector, lo sector)
           auto emit = [&](const uint32_t (&v)[32], int c0) {
             unsigned char* kb_out = out + (size_t)(c0 >> 6) * TILE_IMG;
@@ -542,9 +545,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
                 float2 x[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  x[e] = add2(make_float2(__uint_as_float(v[half * 16 + cc * 8 + 2 * e]),
+                  x[e] = fma2(make_float2(__uint_as_float(v[half * 16 + cc * 8 + 2 * e]),
                                           __uint_as_float(v[half * 16 + cc * 8 + 2 * e + 1])),
-                              bb[e]);
+                              sc2, bb[e]);
                   if (relu) {
                     x[e].x = fmaxf(x[e].x, 0.f);
                     x[e].y = fmaxf(x[e].y, 0.f);
@@ -590,6 +593,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           // warps of a lane quadrant take 64 of the 128 key channels each and group 1 hands its
           // partial sums over through shared memory.
           float sc[TH_MAX_VIEWS];
+          const float s_kp = jb.acc_scale, s_ks = jb.acc_scale2;
 #pragma unroll
           for (int jv = 0; jv < TH_MAX_VIEWS; ++jv) sc[jv] = 0.f;
 #pragma unroll 1
@@ -600,10 +604,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
               const float4 bq = *reinterpret_cast<const float4*>(bias_s + c0 + e);
-              kp[e + 0] = __float_as_uint(__uint_as_float(kp[e + 0]) + bq.x);
-              kp[e + 1] = __float_as_uint(__uint_as_float(kp[e + 1]) + bq.y);
-              kp[e + 2] = __float_as_uint(__uint_as_float(kp[e + 2]) + bq.z);
-              kp[e + 3] = __float_as_uint(__uint_as_float(kp[e + 3]) + bq.w);
+              kp[e + 0] = __float_as_uint(fmaf(__uint_as_float(kp[e + 0]), s_kp, bq.x));
+              kp[e + 1] = __float_as_uint(fmaf(__uint_as_float(kp[e + 1]), s_kp, bq.y));
+              kp[e + 2] = __float_as_uint(fmaf(__uint_as_float(kp[e + 2]), s_kp, bq.z));
+              kp[e + 3] = __float_as_uint(fmaf(__uint_as_float(kp[e + 3]), s_kp, bq.w));
             }
 #pragma unroll
             for (int jv = 0; jv < TH_MAX_VIEWS; ++jv)
@@ -614,10 +618,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
                   const float4 bq = *reinterpret_cast<const float4*>(bias_s + 128 + c0 + e);
-                  sc[jv] = fmaf(__uint_as_float(kp[e + 0]), __uint_as_float(ks[e + 0]) + bq.x, sc[jv]);
-                  sc[jv] = fmaf(__uint_as_float(kp[e + 1]), __uint_as_float(ks[e + 1]) + bq.y, sc[jv]);
-                  sc[jv] = fmaf(__uint_as_float(kp[e + 2]), __uint_as_float(ks[e + 2]) + bq.z, sc[jv]);
-                  sc[jv] = fmaf(__uint_as_float(kp[e + 3]), __uint_as_float(ks[e + 3]) + bq.w, sc[jv]);
+                  sc[jv] = fmaf(__uint_as_float(kp[e + 0]), fmaf(__uint_as_float(ks[e + 0]), s_ks, bq.x), sc[jv]);
+                  sc[jv] = fmaf(__uint_as_float(kp[e + 1]), fmaf(__uint_as_float(ks[e + 1]), s_ks, bq.y), sc[jv]);
+                  sc[jv] = fmaf(__uint_as_float(kp[e + 2]), fmaf(__uint_as_float(ks[e + 2]), s_ks, bq.z), sc[jv]);
+                  sc[jv] = fmaf(__uint_as_float(kp[e + 3]), fmaf(__uint_as_float(ks[e + 3]), s_ks, bq.w), sc[jv]);
                 }
               }
           }
@@ -663,7 +667,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              acc = fmaf(fmaxf(__uint_as_float(v[e]) + bias_s[c0 + e], 0.f), __ldg(pg.afc_w + c0 + e), acc);
+              acc = fmaf(fmaxf(fmaf(__uint_as_float(v[e]), jb.acc_scale, bias_s[c0 + e]), 0.f), __ldg(pg.afc_w + c0 + e), acc);
           }
           alpha_reg = acc + __ldg(pg.afc_b);
           if (pt < pg.P) {
@@ -684,7 +688,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const float t = fmaxf(__uint_as_float(v[e]) + bias_s[c0 + e], 0.f);
+              const float t = fmaxf(fmaf(__uint_as_float(v[e]), jb.acc_scale, bias_s[c0 + e]), 0.f);
               o0 = fmaf(t, __ldg(pg.rgb_w + c0 + e), o0);
               o1 = fmaf(t, __ldg(pg.rgb_w + 128 + c0 + e), o1);
               o2 = fmaf(t, __ldg(pg.rgb_w + 256 + c0 + e), o2);
@@ -857,11 +861,20 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
   for (int v = 0; v < V; ++v)
     j_s[v] = B.add({B.in_view(b.rep, REP_LD, v)}, wimg(h.h_fc0), wf(h.fc0_b), 256, 1, EPI_IMG, B.slotA(v));
   // key embeds: KS_v = key_embed_1 S_v stays in TMEM; KP_v = key_embed_0 X_v is consumed by the score epilogue
+  if (x_in_chunk && V == 3) {
+    // KS_0 is issued right after S_2 (accumulator columns 0..255, still being drained by its epilogue): give the
+    // first two kept key embeds the columns of S_1's accumulator, which was drained a job earlier
+    // (TH_CHAIN_STATS: KS_0 waited 10 kcycles per unit for TMEM at columns 0..127)
+    B.pg.ks_col[0] = 256;
+    B.pg.ks_col[1] = 384;
+    B.pg.ks_col[2] = 0;
+    B.pg.kp_col = 128;
+  }
   for (int v = 0; v < V; ++v)
-    B.add({Builder::scr(B.slotA(v), 256, j_s[v])}, wimg(h.h_k1), nullptr, 128, 0, EPI_KEEP, 0, v, 128 * v, 2);
+    B.add({Builder::scr(B.slotA(v), 256, j_s[v])}, wimg(h.h_k1), nullptr, 128, 0, EPI_KEEP, 0, v, B.pg.ks_col[v], 2);
   for (int v = 0; v < V; ++v) {
     const int j = B.add({x_in_chunk ? B.in_view(b.pix, 256, v) : Builder::scr(B.slotB(v), 256, j_x[v])}, wimg(h.h_k0),
-                        wf(h.k0_b), 128, 0, EPI_SCORES, 0, v, 128 * V, v == 0 ? 2 : 1);
+                        wf(h.k0_b), 128, 0, EPI_SCORES, 0, v, B.pg.kp_col, v == 0 ? 2 : 1);
     B.pg.job[j].bias2 = wf(h.k1_b);
   }
   B.pg.has_mix = 1;
@@ -929,6 +942,10 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     }
   }
   Program& pg = B.pg;
+  for (int j = 0; j < pg.njobs; ++j) {  // accumulator scales of the weight images (PackedHeader::img_inv_scale)
+    pg.job[j].acc_scale = img_inv_scale_of(h, (uint64_t)(pg.job[j].wimg - run.weights));
+    pg.job[j].acc_scale2 = img_inv_scale_of(h, h.h_k1);
+  }
   if (x_in_chunk) {
     // Without the X jobs the hand-set TMEM waits above no longer match the job parity: derive them.
     // Job G may start once the epilogue of job G - wait_back is done, so wait_back = G - (the last job

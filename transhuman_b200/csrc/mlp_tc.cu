@@ -111,6 +111,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < N; i += NUM_THREADS) s_bias[i] = a.g.bias ? a.g.bias[i] : 0.f;
+  const float acc_scale = a.g.acc_scale != 0.f ? a.g.acc_scale : 1.0f;  // 2^-e of the weight image
   if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)TMEM_COLS)
@@ -337,7 +338,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
               float x[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                x[e] = __uint_as_float(v[j + e]) + s_bias[kb * BK + h * 32 + j + e];
+                x[e] = fmaf(__uint_as_float(v[j + e]), acc_scale, s_bias[kb * BK + h * 32 + j + e]);
                 if (a.g.relu) x[e] = fmaxf(x[e], 0.f);
               }
               uint4 hi, lo;
@@ -369,10 +370,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o;
-            o.x = __uint_as_float(v[j + 0]) + s_bias[c0 + j + 0];
-            o.y = __uint_as_float(v[j + 1]) + s_bias[c0 + j + 1];
-            o.z = __uint_as_float(v[j + 2]) + s_bias[c0 + j + 2];
-            o.w = __uint_as_float(v[j + 3]) + s_bias[c0 + j + 3];
+            o.x = fmaf(__uint_as_float(v[j + 0]), acc_scale, s_bias[c0 + j + 0]);
+            o.y = fmaf(__uint_as_float(v[j + 1]), acc_scale, s_bias[c0 + j + 1]);
+            o.z = fmaf(__uint_as_float(v[j + 2]), acc_scale, s_bias[c0 + j + 2]);
+            o.w = fmaf(__uint_as_float(v[j + 3]), acc_scale, s_bias[c0 + j + 3]);
             if (a.g.relu) {
               o.x = fmaxf(o.x, 0.f);
               o.y = fmaxf(o.y, 0.f);
@@ -483,6 +484,7 @@ int launch_premap(const float* src_nchw, const unsigned char* weights, const Pac
       g.M = HW;
       g.N = 256;
       g.relu = 0;
+      g.acc_scale = img_inv_scale_of(hdr, half ? hdr.h_preb : hdr.h_ar0);
       int rc = launch_gemm_tc(g, weights + (half ? hdr.h_preb : hdr.h_ar0), st, PROF_PREMAP);
       if (rc) return rc;
     }
