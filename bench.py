@@ -3,17 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One step = one pass of the hot path (sample -> k-NN/DPaRF -> pixel gather ->
-per-point MLP -> integrate) over one synthetic 512x512 frame at 64 samples/ray,
-300 tokens, K=7, V=3 -- BASELINE.json configs[1] -- in DENSE mode (every sample
-evaluated, `Renderer.render` semantics; data independent).  With N > 1 ranks
-(torchrun), every rank renders its own 512x512 target view of the same frame
-state and the images are gathered with one NCCL all_gather (configs[3]); the
-value is the rays all ranks rendered / max-over-ranks device time ("weak").
+One step = one pass of the hot path over one synthetic 512x512 frame at 64 samples/ray, 300 tokens, K=7, V=3
+-- BASELINE.json configs[1] -- in DENSE mode (every sample evaluated, `Renderer.render` semantics; data
+independent), starting from the encoder's output `(V,384,H,W)`:
 
-`--impl reference` times the oracle port of the reference's PyTorch CPU path
-(oracle/transhuman_oracle.py) on the host cores, on a bounded ray sample of the
-same workload per step.  Rank 0 only.
+    pre-map GEMM over the maps -> sample -> k-NN/DPaRF -> pixel gather -> per-point network -> integrate.
+
+With N > 1 ranks (torchrun), every rank renders its own 512x512 target view of the same frame state and the images
+are gathered with one NCCL all_gather (configs[3]); `value` = rays all ranks rendered / max-over-ranks device time
+("weak").  A `strong` record beside it shards ONE view over the ranks as interleaved 16x16 tiles.
+
+`--impl reference` times the reference's own CPU implementation of the path on the host cores, on a bounded ray
+sample of the same workload per step: the GENUINE `if_clight_renderer.Renderer.render` imported in place through
+`oracle/ref_shim.py` (from `/root/reference`, or from its unmodified copy under the git-ignored `baseline/_ref/` on the
+GPU box) when that tree exists (`kind: "reference"`), else the oracle port (`kind: "port"`).  Rank 0 only.
+
+Extra records of the default N = 1 run (reported, not the headline): `cpu_baseline` (the reference arm, 3 steps, in a
+subprocess), `torch_cuda_baseline` (the genuine reference in torch-CUDA on this GPU, TF32 off and on, full frame --
+the configs[1] bar), `culled` (render_fast semantics), `plugin` (the Renderer plugin end to end with its prologue
+breakdown), `configs` (C3 and C5).
 """
 from __future__ import annotations
 
@@ -100,21 +108,34 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------
-def build_workload(args, rank: int, device):
-    """Synthetic frame state on the device (SURVEY 8d) + this rank's ray bundle."""
-    from transhuman_b200 import ops, synth
-    from transhuman_b200.renderer import segment_mean
+def synthetic_frame(args, rank: int = 0, with_maps: bool = True):
+    """The synthetic frame of SURVEY 8d (numpy) + the (V,384,H,W) encoder output as a torch CPU tensor."""
+    from transhuman_b200 import synth
     H = args.size
     fr = synth.make_frame(H=H, W=H, n_class=args.tokens, V=args.views, feat_hw=H, seed=0,
                           target_azimuth=1.0 + rank * 2.0 * math.pi / 8.0, with_feature_maps=False)
+    maps = None
+    if with_maps:
+        g = torch.Generator().manual_seed(1234)
+        maps = torch.randn((args.views, 384, H, H), generator=g)
+    return fr, maps
+
+
+def build_workload(args, rank: int, device):
+    """Synthetic frame state on the device (SURVEY 8d) + this rank's ray bundle."""
+    from transhuman_b200 import ops
+    from transhuman_b200.renderer import segment_mean
+    fr, maps = synthetic_frame(args, rank, with_maps=True)
+    H = args.size
 
     def t(a):
         return torch.from_numpy(np.ascontiguousarray(a)).to(device)
 
-    g = torch.Generator(device=device).manual_seed(1234)
     premapped = not args.plain_maps and not args.simt and args.views <= 3
-    # the encoder's output layout (V,384,H,W) NCHW, 1.2 GB at 512^2: the step's input
-    feat_nchw = torch.randn((args.views, 384, H, H), generator=g, device=device)
+    # the encoder's output layout (V,384,H,W) NCHW, 1.2 GB at 512^2: the step's input (the same values the
+    # reference arms read)
+    feat_nchw = maps.to(device)
+    del maps
     pc2 = t(fr["pc2voxel_ind"]).long()
     tok_xyz = segment_mean(t(fr["tar_smpl_vertice_smplcoord"]), pc2, args.tokens).float()
     tok_rot = segment_mean(t(fr["blend_mtx"]), pc2, args.tokens)[:, :3, :3].float().contiguous()
@@ -129,38 +150,193 @@ def build_workload(args, rank: int, device):
     return fr, frame, host_rays
 
 
+def _centre_block(H: int, n_rays: int) -> slice:
+    start = (H // 2) * H + max(0, H // 2 - n_rays // 2) if n_rays < H else (H // 2 - n_rays // (2 * H)) * H
+    return slice(start, start + n_rays)
+
+
+def reference_available() -> bool:
+    from oracle import ref_shim
+    return ref_shim.reference_available()
+
+
 def cpu_reference_leg(args, n_rays: int, steps: int, warmup: int):
-    """The oracle port of the reference's PyTorch CPU path on a bounded ray
-    sample of the same workload.  Returns (rays/s, cores, seconds/step, sample)."""
+    """The reference's CPU path on a bounded ray sample of the same workload: the genuine Renderer.render through
+    oracle/ref_shim when the reference tree is present, else the oracle port.
+    Returns (rays/s, cores, seconds/step, sample description, kind)."""
     from oracle import transhuman_oracle as orc
-    from transhuman_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     H = args.size
-    fr = synth.make_frame(H=H, W=H, n_class=args.tokens, V=args.views, feat_hw=H, seed=0, with_feature_maps=False)
-    g = torch.Generator().manual_seed(1234)
-    fr_t = orc.to_torch_frame(fr)
-    fr_t["pixel_feat_map"] = torch.randn((args.views, 384, H, H), generator=g)
-    tokens = orc.build_tokens(fr_t)
-    # a block of rays around the image centre (dense mode: cost is data independent)
-    start = (H // 2) * H + max(0, H // 2 - n_rays // 2) if n_rays < H else (H // 2 - n_rays // (2 * H)) * H
-    sel = slice(start, start + n_rays)
-    sub = dict(fr_t)
-    for k in ("ray_o", "ray_d", "near", "far"):
-        sub[k] = fr_t[k][sel]
+    fr, maps = synthetic_frame(args)
+    sel = _centre_block(H, n_rays)
+    what = (f"{n_rays} rays x {args.samples} samples around the image centre of the {H}x{H} frame, dense, ")
     times = []
-    with torch.no_grad():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            out = orc.render(sub, args.samples, tokens=tokens)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
+    if reference_available():
+        from oracle.make_golden import build_reference
+        fr["pixel_feat_map"] = maps.numpy()
+        ns, net, renderer, batch = build_reference(fr, args.samples, device="cpu")
+        for k in ("ray_o", "ray_d", "near", "far"):
+            batch[k] = batch[k][:, sel]
+        with torch.no_grad():
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                out = renderer.render(dict(batch), is_train=False)
+                dt = time.perf_counter() - t0
+                if i >= warmup:
+                    times.append(dt)
+        kind = "reference"
+        what += "genuine reference Renderer.render (torch CPU fp32) imported through oracle/ref_shim.py"
+    else:
+        fr_t = orc.to_torch_frame(fr)
+        fr_t["pixel_feat_map"] = maps
+        tokens = orc.build_tokens(fr_t)
+        sub = dict(fr_t)
+        for k in ("ray_o", "ray_d", "near", "far"):
+            sub[k] = fr_t[k][sel]
+        with torch.no_grad():
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                out = orc.render(sub, args.samples, tokens=tokens)
+                dt = time.perf_counter() - t0
+                if i >= warmup:
+                    times.append(dt)
+        kind = "port"
+        what += "oracle port of Renderer.render (torch CPU fp32; reference tree not present)"
     assert torch.isfinite(out["rgb_map"]).all()
     sec = float(np.mean(times))
-    sample = (f"{n_rays} rays x {args.samples} samples around the image centre of the {H}x{H} frame, dense, "
-              f"oracle port of Renderer.render (torch CPU fp32)")
-    return n_rays / sec, torch.get_num_threads(), sec, sample
+    return n_rays / sec, torch.get_num_threads(), sec, what, kind
+
+
+def workload_and_metric(args):
+    workload = (f"configs[1]: {args.size}x{args.size} render, {args.samples} samples/ray, {args.tokens} tokens, "
+                f"k=7, V={args.views}, dense (every sample evaluated)")
+    return workload, f"rays/sec at {args.size}x{args.size}x{args.samples} samples"
+
+
+def reference_arm(args):
+    workload, metric = workload_and_metric(args)
+    val, cores, sec, sample, kind = cpu_reference_leg(args, args.cpu_rays, args.steps, args.warmup)
+    return {"impl": "reference", "metric": metric, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload},
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def cpu_baseline_subprocess(args):
+    """The reference arm, 3 steps after 1 warm-up, in its own process (the shim makes `.cuda()` an identity for the CPU
+    run, which must not leak into this process)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+           "--cpu-rays", str(args.cpu_rays), "--size", str(args.size), "--samples", str(args.samples),
+           "--tokens", str(args.tokens), "--views", str(args.views)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT).stdout
+        for line in out.splitlines():
+            if line.startswith("{"):
+                return json.loads(line)["cpu_baseline"]
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:200]}
+    return {"error": "no JSON line from the reference arm"}
+
+
+def torch_cuda_baseline(args, device, ours_img):
+    """BASELINE configs[1]'s bar: the genuine reference Renderer.render in torch-CUDA on this GPU, full frame, TF32 off
+    (the parity setting) and on.  knn_points (pytorch3d, absent) = squared distances + torch.topk on the device."""
+    from oracle import transhuman_oracle as orc
+    from oracle.make_golden import build_reference
+
+    def knn_topk(p1, p2, K=1, return_nn=False):
+        d2 = torch.stack([orc.pairwise_d2(p1[b], p2[b]) for b in range(p1.shape[0])]) if p1.shape[1] * p2.shape[1] < (1 << 28) \
+            else None
+        if d2 is None:
+            return orc.knn_points(p1, p2, K=K, chunk=65536)
+        v, i = torch.topk(d2, K, dim=2, largest=False, sorted=True)
+        return v, i, None
+
+    fr, maps = synthetic_frame(args)
+    fr["pixel_feat_map"] = maps.numpy()
+    ns, net, renderer, batch = build_reference(fr, args.samples, device=str(device), knn=knn_topk)
+    res = {"impl": "genuine reference if_clight_renderer.Renderer.render via oracle/ref_shim.py, torch "
+                   f"{torch.__version__} CUDA eager, full {args.size}x{args.size} frame, dense; prologue = fake encoder / "
+                   "ViT returning the synthetic maps / tokens + the reference's own paint / grouping loops; "
+                   "knn_points = pairwise d2 + torch.topk (pytorch3d absent)"}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    N = args.size * args.size
+    try:
+        for name, tf32 in (("tf32_off", False), ("tf32_on", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                out = renderer.render(dict(batch), is_train=False)       # warm-up
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(2):
+                    out = renderer.render(dict(batch), is_train=False)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            img = torch.cat([out["rgb_map"][0], out["acc_map"][0][:, None], out["depth_map"][0][:, None]], dim=1)
+            res[name] = {"rays_per_s": N / (ms * 1e-3), "ms_per_frame": ms,
+                         "rgb_max_abs_vs_ours": float((img[:, :3] - ours_img[:, :3]).abs().max()),
+                         "rays_beyond_1e-4_vs_ours": int(((img[:, :3] - ours_img[:, :3]).abs().amax(dim=1) > 1e-4).sum())}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return res
+
+
+def other_configs(args, device):
+    """C3 (512^2 x 128 samples, 1500 tokens) and C5 (256^3 density grid, 6000 tokens): parity-test cases, timed here so
+    that the numbers quoted in DESIGN.md come from the driver's run."""
+    from tests.gpu_util import frame_to_device
+    from transhuman_b200 import ops, synth
+    from transhuman_b200.renderer import segment_mean
+    out = {}
+    for name, tokens, S in (("c3_512x512x128_1500tok", 1500, 128),):
+        fr = synth.make_frame(H=512, W=512, n_class=tokens, V=3, feat_hw=256, seed=0)
+        pc2 = torch.from_numpy(fr["pc2voxel_ind"]).long()
+        tk = (segment_mean(torch.from_numpy(fr["tar_smpl_vertice_smplcoord"]), pc2, tokens).float(),
+              segment_mean(torch.from_numpy(fr["blend_mtx"]), pc2, tokens))
+        frame, rays = frame_to_device(fr, tk, device)
+        rec = {}
+        for mode, m in (("dense", ops.TH_RENDER_DENSE), ("culled", ops.TH_RENDER_MASKED)):
+            ops.render_rays(frame, *rays, S, mode=m)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                o = ops.render_rays(frame, *rays, S, mode=m)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            rec[mode] = {"rays_per_s": 512 * 512 / (ms * 1e-3), "ms_per_frame": ms, "counters": o["counters"]}
+        out[name] = rec
+        del frame
+    fr = synth.make_frame(H=8, W=8, n_class=6000, V=3, feat_hw=128, seed=5)
+    pc2 = torch.from_numpy(fr["pc2voxel_ind"]).long()
+    tk = (segment_mean(torch.from_numpy(fr["tar_smpl_vertice_smplcoord"]), pc2, 6000).float(),
+          segment_mean(torch.from_numpy(fr["blend_mtx"]), pc2, 6000))
+    frame, _ = frame_to_device(fr, tk, device)
+    v = fr["tar_smpl_vertice"]
+    lo, hi = v.min(0) - 0.05, v.max(0) + 0.05
+    ax = [torch.linspace(float(lo[i]), float(hi[i]), 256) for i in range(3)]
+    pts = torch.stack(torch.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3).to(device).contiguous()
+    ops.query_density(frame, pts)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(2):
+        alpha, mask = ops.query_density(frame, pts)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    out["c5_grid256_6000tok"] = {"points": pts.shape[0], "inside_radius": int(mask.sum().item()), "ms": ms,
+                                 "grid_points_per_s": pts.shape[0] / (ms * 1e-3),
+                                 "evaluated_points_per_s": int(mask.sum().item()) / (ms * 1e-3)}
+    return out
 
 
 def main():
@@ -176,9 +352,11 @@ def main():
     ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core GEMM path")
     ap.add_argument("--plain-maps", action="store_true",
                     help="round-1 path: plain channel-last 384-channel maps (no pre-map GEMM, alpha_res_0 per point)")
-    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU sample")
+    ap.add_argument("--cpu-rays", type=int, default=4096, help="rays in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-culled", action="store_true", help="skip the extra culled-mode measurement")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip torch_cuda_baseline, plugin and the other configs (quick kernel iteration)")
     ap.add_argument("--profile-run", action="store_true",
                     help="one untimed dense step and exit (for ncu; prints nothing)")
     args = ap.parse_args()
@@ -188,29 +366,19 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     N_rays = args.size * args.size
-    workload = (f"configs[1]: {args.size}x{args.size} render, {args.samples} samples/ray, {args.tokens} tokens, "
-                f"k=7, V={args.views}, dense (every sample evaluated)")
-    metric = f"rays/sec at {args.size}x{args.size}x{args.samples} samples"
+    workload, metric = workload_and_metric(args)
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return
-        val, cores, sec, sample = cpu_reference_leg(args, args.cpu_rays, args.steps, args.warmup)
-        line = {"impl": "reference", "metric": metric, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload},
-                "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
-                "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(reference_arm(args)), flush=True)
         return
 
     # ------------------------------------------------------------------ our arm
     import __graft_entry__ as entry
     entry.build()
-    from transhuman_b200 import ops
+    from transhuman_b200 import ops, sharding
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
@@ -223,16 +391,18 @@ def main():
     dev_rays = tuple(r.to(device) for r in host_rays)
     S = args.samples
     gathered = torch.empty((world, N_rays, 5), device=device) if world > 1 else None
-
     premapped = bool(frame.c.flags & ops.TH_FLAG_PREMAPPED)
 
-    def step(rays, mode=ops.TH_RENDER_DENSE):
+    def render(rays, mode=ops.TH_RENDER_DENSE):
         # one pass of the hot path from the encoder's output: the pre-map GEMM over the (V,384,H,W) maps
         # (alpha_res_0 / rgb_res_0 / rgb_res_1 once per map pixel instead of once per sample) is part of the step
         if premapped:
             ops.premap_features(frame.feat_nchw, frame.weights, out=frame.feat)
         out = ops.render_rays(frame, *rays, S, mode=mode)
-        img = torch.cat([out["rgb_map"], out["acc_map"][:, None], out["depth_map"][:, None]], dim=1)
+        return torch.cat([out["rgb_map"], out["acc_map"][:, None], out["depth_map"][:, None]], dim=1), out
+
+    def step(rays, mode=ops.TH_RENDER_DENSE):
+        img, out = render(rays, mode)
         if world > 1:  # the final image gather over NVLink
             dist.all_gather_into_tensor(gathered, img)
         return img, out
@@ -288,6 +458,13 @@ def main():
     ms_step = ms_t.item() / args.steps
     value = world * N_rays / (ms_step * 1e-3)
     assert torch.isfinite(img).all()
+    if world > 1:
+        # the gathered block of every rank must be that rank's own image (checksum of checksums)
+        sums = gathered.double().sum(dim=(1, 2))
+        mine = torch.zeros(world, dtype=torch.float64, device=device)
+        mine[rank] = img.double().sum()
+        dist.all_reduce(mine)
+        assert torch.equal(sums, mine), "all_gather: a gathered view differs from the image its rank rendered"
 
     # ---- end to end: pinned host rays in, image out, every step
     pinned_out = torch.empty((N_rays, 5)).pin_memory()
@@ -300,6 +477,30 @@ def main():
     ms_e2e = timed(e2e_step, args.steps, 1)
     h2d = sum(r.numel() * 4 for r in host_rays)
     d2h = pinned_out.numel() * 4
+
+    # ---- strong scaling: ONE view sharded over the ranks as interleaved 16x16 tiles + all_gather of the image
+    strong = None
+    if world > 1:
+        fr0, _ = synthetic_frame(args, 0, with_maps=False)                      # every rank renders tiles of view 0
+        view0 = tuple(torch.from_numpy(fr0[k]) for k in ("ray_o", "ray_d", "near", "far"))
+        idx = sharding.tile_interleaved_ray_indices(args.size, args.size, rank, world).to(device)
+        my_rays = tuple(r.to(device)[idx].contiguous() for r in view0)
+
+        def strong_step():
+            im, _ = render(my_rays)
+            return sharding.gather_rays(im, idx, N_rays)
+
+        ms_strong = timed(strong_step, args.steps, 2)
+        full = strong_step()
+        ref_img, _ = render(tuple(r.to(device) for r in view0))
+        strong = {"rays_per_s": N_rays / (ms_strong * 1e-3), "ms_per_step": ms_strong, "n_gpus": world,
+                  "sharding": "one 512x512 view, interleaved 16x16-pixel tiles round robin over ranks, "
+                              "all_gather of (rays/N, 5) per rank",
+                  "equals_unsharded_image": bool(torch.equal(full, ref_img)),
+                  "rays_per_rank": int(idx.numel()),
+                  "limit": "per-rank work = rays/N x 64 points = %.1f chunks of 284,160 points: the last chunk is a "
+                           "partial wave, and the pre-map GEMM + token state are replicated per rank"
+                           % (idx.numel() * S / 284160.0)}
 
     # ---- roofline of the dominant kernel family (the GEMM layers)
     peaks = measured_peaks()
@@ -315,8 +516,11 @@ def main():
     chain = os.environ.get("TH_CHAIN", "1") != "0" and not args.simt and args.views <= 3
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        traffic = tj.get("chain_dram_bytes_per_launch") if chain else tj.get("gemm_dram_bytes_per_launch")
-        l2_bytes = tj.get("chain_l2_bytes_per_launch") if chain else None
+        key = "chain_premapped" if (chain and premapped) else "chain" if chain else "gemm"
+        traffic = tj.get(key + "_dram_bytes_per_launch")
+        l2_bytes = tj.get(key + "_l2_bytes_per_launch") if chain else None
+    executed = 6 * executed_macs_per_point(args.views, premapped) * P_step / (gemm_ms_step * 1e-3) / 1e12 \
+        if (gemm_ms_step > 0 and not args.simt) else 0.0
     # the split scheme issues 3 fp16 tensor products per algorithmic MAC: its ceiling is 1/3 of the fp16 rate
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
@@ -328,17 +532,16 @@ def main():
                 "flops_per_point": flops_per_point(args.views),
                 "tensor_products_per_mac": 1 if args.simt else 3,
                 # what the tensor pipe really executes: folded layers, 3 fp16 products per MAC
-                "executed_tensor_tflops": (0.0 if args.simt or gemm_ms_step <= 0 else
-                                           6 * executed_macs_per_point(args.views, premapped) * P_step / (gemm_ms_step * 1e-3) / 1e12),
-                "issued_tensor_frac": (achieved / peaks["bf16_tflops"] if args.simt or gemm_ms_step <= 0 else
-                                       6 * executed_macs_per_point(args.views, premapped) * P_step / (gemm_ms_step * 1e-3) / 1e12
-                                       / peaks["bf16_tflops"]),
+                "executed_tensor_tflops": executed,
+                "issued_tensor_frac": (achieved if args.simt else executed) / peaks["bf16_tflops"],
                 # ncu: bytes through L2 per launch; live rate = that / the launch's live duration
                 # (practical L2 cap ~6300 B/clk)
                 "l2_bytes_per_launch": l2_bytes,
                 "l2_tbs_live": (l2_bytes * (gemm_launches // args.steps) / (gemm_ms_step * 1e-3) / 1e12
                                 if l2_bytes and gemm_ms_step > 0 else None),
-                "binding": "job-pipeline latency (epilogue ~ MMA time per job; the attention mix, 768 KB per unit and CTA, runs at the ~20 B/clk of SM<->L2 bandwidth the operand stream leaves it); L2->SM at ~80 % of its practical cap" if chain else "HBM (K=256 layers) / tensor (K>=512)",
+                "binding": ("chip-level L2 throughput (operand stream ~85 % of the ~6300 B/clk cap) together with the "
+                            "job pipeline's attention-mix bubble; tensor pipe ~60 % active" if chain
+                            else "HBM (K=256 layers) / tensor (K>=512)"),
                 "hbm_algorithmic_gbs": BYTES_PER_RAY * N_rays / (ms_step * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
     breakdown = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
@@ -354,18 +557,40 @@ def main():
                            "points_in_radius": oc["counters"][0], "rays_surviving": oc["counters"][1],
                            "point_fraction": oc["counters"][0] / P_step,
                            "ms_by_category": {k: round(v[0], 3) for k, v in prof_c.items()}}
+    if strong is not None:
+        extra["strong"] = strong
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
-            val, cores, sec, sample = cpu_reference_leg(args, args.cpu_rays, 1, 0)
-            cpu = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+        if world == 1 and not args.no_extras:
+            ours_img, _ = render(dev_rays)
+            ours_img = ours_img.clone()
+            if reference_available():
+                try:
+                    extra["torch_cuda_baseline"] = torch_cuda_baseline(args, device, ours_img)
+                except Exception as e:  # noqa: BLE001  (a baseline must never take the bench line down)
+                    extra["torch_cuda_baseline"] = {"error": repr(e)[:300]}
+            else:
+                extra["torch_cuda_baseline"] = {"unavailable": "reference tree not present (baseline/_ref)"}
+            try:
+                from tools import bench_plugin
+                extra["plugin"] = bench_plugin.run(device)
+            except Exception as e:  # noqa: BLE001
+                extra["plugin"] = {"error": repr(e)[:300]}
+            try:
+                extra["configs"] = other_configs(args, device)
+            except Exception as e:  # noqa: BLE001
+                extra["configs"] = {"error": repr(e)[:300]}
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_subprocess(args)
         line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "l2": "inputs larger than L2 (1.2 GB feature maps per frame)",
+                "config": {"workload": workload},
+                "detail": {"l2": "inputs larger than L2 (1.2 GB feature maps per frame)",
                            "sharding": "one 512x512 target view per rank, NCCL all_gather of the images",
-                           "mlp": "fp32 CUDA cores" if args.simt else "tcgen05 fp16x3 split, fp32 accumulate" + (", layer-chained" if chain else "")
+                           "mlp": "fp32 CUDA cores" if args.simt else "tcgen05 fp16x3 split, fp32 accumulate"
+                                  + (", layer-chained" if chain else "")
                                   + (", pre-mapped feature maps (pre-map GEMM inside the step)" if premapped else "")},
                 "clocks": clk,
                 "e2e": {"value": world * N_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,

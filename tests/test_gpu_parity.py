@@ -408,6 +408,35 @@ def test_empty_and_ragged_inputs(small):
     assert torch.equal(full["depth_map"][37:166], part["depth_map"])
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_tile_sharded_render_equals_unsharded(small_pre, small, world):
+    """one view sharded as interleaved 16x16 (here 4x4) pixel tiles over `world` ranks -- each shard
+    rendered on its own stream, gathered with sharding.gather_rays -- is bit-identical to the unsharded image
+    (rays are independent; a ray's result does not depend on which rays share its chunk)."""
+    from transhuman_b200 import sharding
+    fr, tf, tokens, frame, rays = small
+    S = 16
+    full = ops.render_rays(small_pre, *rays, S, mode=ops.TH_RENDER_DENSE)
+    want = torch.cat([full["rgb_map"], full["acc_map"][:, None], full["depth_map"][:, None]], dim=1)
+    img = torch.zeros_like(want)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    parts = []
+    for r in range(world):
+        idx = sharding.tile_interleaved_ray_indices(fr["H"], fr["W"], r, world, tile=4).to(DEV)
+        with torch.cuda.stream(streams[r]):
+            streams[r].wait_stream(torch.cuda.current_stream())
+            # one workspace per concurrent stream: the library is re-entrant across distinct streams + workspaces
+            ops._workspaces.clear()
+            o = ops.render_rays(small_pre, *(x[idx].contiguous() for x in rays), S, mode=ops.TH_RENDER_DENSE)
+            keep_ws = ops._workspaces.copy()
+            parts.append((idx, torch.cat([o["rgb_map"], o["acc_map"][:, None], o["depth_map"][:, None]], dim=1), keep_ws))
+    torch.cuda.synchronize()
+    for idx, loc, _ in parts:
+        img = img + sharding.gather_rays(loc, idx, want.shape[0])
+    assert torch.equal(img, want)
+    ops._workspaces.clear()
+
+
 def test_all_rays_culled(small):
     fr, tf, tokens, frame, rays = small
     o, d, n, f = rays

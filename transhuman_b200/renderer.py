@@ -92,6 +92,11 @@ class Renderer:
         self._weights = None
         self._weights_key = None
         self.last_counters = None
+        # set `profile = True` to have every prologue stage bracketed by CUDA events; `last_prologue_ms` then
+        # holds {stage: milliseconds} of the last prepare_frame (bench.py's `plugin` record)
+        self.profile = False
+        self.last_prologue_ms = {}
+        self._stage_events = []
 
     # ---- prologue (torch; out of scope of the CUDA path) ---------------------------------
     def normalize_PE(self, PE):
@@ -133,28 +138,54 @@ class Renderer:
         """Call after loading a new checkpoint into ``net``."""
         self._weights = None
 
+    def _stage(self, name):
+        """Marks the start of a prologue stage (CUDA event on the current stream when profiling)."""
+        if self.profile:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._stage_events.append((name, e))
+
+    def _stages_done(self):
+        if not self.profile:
+            return
+        self._stage("end")
+        torch.cuda.synchronize()
+        ms = {}
+        for (name, e0), (_, e1) in zip(self._stage_events[:-1], self._stage_events[1:]):
+            ms[name] = ms.get(name, 0.0) + e0.elapsed_time(e1)
+        self.last_prologue_ms = ms
+        self._stage_events = []
+
     def prepare_frame(self, batch) -> ops.Frame:
         """encoder -> paint -> group -> ViT -> tokens (if_clight_renderer.py:531-547)."""
         assert int(getattr(self.cfg, 'time_steps', 1)) == 1
         dev = batch['ray_o'].device
+        self._stage_events = []
+        self._stage("pack_weights")
         images = batch['input_imgs'][0].reshape(-1, *batch['input_imgs'][0].shape[2:])
+        weights = self._packed_weights(images.shape[0], dev)
+        self._stage("encoder")
         holder_map, holder_scale, pixel_map, pixel_scale = self.net.encoder(images)
         V = pixel_map.shape[0]
+        self._stage("paint")
         painted = self._paint(batch, holder_map, holder_scale)                       # (V, 6890, 192)
+        self._stage("group")
         pc2 = self.pc2voxel_ind.to(dev)
         grouped = segment_mean(painted.permute(1, 0, 2), pc2, self.num_class).permute(1, 0, 2).float()
         pe = self.voxel_PE_can.to(dev).unsqueeze(0).repeat(V, 1, 1)
-        holder = self.net.ViT(grouped.contiguous(), self.normalize_PE(pe), mask=None)
         tok_xyz = segment_mean(batch['tar_smpl_vertice_smplcoord'][0], pc2, self.num_class).float()
         tok_rot = segment_mean(batch['blend_mtx'][0], pc2, self.num_class)[:, :3, :3].float()
+        self._stage("vit")
+        holder = self.net.ViT(grouped.contiguous(), self.normalize_PE(pe), mask=None)
         image_shape = batch['input_imgs'][0].shape[-2:]
         fs = np.asarray(pixel_scale, dtype=np.float64)
         sc = fs / np.array(image_shape)
-        weights = self._packed_weights(V, dev)
         # pre-mapped maps (alpha_res_0 / rgb_res_0 / rgb_res_1 applied to the maps once per frame, tcgen05 GEMM over
         # the encoder's NCHW output) wherever the layer-chained schedule exists; plain channel-last maps otherwise
+        self._stage("premap")
         premapped = V <= 3
         feat = ops.premap_features(pixel_map, weights) if premapped else ops.nchw_to_nhwc(pixel_map)
+        self._stages_done()
         return ops.Frame(
             holder=holder, tok_xyz=tok_xyz, tok_rot=tok_rot, verts=batch['tar_smpl_vertice'][0],
             feat_nhwc=feat, premapped=premapped, cam_R=batch['input_R'][0].reshape(-1, 3, 3),
