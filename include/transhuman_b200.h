@@ -229,6 +229,41 @@ int th_nchw_to_nhwc(const float* src, float* dst, int32_t n, int32_t c, int32_t 
 int th_premap_features(const float* feat_nchw, const void* packed_weights, int32_t n_views, int32_t h, int32_t w,
                        float* out, void* stream);
 
+/* ---- the steps either side of the path --------------------------------------- */
+/* Token prologue, one kernel: paint_neural_human + can_body_grouping (if_clight_renderer.py:95-184, 415-427 with
+ * voxelization 356-371): project the SMPL vertices `verts` (n_verts,3; batch['input_smpl_vertice']) into every
+ * input view, bilinearly sample the encoder's `holder_feat_map` (V,192,H,W) NCHW at uv * (uv_scale) - 1
+ * (align_corners, border padding), zero the vertices that `vizmap` (V,n_verts; may be NULL = all visible) marks
+ * invisible, and mean-pool each k-means cluster -> tokens (V,n_tok,192).  Clusters in CSR form: the members of
+ * cluster c are cluster_members[cluster_start[c] .. cluster_start[c+1]) in the order of the reference's
+ * dict_voxel2pc_ind[c]; the mean uses torch-CPU's summation order (csrc/prologue.cu).  `painted` (V,n_verts,192)
+ * optionally receives the per-vertex features (= big_holder). */
+int th_paint_group(const float* holder_map, int32_t n_views, int32_t h, int32_t w, float uv_scale_x, float uv_scale_y,
+                   const float* verts, int32_t n_verts, const float* cam_R, const float* cam_T, const float* cam_K,
+                   const uint8_t* vizmap, const int32_t* cluster_start, const int32_t* cluster_members, int32_t n_tok,
+                   float* painted, float* tokens, void* stream);
+/* Renderer.voxelization (if_clight_renderer.py:356-371) of a per-vertex quantity x (n_verts, C), fp32 (is_f64 = 0)
+ * or fp64 (blend_mtx, 543-544): out (n_tok, C) of the same type, bit-equal to torch-CPU's `x[idx].mean(0)`:
+ * `outer_order` = 1 for wide rows (fp32 C >= 32, fp64 C >= 16: rows added sequentially with a 16-row cascade),
+ * 0 for narrow rows such as (n,3) coordinates (four interleaved partial sums). */
+int th_group_mean(const void* x, int32_t is_f64, int32_t n_cols, const int32_t* cluster_start,
+                  const int32_t* cluster_members, int32_t n_tok, int32_t outer_order, void* out, void* stream);
+/* Target-view rays + AABB near/far + compaction (get_rays, get_near_far and the `[mask_at_box]` selection of
+ * sample_ray_grid's test split, if_nerf_data_utils.py:11-30, 65-97, 190-199).  K_inv (3,3) = inverse intrinsics,
+ * R (3,3), T (3), bounds (2,3) or NULL (rays only), all DEVICE fp32.  Dense outputs ray_o, ray_d (H*W,3), near,
+ * far (H*W), mask_at_box (H*W); compacted outputs (optional, all four or none) hold the rays with mask_at_box set,
+ * in pixel order, and *count_dev (DEVICE int64) their number.  near/far are evaluated in float64 like the
+ * reference.  workspace >= th_generate_rays_workspace_bytes(H*W). */
+size_t th_generate_rays_workspace_bytes(int64_t n_pixels);
+/* get_near_far alone (if_nerf_data_utils.py:65-97) on caller-supplied rays: float64 arithmetic on the float32 rays,
+ * bit-equal to the reference.  ray_d is clamped IN PLACE where |d| < 1e-5, like the reference does (71). */
+int th_near_far(const float* ray_o, float* ray_d, int64_t n_rays, const float* bounds, float* near_, float* far_,
+                uint8_t* mask_at_box, void* stream);
+int th_generate_rays(int32_t h, int32_t w, const float* K_inv, const float* R, const float* T, const float* bounds,
+                     float* ray_o, float* ray_d, float* near_, float* far_, uint8_t* mask_at_box, float* ray_o_c,
+                     float* ray_d_c, float* near_c, float* far_c, int64_t* count_dev, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* Optional device-time profile: between start and stop every kernel launch is
  * bracketed by CUDA events on its stream; stop synchronises the device and
  * returns, per category, the summed elapsed milliseconds and launch counts.

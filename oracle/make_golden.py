@@ -98,6 +98,9 @@ def build_reference(frame: dict, S: int, device: str = "cpu", knn=None, fake_pro
                                            rasterize=True), device=device)
     tf = orc.to_torch_frame(frame)
     torch.manual_seed(0)
+    # Network.__init__ leaves cfg.img_feat_size = 384 behind (cross_transformer.py:123), which would size the NEXT
+    # encoder's reduction_layer for 512 channels (encoder.py:85): restore the YAML value before every construction
+    ns.cfg.img_feat_size = 256
     net = ns.cross_transformer.Network()
     sd = net.state_dict()
     for name, arr in tf["weights"].items():
@@ -199,8 +202,55 @@ def make_case(name: str, spec: dict) -> dict:
     return out
 
 
+def make_prologue_case() -> dict:
+    """Token prologue and ray generation (8f-4) through the reference's own functions:
+    ``paint_neural_human`` + ``can_body_grouping`` on a synthetic holder map with random visibility, and
+    ``get_rays`` / ``get_near_far`` of lib/utils/if_nerf/if_nerf_data_utils.py for a small target camera."""
+    import importlib
+    kw = dict(H=8, W=8, n_class=100, V=2, feat_hw=24, seed=9)
+    frame = synth.make_frame(**kw)
+    ns, net, renderer, batch = build_reference(frame, 8)
+    g = torch.Generator().manual_seed(3)
+    viz = torch.rand((1, 2, synth.N_VERTS), generator=g) > 0.3
+    batch["input_vizmaps"] = [viz]
+    tf = orc.to_torch_frame(frame)
+    hm = tf["pixel_feat_map"][:, :192].contiguous()
+    sc = np.array([24, 24])
+    sc = sc / (sc - 1) * 2.0
+    with torch.no_grad():
+        _, big = renderer.paint_neural_human(batch, 0, hm, sc)
+        grouped = renderer.can_body_grouping(big)
+        tok_xyz = renderer.voxelization(renderer.dict_voxel2pc_ind, batch["tar_smpl_vertice_smplcoord"][0])
+        tok_blend = renderer.voxelization(renderer.dict_voxel2pc_ind, batch["blend_mtx"][0])
+    du = importlib.import_module("lib.utils.if_nerf.if_nerf_data_utils")
+    Hc = 24
+    K = frame["target_K"].copy()
+    K[0, 0] = K[1, 1] = 30.0
+    K[0, 2] = K[1, 2] = Hc / 2
+    R, T = frame["target_R"], frame["target_T"]
+    v = frame["tar_smpl_vertice"]
+    bounds = np.stack([v.min(0) - 0.05, v.max(0) + 0.05]).astype(np.float32)
+    ray_o, ray_d = du.get_rays(Hc, Hc, K, R, T)
+    ray_o = ray_o.reshape(-1, 3).astype(np.float32)
+    ray_d = ray_d.reshape(-1, 3).astype(np.float32)
+    near, far, mask_at_box = du.get_near_far(bounds, ray_o, ray_d)        # clamps ray_d in place
+    return {
+        "frame_kwargs": np.array(repr(kw)), "viz": np.packbits(viz[0].numpy()),
+        "painted_sub": big[:, :256].numpy(), "grouped": grouped.numpy(),
+        "tok_xyz": tok_xyz.numpy(), "tok_blend": tok_blend.numpy(),
+        "cam_H": np.int32(Hc), "cam_K": K, "cam_R": R, "cam_T": T, "bounds": bounds,
+        "ray_o": ray_o, "ray_d": ray_d, "near": near.astype(np.float32), "far": far.astype(np.float32),
+        "mask_at_box": np.packbits(mask_at_box),
+    }
+
+
 def main(names=None):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if not names or "prologue_v2_100" in names:
+        out = make_prologue_case()
+        path = os.path.join(GOLDEN_DIR, "prologue_v2_100.npz")
+        np.savez_compressed(path, **out)
+        print(f"prologue_v2_100: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
     for name, spec in CASES.items():
         if names and name not in names:
             continue

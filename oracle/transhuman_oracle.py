@@ -166,6 +166,81 @@ def voxelization(pc2voxel: torch.Tensor, x: torch.Tensor, n_class: int) -> torch
     return torch.stack(out)
 
 
+def voxelization_lists(lists, x: torch.Tensor) -> torch.Tensor:
+    """``Renderer.voxelization`` (356-371) with the cluster member lists as the reference holds them
+    (``dict_voxel2pc_ind.values()``)."""
+    return torch.stack([x[torch.as_tensor(l, dtype=torch.int64)].mean(0) for l in lists])
+
+
+def paint_neural_human(smpl_vertice, input_R, input_T, input_K, holder_feat_map, image_shape, vizmap=None):
+    """``Renderer.paint_neural_human`` (if_clight_renderer.py:95-184, t = 0, cfg.rasterize): vertices (6890,3) world,
+    cameras (V,3,3)/(V,3,1)/(V,3,3), holder map (V,192,H,W), vizmap (V,6890) bool or None -> big_holder
+    (V,6890,192): bilinear samples at the projected vertices, zero where invisible."""
+    vertice_rot = torch.matmul(input_R[:, None], smpl_vertice[None].unsqueeze(-1))[..., 0]      # 121
+    vertice = vertice_rot + input_T[:, None, :3, 0]                                             # 122
+    vertice = torch.matmul(input_K[:, None], vertice.unsqueeze(-1))[..., 0]                     # 123
+    uv = vertice[:, :, :2] / vertice[:, :, 2:]                                                  # 124
+    latent = sample_from_feature_map(holder_feat_map, feat_scale_for(holder_feat_map), tuple(image_shape), uv)
+    latent = latent.permute(0, 2, 1)                                                            # 167-171
+    big = torch.zeros_like(latent)                                                              # 179
+    if vizmap is None:
+        return latent.clone()
+    big[vizmap.bool()] = latent[vizmap.bool()]                                                  # 180
+    return big
+
+
+def can_body_grouping(lists, all_holders):
+    """``Renderer.can_body_grouping`` (415-427): per view, per cluster mean of the painted vertices."""
+    return torch.stack([voxelization_lists(lists, h) for h in all_holders])
+
+
+# --------------------------------------------------------------------------
+# 8f-4  rays of the target camera and their AABB near / far (numpy, like the reference's dataset code:
+#       lib/utils/if_nerf/if_nerf_data_utils.py:11-30, 65-97 and the test split of sample_ray_grid, 190-199)
+# --------------------------------------------------------------------------
+def get_rays_np(H, W, K, R, T):
+    rays_o = -np.dot(R.T, T).ravel()                                                            # 14
+    i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32), indexing='xy')
+    xy1 = np.stack([i, j, np.ones_like(i)], axis=2)
+    pixel_camera = np.dot(xy1, np.linalg.inv(K).T)                                              # 25
+    pixel_world = np.dot(pixel_camera - T.ravel(), R)                                           # 26
+    rays_d = pixel_world - rays_o[None, None]
+    rays_o = np.broadcast_to(rays_o, rays_d.shape)
+    return rays_o, rays_d
+
+
+def get_near_far_np(bounds, ray_o, ray_d):
+    """-> near, far (float64, rays inside the box only), mask_at_box; CLAMPS ray_d in place like the reference (71)."""
+    bounds = bounds + np.array([-0.01, 0.01])[:, None]                                          # 67
+    nominator = bounds[None] - ray_o[:, None]
+    ray_d[np.abs(ray_d) < 1e-5] = 1e-5                                                          # 71
+    d_intersect = (nominator / ray_d[:, None]).reshape(-1, 6)
+    p_intersect = d_intersect[..., None] * ray_d[:, None] + ray_o[:, None]
+    min_x, min_y, min_z, max_x, max_y, max_z = bounds.ravel()
+    eps = 1e-6
+    p_mask_at_box = (p_intersect[..., 0] >= (min_x - eps)) * (p_intersect[..., 0] <= (max_x + eps)) * \
+                    (p_intersect[..., 1] >= (min_y - eps)) * (p_intersect[..., 1] <= (max_y + eps)) * \
+                    (p_intersect[..., 2] >= (min_z - eps)) * (p_intersect[..., 2] <= (max_z + eps))
+    mask_at_box = p_mask_at_box.sum(-1) == 2                                                    # 86
+    p_intervals = p_intersect[mask_at_box][p_mask_at_box[mask_at_box]].reshape(-1, 2, 3)
+    ray_o = ray_o[mask_at_box]
+    ray_d = ray_d[mask_at_box]
+    norm_ray = np.linalg.norm(ray_d, axis=1)
+    d0 = np.linalg.norm(p_intervals[:, 0] - ray_o, axis=1) / norm_ray
+    d1 = np.linalg.norm(p_intervals[:, 1] - ray_o, axis=1) / norm_ray
+    return np.minimum(d0, d1), np.maximum(d0, d1), mask_at_box
+
+
+def test_split_rays(H, W, K, R, T, bounds):
+    """The test split of ``sample_ray_grid`` (190-199) without the image: float32 rays, near / far, mask."""
+    ray_o, ray_d = get_rays_np(H, W, K, R, T)
+    ray_o = ray_o.reshape(-1, 3).astype(np.float32)
+    ray_d = ray_d.reshape(-1, 3).astype(np.float32)
+    near, far, mask_at_box = get_near_far_np(bounds, ray_o, ray_d)
+    return {"ray_o_all": ray_o, "ray_d_all": ray_d, "near": near.astype(np.float32), "far": far.astype(np.float32),
+            "mask_at_box": mask_at_box, "ray_o": ray_o[mask_at_box], "ray_d": ray_d[mask_at_box]}
+
+
 # --------------------------------------------------------------------------
 # a5  pixel-aligned feature gather (if_clight_renderer.py:186-208, 210-269)
 # --------------------------------------------------------------------------

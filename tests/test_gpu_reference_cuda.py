@@ -74,6 +74,15 @@ def test_full_frame_c2_dense_matches_reference_cuda():
     frame, rays = frame_to_device(fr, tokens, DEV)
     got = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_DENSE, want_raw=True)
     raw_ref = box["raw"].reshape(-1, S, 4).cpu()
+    # diagnostics first: where do the two raws differ most, and do the pixels follow?
+    dr = (got["raw"].cpu() - raw_ref).abs()
+    per_ray = dr.amax(dim=(1, 2))
+    e_rgb = (got["rgb_map"].cpu() - ref["rgb_map"][0].cpu()).abs().amax(dim=1)
+    worst = torch.topk(per_ray, 8).indices
+    for r in worst.tolist():
+        s_ = int(dr[r].amax(dim=1).argmax())
+        print(f"[full frame] ray {r}: raw diff {float(per_ray[r]):.3e} at sample {s_} "
+              f"(ours {got['raw'][r, s_].cpu().tolist()} ref {raw_ref[r, s_].tolist()}), rgb diff {float(e_rgb[r]):.3e}")
     n_edge = assert_maps_close(got, {k: ref[k].cpu() for k in ("rgb_map", "acc_map", "depth_map")}, raw_ref,
                                box["z_vals"].reshape(-1, S).cpu(), tf["ray_d"], S, float(fr["far"].max()),
                                "full C2 frame vs reference torch-CUDA (TF32 off)")

@@ -86,3 +86,29 @@ def test_raw2outputs_masked_points_are_transparent():
     rgb, acc, w, depth = orc.raw2outputs(raw, z, d)
     assert torch.all(w[:, :4] == 0) and torch.all(w[:, 5:7] == 0)
     assert torch.allclose(acc, w[:, 4])
+
+
+def test_prologue_golden_matches_oracle():
+    """tests/golden/prologue_v2_100.npz (the reference's own paint / grouping / ray functions) against the oracle
+    restatements -- the fixture that carries SURVEY 8f-1 / 8f-4 to the GPU box."""
+    import ast
+    import os
+    from tests.conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "prologue_v2_100.npz"))
+    kw = ast.literal_eval(str(z["frame_kwargs"]))
+    fr = synth.make_frame(**kw)
+    tf = orc.to_torch_frame(fr)
+    viz = torch.from_numpy(np.unpackbits(z["viz"])[: 2 * synth.N_VERTS].reshape(2, -1).astype(bool))
+    hm = tf["pixel_feat_map"][:, :192].contiguous()
+    big = orc.paint_neural_human(tf["tar_smpl_vertice"], tf["input_R"], tf["input_T"], tf["input_K"], hm, (24, 24), viz)
+    assert np.array_equal(big[:, :256].numpy(), z["painted_sub"])
+    pc2 = tf["pc2voxel_ind"].long()
+    lists = [torch.nonzero(pc2 == c)[:, 0] for c in range(kw["n_class"])]
+    assert np.array_equal(orc.can_body_grouping(lists, big).numpy(), z["grouped"])
+    assert np.array_equal(orc.voxelization(pc2, tf["tar_smpl_vertice_smplcoord"], 100).numpy(), z["tok_xyz"])
+    assert np.array_equal(orc.voxelization(pc2, tf["blend_mtx"], 100).numpy(), z["tok_blend"])
+    H = int(z["cam_H"])
+    r = orc.test_split_rays(H, H, z["cam_K"], z["cam_R"], z["cam_T"], z["bounds"])
+    m = np.unpackbits(z["mask_at_box"])[: H * H].astype(bool)
+    assert np.array_equal(r["mask_at_box"], m) and np.array_equal(r["near"], z["near"]) and np.array_equal(r["far"], z["far"])
+    assert np.array_equal(r["ray_d_all"], z["ray_d"]) and np.array_equal(r["ray_o_all"], z["ray_o"])

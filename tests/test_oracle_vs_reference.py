@@ -81,3 +81,36 @@ def test_voxelization_on_real_kmeans_dict(ref):
         c = synth.segment_mean(frame["blend_mtx"], pc2voxel, n)
         bm = renderer.voxelization(v2pc, torch.from_numpy(frame["blend_mtx"]))
         assert np.abs(c - bm.numpy()).max() < 1e-12
+
+
+def test_prologue_paint_group_and_rays_bit_equal(ref):
+    """SURVEY 8f-1 / 8f-4 restatements against the reference's own functions, bit for bit."""
+    import importlib
+    frame, ns, net, renderer, batch = ref
+    tf = orc.to_torch_frame(frame)
+    g = torch.Generator().manual_seed(3)
+    viz = torch.rand((1, 3, synth.N_VERTS), generator=g) > 0.3
+    b2 = dict(batch)
+    b2["input_vizmaps"] = [viz]
+    hm = tf["pixel_feat_map"][:, :192].contiguous()
+    hw = frame["feat_hw"]
+    sc = np.array([hw, hw])
+    sc = sc / (sc - 1) * 2.0
+    with torch.no_grad():
+        _, big = renderer.paint_neural_human(b2, 0, hm, sc)
+        grouped = renderer.can_body_grouping(big)
+    mine = orc.paint_neural_human(tf["tar_smpl_vertice"], tf["input_R"], tf["input_T"], tf["input_K"], hm, (hw, hw), viz[0])
+    assert torch.equal(mine, big)
+    lists = list(renderer.dict_voxel2pc_ind.values())
+    assert torch.equal(orc.can_body_grouping(lists, mine), grouped)
+    du = importlib.import_module("lib.utils.if_nerf.if_nerf_data_utils")
+    K, R, T = frame["target_K"], frame["target_R"], frame["target_T"]
+    ro, rd = du.get_rays(20, 20, K, R, T)
+    ro2, rd2 = orc.get_rays_np(20, 20, K, R, T)
+    assert np.array_equal(ro, ro2) and np.array_equal(rd, rd2)
+    v = frame["tar_smpl_vertice"]
+    bounds = np.stack([v.min(0) - 0.05, v.max(0) + 0.05]).astype(np.float32)
+    f32 = lambda a: a.reshape(-1, 3).astype(np.float32).copy()
+    a = du.get_near_far(bounds, f32(ro), f32(rd))
+    b = orc.get_near_far_np(bounds, f32(ro), f32(rd))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and 0 < a[2].sum() < a[2].size

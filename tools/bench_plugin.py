@@ -45,6 +45,7 @@ def _network(fr, device):
             kmeans={n: synth.cluster_body(synth.make_body(0), n) for n in (300,)})
         ns = ref_shim.load_reference(orc.knn_points, cwd, opts=dict(perturb=0, rasterize=True), device="cuda")
         torch.manual_seed(0)
+        ns.cfg.img_feat_size = 256      # Network.__init__ overwrites it (cross_transformer.py:123); see make_golden.py
         net = ns.cross_transformer.Network()
         sd = net.state_dict()
         for name, arr in fr["weights"].items():

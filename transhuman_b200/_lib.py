@@ -88,6 +88,13 @@ SIGNATURES = {
     "th_integrate": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp]),
     "th_nchw_to_nhwc": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "th_premap_features": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp, _fp]),
+    "th_paint_group": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _fp, C.c_int32, _fp, _fp, _fp,
+                                 _fp, _fp, _fp, C.c_int32, _fp, _fp, _fp]),
+    "th_group_mean": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
+    "th_near_far": (C.c_int, [_fp, _fp, C.c_int64, _fp, _fp, _fp, _fp, _fp]),
+    "th_generate_rays_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "th_generate_rays": (C.c_int, [C.c_int32, C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                                   _fp, _fp, C.c_size_t, _fp]),
     "th_debug_chain_program": (C.c_int64, [_fp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _fp, C.c_int64]),
 }
 

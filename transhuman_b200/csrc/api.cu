@@ -825,6 +825,55 @@ int th_premap_features(const float* feat_nchw, const void* packed_weights, int32
   return launch_premap(feat_nchw, static_cast<const unsigned char*>(packed_weights), hdr, out, n_views, h, w, st);
 }
 
+int th_paint_group(const float* holder_map, int32_t n_views, int32_t h, int32_t w, float uv_scale_x, float uv_scale_y,
+                   const float* verts, int32_t n_verts, const float* cam_R, const float* cam_T, const float* cam_K,
+                   const uint8_t* vizmap, const int32_t* cluster_start, const int32_t* cluster_members, int32_t n_tok,
+                   float* painted, float* tokens, void* stream) {
+  TH_CHECK_ARG(holder_map && verts && cam_R && cam_T && cam_K && cluster_start && cluster_members && tokens,
+               "null pointer");
+  TH_CHECK_ARG(n_views >= 1 && n_views <= 65535 && h >= 1 && w >= 1 && n_verts >= 1 && n_tok >= 1, "bad sizes");
+  return launch_paint_group(holder_map, n_views, h, w, uv_scale_x, uv_scale_y, verts, cam_R, cam_T, cam_K, vizmap,
+                            n_verts, cluster_start, cluster_members, n_tok, painted, tokens,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int th_group_mean(const void* x, int32_t is_f64, int32_t n_cols, const int32_t* cluster_start,
+                  const int32_t* cluster_members, int32_t n_tok, int32_t outer_order, void* out, void* stream) {
+  TH_CHECK_ARG(x && cluster_start && cluster_members && out, "null pointer");
+  TH_CHECK_ARG(n_cols >= 1 && n_tok >= 1, "bad sizes");
+  return launch_group_mean(x, is_f64, n_cols, cluster_start, cluster_members, n_tok, outer_order, out,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int th_near_far(const float* ray_o, float* ray_d, int64_t n_rays, const float* bounds, float* near_, float* far_,
+                uint8_t* mask_at_box, void* stream) {
+  TH_CHECK_ARG(ray_o && ray_d && bounds && near_ && far_ && mask_at_box && n_rays >= 0, "bad argument");
+  return launch_near_far(ray_o, ray_d, n_rays, bounds, near_, far_, mask_at_box, static_cast<cudaStream_t>(stream));
+}
+
+size_t th_generate_rays_workspace_bytes(int64_t n_pixels) {
+  return n_pixels > 0 ? generate_rays_workspace_bytes(n_pixels) : 256;
+}
+
+int th_generate_rays(int32_t h, int32_t w, const float* K_inv, const float* R, const float* T, const float* bounds,
+                     float* ray_o, float* ray_d, float* near_, float* far_, uint8_t* mask_at_box, float* ray_o_c,
+                     float* ray_d_c, float* near_c, float* far_c, int64_t* count_dev, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  TH_CHECK_ARG(h >= 1 && w >= 1 && K_inv && R && T && ray_o && ray_d, "bad argument");
+  if (bounds) TH_CHECK_ARG(near_ && far_ && mask_at_box, "bounds given: near / far / mask_at_box outputs are required");
+  const bool compact = ray_o_c || ray_d_c || near_c || far_c;
+  if (compact) {
+    TH_CHECK_ARG(bounds && ray_o_c && ray_d_c && near_c && far_c && count_dev, "compacted outputs: all four + count, with bounds");
+    if (!workspace || workspace_bytes < generate_rays_workspace_bytes((int64_t)h * w)) {
+      set_error("th_generate_rays: workspace %zu < %zu bytes", workspace_bytes,
+                generate_rays_workspace_bytes((int64_t)h * w));
+      return TH_EWORKSPACE;
+    }
+  }
+  return launch_generate_rays(h, w, K_inv, R, T, bounds, ray_o, ray_d, near_, far_, mask_at_box, compact ? ray_o_c : nullptr,
+                              ray_d_c, near_c, far_c, count_dev, workspace, static_cast<cudaStream_t>(stream));
+}
+
 int th_nchw_to_nhwc(const float* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w, void* stream) {
   TH_CHECK_ARG(src && dst && n >= 1 && c >= 1 && h >= 1 && w >= 1, "bad argument");
   return launch_nchw_to_nhwc(src, dst, n, c, h, w, static_cast<cudaStream_t>(stream));

@@ -1,5 +1,7 @@
 // Internal declarations shared by geometry.cu, mlp_simt.cu, mlp_tc.cu and api.cu.
 #pragma once
+#include <stddef.h>
+
 #include "common.cuh"
 
 namespace th {
@@ -67,6 +69,19 @@ int launch_integrate(const float* raw, const uint8_t* mask, const uint8_t* ray_a
                      float* acc, float* depth, cudaStream_t st);
 int launch_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, cudaStream_t st);
 
+// ---- prologue.cu -------------------------------------------------
+int launch_paint_group(const float* map, int V, int H, int W, float sx, float sy, const float* verts, const float* cam_R,
+                       const float* cam_T, const float* cam_K, const uint8_t* viz, int n_verts, const int32_t* start,
+                       const int32_t* members, int n_tok, float* painted, float* out, cudaStream_t st);
+int launch_group_mean(const void* x, int is_f64, int C, const int32_t* start, const int32_t* members, int n_tok, int outer,
+                      void* out, cudaStream_t st);
+int launch_near_far(const float* ray_o, float* ray_d, int64_t n, const float* bounds, float* near_, float* far_,
+                    uint8_t* mask, cudaStream_t st);
+size_t generate_rays_workspace_bytes(int64_t n);
+int launch_generate_rays(int H, int W, const float* Kinv, const float* R, const float* T, const float* bounds,
+                         float* ray_o, float* ray_d, float* near_, float* far_, uint8_t* mask, float* o_c, float* d_c,
+                         float* n_c, float* f_c, int64_t* count, void* workspace, cudaStream_t st);
+
 // ---- packed weights (api.cu writes, mlp_*.cu read) --------------------------------
 // Offsets (in floats) into the fp32 section of the blob.  Folded matrices are
 // built in float64 by th_pack_weights:
@@ -129,10 +144,14 @@ struct PackedHeader {
   float img_inv_scale[24];
   int32_t n_img, pad_;
 };
-inline float img_inv_scale_of(const PackedHeader& h, uint64_t off) {
+// DEVICE address of the 2^-e of the weight image at byte offset `off` (nullptr = unknown image, scale 1).  The scale
+// is per blob (it depends on the weights), so kernels read it from the blob itself; the host only needs the INDEX,
+// which -- like every offset in this header -- is a pure function of the view count (safe to cache across blobs).
+inline const float* img_inv_scale_ptr(const unsigned char* weights_dev, const PackedHeader& h, uint64_t off) {
   for (int i = 0; i < h.n_img && i < 24; ++i)
-    if (h.img_off[i] == off) return h.img_inv_scale[i];
-  return 1.0f;
+    if (h.img_off[i] == off)
+      return reinterpret_cast<const float*>(weights_dev + offsetof(PackedHeader, img_inv_scale)) + i;
+  return nullptr;
 }
 constexpr uint32_t PACK_MAGIC = 0x35574854u;
 
@@ -227,7 +246,8 @@ struct GemmArgs {
   int64_t M;
   int N;  // multiple of 128
   int relu;
-  float acc_scale;  // tensor-core path: the accumulator is multiplied by this before the bias (img_inv_scale_of); 0 = 1
+  const float* acc_scale;  // tensor-core path: DEVICE pointer to the 2^-e of the weight image (img_inv_scale_ptr);
+                           // the accumulator is multiplied by it before the bias; nullptr = 1
 };
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& a, const void* w_hi_lo, cudaStream_t st, int prof_cat = PROF_GEMM);

@@ -71,8 +71,8 @@ struct Job {
   const float* bias2;       // EPI_SCORES: bias of the kept key embed
   uint32_t out_off;         // EPI_IMG: destination inside the CTA's scratch
   int32_t nseg, nkb, N, relu, epi, tmem_col, wait_back, view;
-  float acc_scale;          // 2^-e of this job's weight image (PackedHeader::img_inv_scale): acc * scale + bias
-  float acc_scale2;         // EPI_SCORES: the scale of the kept key embeds' weight image
+  const float* acc_scale;   // DEVICE pointer to the 2^-e of this job's weight image (img_inv_scale_ptr): acc * scale + bias
+  const float* acc_scale2;  // EPI_SCORES: the scale of the kept key embeds' weight image
 };
 struct Program {
   // TMA descriptors: tile images as rows of 64 fp16 (128 B).  tm_a: box 256 rows (one 32 KB hi|lo
@@ -529,7 +529,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           const int ncol = N >> 1, cbeg = grp * ncol;
           const bool swap = (et & 1) != 0;
           const bool relu = jb.relu != 0;
-          const float2 sc2 = make_float2(jb.acc_scale, jb.acc_scale);
+          const float acc_s = __ldg(jb.acc_scale);
+          const float2 sc2 = make_float2(acc_s, acc_s);
           // 32 accumulator columns -> 2 x (hi sector, lo sector)
           auto emit = [&](const uint32_t (&v)[32], int c0) {
             unsigned char* kb_out = out + (size_t)(c0 >> 6) * TILE_IMG;
@@ -593,7 +594,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           // warps of a lane quadrant take 64 of the 128 key channels each and group 1 hands its
           // partial sums over through shared memory.
           float sc[TH_MAX_VIEWS];
-          const float s_kp = jb.acc_scale, s_ks = jb.acc_scale2;
+          const float s_kp = __ldg(jb.acc_scale), s_ks = __ldg(jb.acc_scale2);
 #pragma unroll
           for (int jv = 0; jv < TH_MAX_VIEWS; ++jv) sc[jv] = 0.f;
 #pragma unroll 1
@@ -660,6 +661,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         } else if (epi == EPI_ALPHA) {
           // alpha = relu(O) . alpha_fc + b (cross_transformer.py:324-328): O never leaves the SM
           float acc = 0.f;
+          const float acc_s = __ldg(jb.acc_scale);
 #pragma unroll 1
           for (int c0 = 0; c0 < 256; c0 += 32) {
             uint32_t v[32];
@@ -667,7 +669,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              acc = fmaf(fmaxf(fmaf(__uint_as_float(v[e]), jb.acc_scale, bias_s[c0 + e]), 0.f), __ldg(pg.afc_w + c0 + e), acc);
+              acc = fmaf(fmaxf(fmaf(__uint_as_float(v[e]), acc_s, bias_s[c0 + e]), 0.f), __ldg(pg.afc_w + c0 + e), acc);
           }
           alpha_reg = acc + __ldg(pg.afc_b);
           if (pt < pg.P) {
@@ -681,6 +683,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         } else if (epi == EPI_RGB) {
           // rgb = relu(T) rgb_fc^T + b (cross_transformer.py:349-351); raw = (rgb, alpha)
           float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+          const float acc_s = __ldg(jb.acc_scale);
 #pragma unroll 1
           for (int c0 = 0; c0 < 128; c0 += 32) {
             uint32_t v[32];
@@ -688,7 +691,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const float t = fmaxf(fmaf(__uint_as_float(v[e]), jb.acc_scale, bias_s[c0 + e]), 0.f);
+              const float t = fmaxf(fmaf(__uint_as_float(v[e]), acc_s, bias_s[c0 + e]), 0.f);
               o0 = fmaf(t, __ldg(pg.rgb_w + c0 + e), o0);
               o1 = fmaf(t, __ldg(pg.rgb_w + 128 + c0 + e), o1);
               o2 = fmaf(t, __ldg(pg.rgb_w + 256 + c0 + e), o2);
@@ -943,8 +946,12 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
   }
   Program& pg = B.pg;
   for (int j = 0; j < pg.njobs; ++j) {  // accumulator scales of the weight images (PackedHeader::img_inv_scale)
-    pg.job[j].acc_scale = img_inv_scale_of(h, (uint64_t)(pg.job[j].wimg - run.weights));
-    pg.job[j].acc_scale2 = img_inv_scale_of(h, h.h_k1);
+    pg.job[j].acc_scale = img_inv_scale_ptr(run.weights, h, (uint64_t)(pg.job[j].wimg - run.weights));
+    pg.job[j].acc_scale2 = img_inv_scale_ptr(run.weights, h, h.h_k1);
+    if (!pg.job[j].acc_scale || !pg.job[j].acc_scale2) {
+      set_error("mlp_forward_chain: job %d reads a weight image the blob header does not list", j);
+      return TH_EINVAL;
+    }
   }
   if (x_in_chunk) {
     // Without the X jobs the hand-set TMEM waits above no longer match the job parity: derive them.

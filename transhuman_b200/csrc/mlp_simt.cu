@@ -524,7 +524,7 @@ static int mlp_forward_tc(const MlpRun& run, const MlpBuffers& b, const PackedHe
     g.M = M;
     g.N = N;
     g.relu = relu;
-    g.acc_scale = img_inv_scale_of(h, w_img);
+    g.acc_scale = img_inv_scale_ptr(run.weights, h, w_img);
     return launch_gemm_tc(g, run.weights + w_img, st);
   };
   // image of a (V*Pp, C) activation: the slice of view v starts (v*Pp/128) row tiles in
@@ -558,7 +558,7 @@ static int mlp_forward_tc(const MlpRun& run, const MlpBuffers& b, const PackedHe
     g.M = Pp;
     g.N = 256;
     g.relu = 1;
-    g.acc_scale = img_inv_scale_of(h, h.h_fc3m);
+    g.acc_scale = img_inv_scale_ptr(run.weights, h, h.h_fc3m);
     if ((rc = launch_gemm_tc(g, run.weights + h.h_fc3m, st))) return rc;
   }
   if ((rc = run_heads(run, o, nullptr, alpha, h, false, st))) return rc;
@@ -586,7 +586,7 @@ static int mlp_forward_tc(const MlpRun& run, const MlpBuffers& b, const PackedHe
     g.M = Pp;
     g.N = 128;
     g.relu = 1;
-    g.acc_scale = img_inv_scale_of(h, h.h_t);
+    g.acc_scale = img_inv_scale_ptr(run.weights, h, h.h_t);
     if ((rc = launch_gemm_tc(g, run.weights + h.h_t, st))) return rc;
   }
   return run_heads(run, o, t, alpha, h, true, st);

@@ -111,7 +111,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < N; i += NUM_THREADS) s_bias[i] = a.g.bias ? a.g.bias[i] : 0.f;
-  const float acc_scale = a.g.acc_scale != 0.f ? a.g.acc_scale : 1.0f;  // 2^-e of the weight image
+  const float acc_scale = a.g.acc_scale ? __ldg(a.g.acc_scale) : 1.0f;  // 2^-e of the weight image (read from the blob)
   if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)TMEM_COLS)
@@ -484,7 +484,7 @@ int launch_premap(const float* src_nchw, const unsigned char* weights, const Pac
       g.M = HW;
       g.N = 256;
       g.relu = 0;
-      g.acc_scale = img_inv_scale_of(hdr, half ? hdr.h_preb : hdr.h_ar0);
+      g.acc_scale = img_inv_scale_ptr(weights, hdr, half ? hdr.h_preb : hdr.h_ar0);
       int rc = launch_gemm_tc(g, weights + (half ? hdr.h_preb : hdr.h_ar0), st, PROF_PREMAP);
       if (rc) return rc;
     }

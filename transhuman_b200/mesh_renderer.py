@@ -33,6 +33,8 @@ class Renderer(_BaseRenderer):
         try:  # if_mesh_renderer.py:98-109 (CPU, third party; out of scope of the CUDA path)
             import mcubes
             import trimesh
+            if not (getattr(mcubes, "__file__", None) and getattr(trimesh, "__file__", None)):
+                raise ImportError("mcubes / trimesh are placeholders")      # e.g. the test shim's stub modules
             voxel_size = np.array(self.cfg.voxel_size)
             vertices, triangles = mcubes.marching_cubes(cube, self.cfg.mesh_th)
             can_bounds = batch['can_bounds'][0].cpu().numpy()

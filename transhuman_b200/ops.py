@@ -18,6 +18,7 @@ from ._lib import (TH_FLAG_LAYERWISE, TH_FLAG_PREMAPPED, TH_FLAG_SIMT_MLP, TH_FL
 
 __all__ = ["PackedWeights", "Frame", "render_rays", "query_density", "sample_points", "cull_knn1", "cull_grid",
            "world2smpl", "view_embed", "pixel_gather", "knn_dparf", "mlp_raw", "integrate", "nchw_to_nhwc",
+           "premap_features", "ClusterIndex", "paint_group", "group_mean", "generate_rays", "near_far",
            "launch_count", "TH_RENDER_DENSE", "TH_RENDER_MASKED", "TH_RENDER_FAST"]
 
 
@@ -343,4 +344,125 @@ def premap_features(x, weights: PackedWeights, out=None):
     assert out.shape == (n, h, w, 512) and out.is_contiguous() and out.dtype == torch.float32
     _lib.check(lib.th_premap_features(_ptr(x), weights.blob.data_ptr(), n, h, w, _ptr(out), _stream()),
                "th_premap_features")
+    return out
+
+
+# ---- the steps either side of the path -------------------------------------------
+class ClusterIndex:
+    """The k-means vertex clusters in CSR form (``cluster_start (n_tok+1)``, ``cluster_members (n_verts)`` int32):
+    members of cluster c in the order of the reference's ``dict_voxel2pc_ind[c]``
+    (if_clight_renderer.py:55; ascending vertex ids when only ``pc2voxel_ind`` is known)."""
+
+    def __init__(self, pc2voxel_ind=None, dict_voxel2pc_ind=None, n_tok: int | None = None, device="cuda"):
+        if dict_voxel2pc_ind is not None:
+            keys = sorted(dict_voxel2pc_ind.keys())
+            assert [int(k) for k in keys] == list(range(len(keys))), "cluster ids must be exactly arange(n)"
+            lists = [np.asarray(dict_voxel2pc_ind[k], dtype=np.int64).reshape(-1) for k in keys]
+        else:
+            pc2 = np.asarray(pc2voxel_ind).reshape(-1).astype(np.int64)
+            n = int(pc2.max()) + 1 if n_tok is None else int(n_tok)
+            order = np.argsort(pc2, kind="stable")
+            counts = np.bincount(pc2, minlength=n)
+            lists = np.split(order, np.cumsum(counts)[:-1])
+        assert all(len(l) > 0 for l in lists), "empty cluster"
+        self.n_tok = len(lists)
+        self.n_verts = int(sum(len(l) for l in lists))
+        start = np.zeros(self.n_tok + 1, dtype=np.int32)
+        start[1:] = np.cumsum([len(l) for l in lists])
+        self.start_host, self.members_host = start, np.concatenate(lists).astype(np.int32)
+        self._dev = {}
+        self.to(device)
+
+    def to(self, device):
+        key = str(torch.device(device))
+        if key not in self._dev:
+            self._dev[key] = (torch.from_numpy(self.start_host).to(device), torch.from_numpy(self.members_host).to(device))
+        self.start, self.members = self._dev[key]
+        return self
+
+
+def paint_group(holder_map, uv_scale, verts, cam_R, cam_T, cam_K, vizmap, clusters: ClusterIndex, want_painted=False):
+    """8f-1: holder map (V,192,H,W) NCHW -> tokens (V,n_tok,192) (``th_paint_group``); ``vizmap`` (V,n_verts) bool
+    or None."""
+    lib = _lib.load()
+    hm = _f32(holder_map, "holder_map")
+    V, c, H, W = hm.shape
+    assert c == 192
+    verts = _f32(verts, "verts").view(-1, 3)
+    nv = verts.shape[0]
+    clusters.to(hm.device)
+    assert clusters.n_verts == nv
+    R, T, K = _f32(cam_R, "cam_R").view(V, 3, 3), _f32(cam_T, "cam_T").view(V, 3), _f32(cam_K, "cam_K").view(V, 3, 3)
+    viz = None if vizmap is None else vizmap.to(torch.uint8).contiguous().view(V, nv)
+    out = torch.empty((V, clusters.n_tok, 192), device=hm.device)
+    painted = torch.empty((V, nv, 192), device=hm.device) if want_painted else None
+    _lib.check(lib.th_paint_group(_ptr(hm), V, H, W, float(uv_scale[0]), float(uv_scale[1]), _ptr(verts), nv, _ptr(R),
+                                  _ptr(T), _ptr(K), _ptr(viz), _ptr(clusters.start), _ptr(clusters.members),
+                                  clusters.n_tok, _ptr(painted), _ptr(out), _stream()), "th_paint_group")
+    return (out, painted) if want_painted else out
+
+
+def group_mean(x, clusters: ClusterIndex, outer_order=None):
+    """``Renderer.voxelization`` of a per-vertex tensor (n_verts, ...), fp32 or fp64, bit-equal to torch-CPU's
+    ``x[idx].mean(0)`` (``th_group_mean``).  ``outer_order`` defaults to torch's choice for the row width."""
+    lib = _lib.load()
+    assert x.is_cuda and x.dtype in (torch.float32, torch.float64)
+    x = x.contiguous()
+    n = x.shape[0]
+    C_ = x.numel() // n
+    clusters.to(x.device)
+    assert clusters.n_verts == n
+    f64 = x.dtype == torch.float64
+    if outer_order is None:
+        outer_order = C_ >= (16 if f64 else 32)
+    out = torch.empty((clusters.n_tok,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    _lib.check(lib.th_group_mean(_ptr(x), 1 if f64 else 0, C_, _ptr(clusters.start), _ptr(clusters.members),
+                                 clusters.n_tok, 1 if outer_order else 0, _ptr(out), _stream()), "th_group_mean")
+    return out
+
+
+def near_far(ray_o, ray_d, bounds) -> dict:
+    """``get_near_far`` on given rays (``th_near_far``); returns near, far, mask_at_box and the clamped ray_d copy."""
+    lib = _lib.load()
+    ray_o = _f32(ray_o, "ray_o").view(-1, 3)
+    ray_d = _f32(ray_d, "ray_d").view(-1, 3).clone()
+    b = _f32(bounds, "bounds").view(2, 3)
+    n = ray_o.shape[0]
+    near, far = torch.empty((n,), device=ray_o.device), torch.empty((n,), device=ray_o.device)
+    mask = torch.empty((n,), dtype=torch.uint8, device=ray_o.device)
+    _lib.check(lib.th_near_far(_ptr(ray_o), _ptr(ray_d), n, _ptr(b), _ptr(near), _ptr(far), _ptr(mask), _stream()),
+               "th_near_far")
+    return {"near": near, "far": far, "mask_at_box": mask, "ray_d": ray_d}
+
+
+def generate_rays(H: int, W: int, K, R, T, bounds=None, compact: bool = True) -> dict:
+    """8f-4: ``get_rays`` + ``get_near_far`` + the ``[mask_at_box]`` selection for one target camera
+    (``th_generate_rays``).  K (3,3), R (3,3), T (3,) or (3,1), bounds (2,3): CUDA tensors.  Returns dense
+    ``ray_o, ray_d (H*W,3)`` and, with bounds, ``near, far, mask_at_box`` plus (``compact``) the rays inside the box
+    in pixel order -- one device->host read of their count."""
+    lib = _lib.load()
+    K = _f32(K, "K").view(3, 3)
+    dev = K.device
+    Kinv = torch.linalg.inv(K).contiguous()             # np.linalg.inv(K) in float32 (if_nerf_data_utils.py:23)
+    R, T = _f32(R, "R").view(3, 3), _f32(T, "T").view(3)
+    n = H * W
+    out = {"ray_o": torch.empty((n, 3), device=dev), "ray_d": torch.empty((n, 3), device=dev)}
+    b = near = far = mask = oc = dc = nc = fc = cnt = ws = None
+    if bounds is not None:
+        b = _f32(bounds, "bounds").view(2, 3)
+        near, far = torch.empty((n,), device=dev), torch.empty((n,), device=dev)
+        mask = torch.empty((n,), dtype=torch.uint8, device=dev)
+        if compact:
+            oc, dc = torch.empty((n, 3), device=dev), torch.empty((n, 3), device=dev)
+            nc, fc = torch.empty((n,), device=dev), torch.empty((n,), device=dev)
+            cnt = torch.zeros((1,), dtype=torch.int64, device=dev)
+            ws = torch.empty(lib.th_generate_rays_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    _lib.check(lib.th_generate_rays(H, W, _ptr(Kinv), _ptr(R), _ptr(T), _ptr(b), _ptr(out["ray_o"]), _ptr(out["ray_d"]),
+                                    _ptr(near), _ptr(far), _ptr(mask), _ptr(oc), _ptr(dc), _ptr(nc), _ptr(fc), _ptr(cnt),
+                                    _ptr(ws), 0 if ws is None else ws.numel(), _stream()), "th_generate_rays")
+    if bounds is not None:
+        out.update(near=near, far=far, mask_at_box=mask)
+        if compact:
+            m = int(cnt.item())
+            out.update(ray_o_c=oc[:m], ray_d_c=dc[:m], near_c=nc[:m], far_c=fc[:m], count=m)
     return out

@@ -11,10 +11,10 @@ Select it from the reference's YAML (no reference file edited)::
 return dict (``rgb_map (1,N,3)``, ``acc_map (1,N)``, ``depth_map (1,N)``) and
 batch keys as ``lib/networks/renderer/if_clight_renderer.py``.
 
-The per-frame prologue (image encoder, SMPL painting, cluster grouping, ViT)
-stays in torch exactly as SURVEY.md section 8 scopes it -- only its Python loops
-over clusters are replaced by a segment mean (8f-1).  Everything per sample
-point runs in ``libtranshuman_b200.so`` through :mod:`transhuman_b200.ops`.
+Per frame, the image encoder and the ViT stay the reference's torch modules (``net.encoder``, ``net.ViT``);
+everything else runs in ``libtranshuman_b200.so`` through :mod:`transhuman_b200.ops`: SMPL painting + cluster
+grouping (``th_paint_group`` / ``th_group_mean``), the pre-map GEMM over the encoder's maps
+(``th_premap_features``, 8f-2) and the whole per-sample-point path (``th_render_rays``).
 Forward only: training (autograd + stratified jitter) keeps the reference path.
 """
 from __future__ import annotations
@@ -24,7 +24,6 @@ import pickle
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import ops
 
@@ -80,15 +79,22 @@ class Renderer:
         self.vertex_can = torch.as_tensor(np.asarray(vertex_can)).contiguous()
         self.CR = torch.tensor([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
         num_voxel = int(self.cfg.num_class)
+        dict_voxel2pc_ind = None
         if pc2voxel_ind is None:
             # if_clight_renderer.py:55
             d = np.load(f'./kmeans_dict/kmeans_dict_{num_voxel}.npy', allow_pickle=True).item()
             pc2voxel_ind = d['pc2voxel_ind']
+            dict_voxel2pc_ind = d.get('dict_voxel2pc_ind')
         self.pc2voxel_ind = torch.as_tensor(np.asarray(pc2voxel_ind)).to(torch.int64)
         self.num_class = num_voxel
         assert int(self.pc2voxel_ind.max()) + 1 == num_voxel and len(torch.unique(self.pc2voxel_ind)) == num_voxel, \
             "cluster ids must be exactly arange(num_class)"
-        self.voxel_PE_can = segment_mean(self.vertex_can.to(torch.float64), self.pc2voxel_ind, num_voxel)
+        # clusters in CSR form for the paint / grouping kernels (member order = the reference's dict lists)
+        self.clusters = ops.ClusterIndex(pc2voxel_ind=self.pc2voxel_ind.numpy(), dict_voxel2pc_ind=dict_voxel2pc_ind,
+                                         n_tok=num_voxel, device="cpu")
+        # voxel_PE_can (if_clight_renderer.py:71): the literal per-cluster mean, once, on the CPU
+        st, mem = self.clusters.start_host, torch.from_numpy(self.clusters.members_host.astype(np.int64))
+        self.voxel_PE_can = torch.stack([self.vertex_can[mem[st[c]:st[c + 1]]].mean(0) for c in range(num_voxel)])
         self._weights = None
         self._weights_key = None
         self.last_counters = None
@@ -103,29 +109,6 @@ class Renderer:
         # if_clight_renderer.py:373-383
         lo, hi = self.CR[:3][None, None].to(PE.device), self.CR[3:][None, None].to(PE.device)
         return ((((PE - lo) / (hi - lo)) - 0.5) * 2).type(torch.float32)
-
-    @staticmethod
-    def _sample_from_feature_map(feat_map, feat_scale, image_shape, uv):
-        # if_clight_renderer.py:186-208
-        scale = torch.tensor(feat_scale / np.array(image_shape)).to(dtype=torch.float32, device=feat_map.device)
-        uv = (uv * scale - 1.0).unsqueeze(2)
-        return F.grid_sample(feat_map, uv, align_corners=True, mode="bilinear", padding_mode="border")[:, :, :, 0]
-
-    def _paint(self, batch, holder_feat_map, holder_feat_scale):
-        # paint_neural_human, if_clight_renderer.py:95-184 (t = 0)
-        smpl_vertice = batch['input_smpl_vertice'][0]
-        image_shape = batch['input_imgs'][0].shape[-2:]
-        R = batch['input_R'][0].reshape(-1, 3, 3)
-        T = batch['input_T'][0].reshape(-1, 3, 1)
-        K = batch['input_K'][0].reshape(-1, 3, 3)
-        v = torch.matmul(R[:, None], smpl_vertice.unsqueeze(-1))[..., 0] + T[:, None, :3, 0]
-        v = torch.matmul(K[:, None], v.unsqueeze(-1))[..., 0]
-        uv = v[:, :, :2] / v[:, :, 2:]
-        latent = self._sample_from_feature_map(holder_feat_map, holder_feat_scale, image_shape, uv).permute(0, 2, 1)
-        if getattr(self.cfg, 'rasterize', True) and 'input_vizmaps' in batch:
-            viz = batch['input_vizmaps'][0][0].to(torch.bool)
-            latent = torch.where(viz[..., None], latent, torch.zeros_like(latent))
-        return latent
 
     def _packed_weights(self, V, device):
         key = (V, str(device))
@@ -167,17 +150,22 @@ class Renderer:
         self._stage("encoder")
         holder_map, holder_scale, pixel_map, pixel_scale = self.net.encoder(images)
         V = pixel_map.shape[0]
-        self._stage("paint")
-        painted = self._paint(batch, holder_map, holder_scale)                       # (V, 6890, 192)
-        self._stage("group")
-        pc2 = self.pc2voxel_ind.to(dev)
-        grouped = segment_mean(painted.permute(1, 0, 2), pc2, self.num_class).permute(1, 0, 2).float()
+        # 8f-1: project + sample + visibility + cluster mean in ONE kernel (th_paint_group); token coordinates and
+        # blend matrices through th_group_mean (bit-equal to the reference's voxelization on the CPU)
+        self._stage("paint_group")
+        image_shape = batch['input_imgs'][0].shape[-2:]
+        hs = np.asarray(holder_scale, dtype=np.float64) / np.array(image_shape)
+        viz = batch['input_vizmaps'][0][0] if (getattr(self.cfg, 'rasterize', True) and 'input_vizmaps' in batch) else None
+        grouped = ops.paint_group(holder_map, (np.float32(hs[0]), np.float32(hs[1])), batch['input_smpl_vertice'][0][0],
+                                  batch['input_R'][0].reshape(-1, 3, 3), batch['input_T'][0].reshape(-1, 3),
+                                  batch['input_K'][0].reshape(-1, 3, 3), viz, self.clusters)
         pe = self.voxel_PE_can.to(dev).unsqueeze(0).repeat(V, 1, 1)
-        tok_xyz = segment_mean(batch['tar_smpl_vertice_smplcoord'][0], pc2, self.num_class).float()
-        tok_rot = segment_mean(batch['blend_mtx'][0], pc2, self.num_class)[:, :3, :3].float()
+        tok_xyz = ops.group_mean(batch['tar_smpl_vertice_smplcoord'][0].float().contiguous(), self.clusters)
+        blend = batch['blend_mtx'][0]
+        tok_rot = ops.group_mean(blend.contiguous(), self.clusters)[:, :3, :3].float() if blend.dtype == torch.float64 \
+            else ops.group_mean(blend.float().contiguous(), self.clusters, outer_order=False)[:, :3, :3]
         self._stage("vit")
         holder = self.net.ViT(grouped.contiguous(), self.normalize_PE(pe), mask=None)
-        image_shape = batch['input_imgs'][0].shape[-2:]
         fs = np.asarray(pixel_scale, dtype=np.float64)
         sc = fs / np.array(image_shape)
         # pre-mapped maps (alpha_res_0 / rgb_res_0 / rgb_res_1 applied to the maps once per frame, tcgen05 GEMM over
