@@ -242,7 +242,7 @@ def cpu_baseline_subprocess(args):
     return {"error": "no JSON line from the reference arm"}
 
 
-def torch_cuda_baseline(args, device, ours_img):
+def torch_cuda_baseline(args, device, ours_img, ours_render=None):
     """BASELINE configs[1]'s bar: the genuine reference Renderer.render in torch-CUDA on this GPU, full frame, TF32 off
     (the parity setting) and on.  knn_points (pytorch3d, absent) = squared distances + torch.topk on the device."""
     from oracle import transhuman_oracle as orc
@@ -259,6 +259,14 @@ def torch_cuda_baseline(args, device, ours_img):
     fr, maps = synthetic_frame(args)
     fr["pixel_feat_map"] = maps.numpy()
     ns, net, renderer, batch = build_reference(fr, args.samples, device=str(device), knn=knn_topk)
+    # Parity is quoted on the same tokens: the reference averages the token coordinates with a CUDA mean here, whose
+    # rounding differs from torch-CPU's (which th_group_mean reproduces) by an ulp -- enough to swap a 7th / 8th
+    # neighbour at ~1e-6 of the 16.7 M sample points
+    with torch.no_grad():
+        tok_xyz = renderer.voxelization(renderer.dict_voxel2pc_ind, batch["tar_smpl_vertice_smplcoord"][0]).float()
+        tok_rot = renderer.voxelization(renderer.dict_voxel2pc_ind, batch["blend_mtx"][0])[:, :3, :3].float().contiguous()
+    if ours_render is not None:
+        ours_img = ours_render(tok_xyz.contiguous(), tok_rot)
     res = {"impl": "genuine reference if_clight_renderer.Renderer.render via oracle/ref_shim.py, torch "
                    f"{torch.__version__} CUDA eager, full {args.size}x{args.size} frame, dense; prologue = fake encoder / "
                    "ViT returning the synthetic maps / tokens + the reference's own paint / grouping loops; "
@@ -565,9 +573,18 @@ def main():
         if world == 1 and not args.no_extras:
             ours_img, _ = render(dev_rays)
             ours_img = ours_img.clone()
+
+            def render_with_tokens(tok_xyz, tok_rot):
+                f2 = ops.Frame(holder=frame.holder, tok_xyz=tok_xyz, tok_rot=tok_rot, verts=frame.verts,
+                               feat_nhwc=frame.feat, cam_R=frame.cam_R, cam_T=frame.cam_T, cam_K=frame.cam_K,
+                               Rh=frame.Rh, Th=frame.Th, weights=frame.weights,
+                               uv_scale=(frame.c.uv_scale_x, frame.c.uv_scale_y), premapped=premapped)
+                o = ops.render_rays(f2, *dev_rays, S)
+                return torch.cat([o["rgb_map"], o["acc_map"][:, None], o["depth_map"][:, None]], dim=1)
+
             if reference_available():
                 try:
-                    extra["torch_cuda_baseline"] = torch_cuda_baseline(args, device, ours_img)
+                    extra["torch_cuda_baseline"] = torch_cuda_baseline(args, device, ours_img, render_with_tokens)
                 except Exception as e:  # noqa: BLE001  (a baseline must never take the bench line down)
                     extra["torch_cuda_baseline"] = {"error": repr(e)[:300]}
             else:

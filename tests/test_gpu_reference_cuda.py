@@ -43,6 +43,17 @@ def _fp32_reference():
     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 
 
+def _reference_tokens(renderer, batch):
+    """Token coordinates / blend matrices exactly as the reference computes them ON THIS DEVICE
+    (if_clight_renderer.py:543-544): its `mean(0)` runs in CUDA here, whose summation order differs from torch-CPU's
+    by an ulp -- enough to swap the 7th / 8th neighbour of ~1e-6 of the sample points.  Both sides get the same
+    tokens; th_group_mean's own bit-equality (to the CPU order) is tested in tests/test_gpu_prologue.py."""
+    with torch.no_grad():
+        xyz = renderer.voxelization(renderer.dict_voxel2pc_ind, batch["tar_smpl_vertice_smplcoord"][0])
+        blend = renderer.voxelization(renderer.dict_voxel2pc_ind, batch["blend_mtx"][0])
+    return xyz.cpu(), blend.cpu()
+
+
 def _capture_raw(ns):
     """Keep the raw tensor the reference hands to raw2outputs (for the knife-edge set)."""
     box = {}
@@ -70,7 +81,7 @@ def test_full_frame_c2_dense_matches_reference_cuda():
     finally:
         restore()
     tf = orc.to_torch_frame(fr)
-    tokens = orc.build_tokens(tf)
+    tokens = _reference_tokens(renderer, batch)
     frame, rays = frame_to_device(fr, tokens, DEV)
     got = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_DENSE, want_raw=True)
     raw_ref = box["raw"].reshape(-1, S, 4).cpu()
@@ -109,7 +120,7 @@ def test_full_frame_c2_culled_matches_reference_cuda():
     finally:
         restore()
     tf = orc.to_torch_frame(fr)
-    tokens = orc.build_tokens(tf)
+    tokens = _reference_tokens(renderer, batch)
     frame, rays = frame_to_device(fr, tokens, DEV)
     got = ops.render_rays(frame, *rays, S, mode=ops.TH_RENDER_FAST, want_raw=True, want_mask=True)
     alive_ref = ref["acc_map"][0] != 0

@@ -186,18 +186,20 @@ __global__ void k_near_far(const float* __restrict__ ray_o, float* __restrict__ 
   const double eps = 1e-6;
   int hits = 0;
   double dist[2] = {0.0, 0.0};
+  // numpy evaluates every product and sum separately (no FMA): explicit _rn intrinsics keep nvcc from contracting.
   // face order of `(nominator / ray_d[:, None]).reshape(-1, 6)`: (min x, min y, min z, max x, max y, max z)
 #pragma unroll
   for (int f = 0; f < 6; ++f) {
     const int side = f / 3, a = f % 3;
-    const double t = (bd[side][a] - o[a]) / d[a];
-    const double p0 = t * d[0] + o[0], p1 = t * d[1] + o[1], p2 = t * d[2] + o[2];
+    const double t = __ddiv_rn(__dsub_rn(bd[side][a], o[a]), d[a]);
+    const double p0 = __dadd_rn(__dmul_rn(t, d[0]), o[0]), p1 = __dadd_rn(__dmul_rn(t, d[1]), o[1]),
+                 p2 = __dadd_rn(__dmul_rn(t, d[2]), o[2]);
     const bool in = p0 >= bd[0][0] - eps && p0 <= bd[1][0] + eps && p1 >= bd[0][1] - eps && p1 <= bd[1][1] + eps &&
                     p2 >= bd[0][2] - eps && p2 <= bd[1][2] + eps;
     if (in) {
       if (hits < 2) {
-        const double q0 = p0 - o[0], q1 = p1 - o[1], q2 = p2 - o[2];
-        dist[hits] = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+        const double q0 = __dsub_rn(p0, o[0]), q1 = __dsub_rn(p1, o[1]), q2 = __dsub_rn(p2, o[2]);
+        dist[hits] = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(q0, q0), __dmul_rn(q1, q1)), __dmul_rn(q2, q2)));
       }
       ++hits;
     }
@@ -205,8 +207,9 @@ __global__ void k_near_far(const float* __restrict__ ray_o, float* __restrict__ 
   const bool ok = hits == 2;
   mask[g] = ok ? 1 : 0;
   if (ok) {
-    const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    const double d0 = dist[0] / nd, d1 = dist[1] / nd;
+    // `np.linalg.norm(ray_d, axis=1)` runs on the float32 rays: a float32 norm (95), promoted only by the division
+    const float ndf = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(df[0], df[0]), __fmul_rn(df[1], df[1])), __fmul_rn(df[2], df[2])));
+    const double d0 = __ddiv_rn(dist[0], (double)ndf), d1 = __ddiv_rn(dist[1], (double)ndf);
     near_[g] = (float)fmin(d0, d1);
     far_[g] = (float)fmax(d0, d1);
   } else {
