@@ -154,6 +154,11 @@ def _matrices(blob, V):
               "fc1": (256, 256), "fc2": (256, 256), "fc3m": (256, 256 * V), "afc": (1, 256), "f": (256, 640),
               "view": (128, 320), "t": (128, 128 * V + 384), "rgb": (3, 128), "fc1f": (256, 512), "gvf": (128, 704),
               "pre": (512, 384), "gvfp": (128, 448), "tp": (128, 128 * V + 128), "xid": (256, 256)}
+    # fc_1' cut into S / X parts and halves of 128 rows: (w, b) pairs after img_off / img_inv_scale / n_img
+    tail = struct.unpack_from("<12Q", blob, 16 + 57 * 8 + 24 * 8 + 24 * 4 + 8)
+    for i, name in enumerate(["fc1s0", "fc1s1", "fc1x0", "fc1x1"]):
+        pair[name] = (tail[2 * i], tail[2 * i + 1])
+        shapes[name] = (128, 256)
     out = {}
     for name, (ow, ob) in pair.items():
         n, k = shapes[name]

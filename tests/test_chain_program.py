@@ -17,13 +17,13 @@ import torch
 from tests.test_cabi_host import _matrices, _pack, lib  # noqa: F401  (fixture)
 from transhuman_b200 import synth
 
-EPI_IMG, EPI_KEEP, EPI_SCORES, EPI_ALPHA, EPI_RGB = 0, 2, 3, 4, 5
+EPI_IMG, EPI_KEEP, EPI_SCORES, EPI_ALPHA, EPI_RGB, EPI_MIX = 0, 2, 3, 4, 5, 6
 MAX_SEG = 5
 IMG_NAMES = ["fc0", "ar0", "k0", "k1", "v", "fc1", "fc2", "fc3m", "f", "view", "t", "fc1f", "gvf"]
 
 
 def _program(lib, blob, V, P, alpha_only, premapped):
-    cap = 8 + 28 * (16 + 6 * MAX_SEG)
+    cap = 8 + 32 * (16 + 6 * MAX_SEG)
     table = np.zeros(cap, dtype=np.int64)
     n = lib.th_debug_chain_program(blob.ctypes.data, V, P, alpha_only, premapped, table.ctypes.data, cap)
     assert n > 0, n
@@ -31,7 +31,8 @@ def _program(lib, blob, V, P, alpha_only, premapped):
     jobs = []
     for j in range(int(head[0])):
         t = table[8 + j * (16 + 6 * MAX_SEG):8 + (j + 1) * (16 + 6 * MAX_SEG)]
-        keys = ["N", "relu", "epi", "out_off", "tmem_col", "wait_back", "view", "nseg", "nkb", "wimg", "bias", "bias2"]
+        keys = ["N", "relu", "epi", "out_off", "tmem_col", "wait_back", "view", "nseg", "nkb", "wimg", "bias", "bias2",
+                "reader"]
         job = {k: int(t[i]) for i, k in enumerate(keys)}
         job["segs"] = [dict(zip(["chunk", "off", "tile_off", "kbs", "dep", "dep_mix"], map(int, t[16 + 6 * s:22 + 6 * s])))
                        for s in range(job["nseg"])]
@@ -48,6 +49,11 @@ def _images(blob, V):
               "tp": (128, 128 * V + 128), "xid": (256, 256)}
     img = {n: offs[30 + i] for i, n in enumerate(IMG_NAMES)}
     img.update({"gvfp": offs[51], "tp": offs[52], "xid": offs[53]})
+    # fc_1' cut into S / X parts and halves of 128 rows (after img_off[24] / img_inv_scale[24] / n_img in the header)
+    tail = struct.unpack_from("<12Q", blob, 16 + 57 * 8 + 24 * 8 + 24 * 4 + 8)
+    for i, n in enumerate(["fc1s0", "fc1s1", "fc1x0", "fc1x1"]):
+        img[n] = tail[8 + i]
+        shapes[n] = (128, 256)
     return {n: (o, shapes[n]) for n, o in img.items()}
 
 
@@ -56,14 +62,23 @@ def _check_tmem(head, jobs):
     the epilogue of job G - wait_back; kept key embeds are read by every score epilogue."""
     n = head["njobs"]
     flip_on = 256 if n & 1 else 0
-    last_scores = max((j for j, jb in enumerate(jobs) if jb["epi"] == EPI_SCORES), default=-1)
     seq = []
     for unit in range(3):
         for j, jb in enumerate(jobs):
             col = (jb["tmem_col"] + (flip_on if unit & 1 else 0)) & 511
             assert col + jb["N"] <= 512
-            last_reader = unit * n + (last_scores if jb["epi"] == EPI_KEEP else j)
-            seq.append((col, col + jb["N"], last_reader, jb["wait_back"]))
+            last = j
+            if jb["epi"] == EPI_KEEP:   # independent of the builder's bookkeeping: who reads a kept accumulator?
+                k = j + 1
+                while jobs[k]["epi"] == EPI_KEEP:
+                    k += 1
+                kind = jobs[k]["epi"]                             # key embeds -> scores, Y_i -> the mix epilogues
+                assert kind in (EPI_SCORES, EPI_MIX)
+                while k + 1 < n and jobs[k + 1]["epi"] == kind:
+                    k += 1
+                last = k                                          # the last job of that contiguous run
+                assert jb["reader"] == last, (j, jb["reader"], last)
+            seq.append((col, col + jb["N"], unit * n + last, jb["wait_back"]))
     for g, (c0, c1, _, wb) in enumerate(seq):
         for a in range(g):
             a0, a1, reader, _ = seq[a]
@@ -82,7 +97,7 @@ def _interpret(blob, head, jobs, data):
     o_pm = o_pix + V * Pp * 384 * 4 + 4 * V * Pp * 256 * 4 + 2 * V * Pp * 128 * 4
     chunk = {0: "rep", o_pix: "pix", o_pix + V * Pp * 256 * 4: "p2", o_pm: "pix_mean", o_pm + Pp * 384 * 4: "vd"}
     slots, written_by = {}, {}
-    KS, scores, alpha, out_final = {}, {}, None, None
+    kept, scores, alpha, out_final, Aw = {}, {}, None, None, None
     data = dict(data)
     mixed_in_chunk = False
     for j, jb in enumerate(jobs):
@@ -98,14 +113,16 @@ def _interpret(blob, head, jobs, data):
                 assert buf.shape[-1] == C_, (j, name, buf.shape, C_)
                 parts.append(buf[view if buf.shape[0] > 1 else 0])
             else:
-                assert sg["off"] % scr == 0
-                slot = sg["off"] // scr
+                slot, kb0 = sg["off"] // scr, (sg["off"] % scr) // head["tile_img"]
+                assert (sg["off"] % scr) % head["tile_img"] == 0
                 assert slot in slots, f"job {j} reads scratch slot {slot} before anything stored it"
                 if sg["dep"] >= 0:
-                    assert written_by[slot] == sg["dep"] < j, (j, slot, written_by[slot], sg["dep"])
-                assert bool(sg["dep_mix"]) == (head["has_mix"] == 1 and slot >= V and jobs[written_by[slot]]["epi"] == EPI_IMG
+                    for kb in range(kb0, kb0 + sg["kbs"]):
+                        assert written_by[(slot, kb)] == sg["dep"] < j, (j, slot, kb, written_by[(slot, kb)], sg["dep"])
+                assert bool(sg["dep_mix"]) == (head["has_mix"] == 1 and slot >= V and
+                                               jobs[written_by[(slot, kb0)]]["epi"] == EPI_IMG
                                                and jb["epi"] == EPI_IMG and jb["N"] == 256 and len(jb["segs"]) == 2)
-                parts.append(slots[slot][:, :C_])
+                parts.append(slots[slot][:, 64 * kb0:64 * kb0 + C_])
         A = torch.cat(parts, -1)
         assert A.shape[1] == jb["nkb"] * 64
         name = next(n for n, (o, (N, K)) in images.items() if o <= jb["wimg"] < o + N * K * 4)
@@ -116,25 +133,31 @@ def _interpret(blob, head, jobs, data):
         assert W.shape[1] == A.shape[1], (j, name, kb0)
         out = A @ W.T
         bias = f32(jb["bias"], N) if jb["bias"] >= 0 else None
-        if jb["epi"] == EPI_IMG:
+        if jb["epi"] in (EPI_IMG, EPI_MIX):
             out = out + bias if bias is not None else out
+            if jb["epi"] == EPI_MIX:   # + sum_i A[i][j] Y_i, Y_i = the kept accumulators of the X part
+                assert Aw is not None and len(kept) == V
+                out = out + sum(Aw[:, i, jb["view"], None] * kept[i] for i in range(V))
             out = torch.relu(out) if jb["relu"] else out
-            slot = jb["out_off"] // scr
-            assert jb["out_off"] % scr == 0
-            full = torch.zeros((out.shape[0], 256), dtype=torch.float64)
-            full[:, :N] = out
-            slots[slot], written_by[slot] = full, j
+            slot, kb0 = jb["out_off"] // scr, (jb["out_off"] % scr) // head["tile_img"]
+            assert (jb["out_off"] % scr) % head["tile_img"] == 0 and 64 * kb0 + N <= 256
+            if slot not in slots or jb["epi"] == EPI_IMG:
+                slots[slot] = torch.zeros((out.shape[0], 256), dtype=torch.float64)   # a whole new tile
+            slots[slot][:, 64 * kb0:64 * kb0 + N] = out
+            for kb in range(kb0, kb0 + N // 64):
+                written_by[(slot, kb)] = j
         elif jb["epi"] == EPI_KEEP:
             assert bias is None
-            KS[jb["view"]] = out
+            kept[jb["view"]] = out
         elif jb["epi"] == EPI_SCORES:
             kp = out + bias
             b2 = f32(jb["bias2"], 128)
             for jv in range(V):
-                scores[(jb["view"], jv)] = (kp * (KS[jv] + b2)).sum(-1) / np.sqrt(128.0)
+                scores[(jb["view"], jv)] = (kp * (kept[jv] + b2)).sum(-1) / np.sqrt(128.0)
             if jb["view"] == V - 1:
                 S_ = torch.stack([torch.stack([scores[(i, jv)] for jv in range(V)], -1) for i in range(V)], 1)  # (P,i,j)
                 Aw = torch.softmax(S_, dim=1)
+                kept = {}                                        # the key embeds are dead once the scores exist
                 if head["has_mix"] == 1 and (V in slots):
                     X = torch.stack([slots[V + i] for i in range(V)], 0)                      # (i,P,256)
                     XT = torch.einsum("pij,ipc->jpc", Aw, X)
@@ -163,7 +186,9 @@ def test_chain_program(lib, V, variant):
     P = 200
     premapped, alpha_only = variant.startswith("premapped"), variant.endswith("alpha_only")
     head, jobs = _program(lib, blob, V, P, int(alpha_only), int(premapped))
-    assert head["V"] == V and head["Pp"] == 256 and head["njobs"] == len(jobs) <= 28
+    assert head["V"] == V and head["Pp"] == 256 and head["njobs"] == len(jobs) <= 32
+    if premapped:    # the pre-mapped program mixes on the accumulator side: no mix warps, X never rewritten
+        assert head["has_mix"] == 0 and sum(jb["epi"] == EPI_MIX for jb in jobs) == 2 * V
     _check_tmem(head, jobs)
 
     g = torch.Generator().manual_seed(4)

@@ -118,6 +118,10 @@ static std::vector<MatSpec> mat_specs(int V) {
       {&H::tp_w, &H::tp_b, &H::h_tp, 128, 128 * V + 128},
       {&H::xid_w, &H::xid_b, &H::h_xid, 256, 256},
       {&H::preb_w, &H::preb_b, &H::h_preb, 256, 384},
+      {&H::fc1s0_w, &H::fc1s0_b, &H::h_fc1s0, 128, 256},
+      {&H::fc1s1_w, &H::fc1s1_b, &H::h_fc1s1, 128, 256},
+      {&H::fc1x0_w, &H::fc1x0_b, &H::h_fc1x0, 128, 256},
+      {&H::fc1x1_w, &H::fc1x1_b, &H::h_fc1x1, 128, 256},
   };
 }
 
@@ -325,6 +329,16 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
     for (int n = 0; n < 256; ++n) W(h.xid_w)[(size_t)n * 256 + n] = 1.0f;
     // rows 256..511 of W_pre as a matrix of their own (the second launch of the pre-map GEMM; zero bias)
     memcpy(W(h.preb_w), W(h.pre_w) + (size_t)256 * 384, (size_t)256 * 384 * 4);
+    // fc_1' cut into S / X parts and halves of 128 output rows (PackedHeader)
+    float* const fs[2] = {W(h.fc1s0_w), W(h.fc1s1_w)};
+    float* const fx[2] = {W(h.fc1x0_w), W(h.fc1x1_w)};
+    float* const fb[2] = {W(h.fc1s0_b), W(h.fc1s1_b)};
+    for (int hh = 0; hh < 2; ++hh)
+      for (int n = 0; n < 128; ++n) {
+        memcpy(fs[hh] + (size_t)n * 256, W(h.fc1f_w) + (size_t)(128 * hh + n) * 512, 256 * 4);
+        memcpy(fx[hh] + (size_t)n * 256, W(h.fc1f_w) + (size_t)(128 * hh + n) * 512 + 256, 256 * 4);
+        fb[hh][n] = W(h.fc1f_b)[128 * hh + n];
+      }
   }
   // fp16 hi/lo split of the GEMM matrices, stored as shared-memory tile images for
   // the tensor-core path: per 64-wide k-block and per half of the N rows (one half per CTA of a

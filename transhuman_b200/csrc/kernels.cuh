@@ -143,6 +143,11 @@ struct PackedHeader {
   uint64_t img_off[24];
   float img_inv_scale[24];
   int32_t n_img, pad_;
+  // fc_1' = [fc_1 @ v1 | fc_1 @ v0] cut into its S part and its X part and into two halves of 128 output rows
+  // each (N = 128 jobs of the TMEM-side attention mix, mlp_chain.cu): fc1s{h} = W_fc1f[128h:128h+128, 0:256]
+  // with bias b_fc1f[128h:], fc1x{h} = W_fc1f[128h:128h+128, 256:512] with zero bias
+  uint64_t fc1s0_w, fc1s0_b, fc1s1_w, fc1s1_b, fc1x0_w, fc1x0_b, fc1x1_w, fc1x1_b;
+  uint64_t h_fc1s0, h_fc1s1, h_fc1x0, h_fc1x1;
 };
 // DEVICE address of the 2^-e of the weight image at byte offset `off` (nullptr = unknown image, scale 1).  The scale
 // is per blob (it depends on the weights), so kernels read it from the blob itself; the host only needs the INDEX,

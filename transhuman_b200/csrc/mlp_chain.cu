@@ -47,14 +47,16 @@ constexpr int MIX_THREADS = 192, LOADER_WARP = 6, MMA_WARP = 7, EPI_WARP0 = 8;
 constexpr int EPI_WARPS = 8;
 constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = 65536;  // A hi/lo (32 KB) + this CTA's half of B hi/lo (<= 32 KB)
-constexpr int MAX_SEG = 5, MAX_JOBS = 24;
+constexpr int MAX_SEG = 5, MAX_JOBS = 32;
 constexpr uint32_t TILE_IMG = 2 * A_TILE_BYTES;       // one 128-row x 64-column hi/lo k-block
 constexpr uint32_t SCR_ACT = 4 * TILE_IMG;            // a 256-wide activation tile: 128 KB
 constexpr int CHAIN_MAX_V = 3;                        // V key embeds + one more must fit 512 TMEM columns
 // Per-CTA scratch for V views: slot A (S -> N1 -> INTER) and slot B (X -> XT -> G), V tiles each.
 __host__ __device__ inline uint32_t scratch_stride(int V) { return 2u * (uint32_t)V * SCR_ACT; }
 
-enum { EPI_IMG = 0, EPI_KEEP = 2, EPI_SCORES = 3, EPI_ALPHA = 4, EPI_RGB = 5 };
+// EPI_MIX: the attention mix on the ACCUMULATOR side (pre-mapped program): out = relu(Z + b + sum_i A[i][j] Y_i) with
+// Z = this job's accumulator (the S part of fc_1', view j) and Y_i = kept accumulators of the X part for every view i
+enum { EPI_IMG = 0, EPI_KEEP = 2, EPI_SCORES = 3, EPI_ALPHA = 4, EPI_RGB = 5, EPI_MIX = 6 };
 
 struct Seg {
   const unsigned char* img;  // chunk-level tile image, or nullptr = this CTA's scratch
@@ -63,6 +65,7 @@ struct Seg {
   int32_t kbs;
   int32_t dep;      // job (same unit) whose stored output this segment reads, -1 = chunk input
   int32_t dep_mix;  // 1 = written by the mix warps, released per k-block
+  int32_t keep;     // chunk input that a later job of the unit reads again: keep it in L2 (default: evict first)
 };
 struct Job {
   Seg seg[MAX_SEG];
@@ -72,7 +75,8 @@ struct Job {
   uint32_t out_off;         // EPI_IMG: destination inside the CTA's scratch
   int32_t nseg, nkb, N, relu, epi, tmem_col, wait_back, view;
   const float* acc_scale;   // DEVICE pointer to the 2^-e of this job's weight image (img_inv_scale_ptr): acc * scale + bias
-  const float* acc_scale2;  // EPI_SCORES: the scale of the kept key embeds' weight image
+  const float* acc_scale2;  // EPI_SCORES: the scale of the kept key embeds' weight image; EPI_MIX: of the Y jobs'
+  int32_t reader;           // host only: last job whose epilogue reads this accumulator (-1 = its own epilogue)
 };
 struct Program {
   // TMA descriptors: tile images as rows of 64 fp16 (128 B).  tm_a: box 256 rows (one 32 KB hi|lo
@@ -398,7 +402,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
                                                   : scratch + sg.scratch_off;
             // chunk inputs stream through L2 once (evict first); scratch tiles and weights are the
             // working set that should stay resident (evict last)
-            const uint64_t pol = from_chunk ? L2_EVICT_FIRST : L2_EVICT_LAST;
+            const uint64_t pol = (from_chunk && !sg.keep) ? L2_EVICT_FIRST : L2_EVICT_LAST;
             if (sg.dep >= 0 && !((dep_seen >> sg.dep) & 1u)) {
               TH_TIMED(0, wait_counter(cnt_job + 4 * sg.dep, done_target, 2));
               // whatever else is stored by now rides on the same fence
@@ -521,7 +525,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         tc_fence_after();
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t taddr = lane_addr + (((uint32_t)jb.tmem_col + flip) & 511u);
-        if (epi == EPI_IMG) {
+        if (epi == EPI_IMG || epi == EPI_MIX) {
           // bias / ReLU / fp16 hi-lo split straight from the accumulator to the scratch tile image:
           // a thread owns one row; 16 columns = one 32-byte sector of the hi plane and one of the lo
           // plane (the 128-byte swizzle permutes 16-byte chunks inside a sector pair-wise).
@@ -530,7 +534,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           const bool swap = (et & 1) != 0;
           const bool relu = jb.relu != 0;
           const float acc_s = __ldg(jb.acc_scale);
-          const float2 sc2 = make_float2(acc_s, acc_s);
+          // EPI_MIX adds the bias to an already scaled and mixed value: scale 1
+          const float2 sc2 = epi == EPI_MIX ? make_float2(1.f, 1.f) : make_float2(acc_s, acc_s);
           // 32 accumulator columns -> 2 x (hi sector, lo sector)
           auto emit = [&](const uint32_t (&v)[32], int c0) {
             unsigned char* kb_out = out + (size_t)(c0 >> 6) * TILE_IMG;
@@ -567,17 +572,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
               st32_keep(dst + A_TILE_BYTES, swap ? lo[1] : lo[0], swap ? lo[0] : lo[1]);
             }
           };
-          // software pipelined: the next 32 columns are in flight from TMEM while these are converted
           uint32_t va[32], vb[32];
-          tmem_ld32(taddr + cbeg, va);
+          if (epi == EPI_IMG) {
+            // software pipelined: the next 32 columns are in flight from TMEM while these are converted
+            tmem_ld32(taddr + cbeg, va);
 #pragma unroll 1
-          for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 64) {
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tmem_ld32(taddr + c0 + 32, vb);  // ncol is a multiple of 64
-            emit(va, c0);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c0 + 64 < cbeg + ncol) tmem_ld32(taddr + c0 + 64, va);
-            emit(vb, c0 + 32);
+            for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 64) {
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              tmem_ld32(taddr + c0 + 32, vb);  // ncol is a multiple of 64
+              emit(va, c0);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              if (c0 + 64 < cbeg + ncol) tmem_ld32(taddr + c0 + 64, va);
+              emit(vb, c0 + 32);
+            }
+          } else {
+            // N1_j = relu(Z s_z + b + sum_i (A[i][j] s_y) Y_i): Z = this job's accumulator, Y_i = the kept
+            // accumulators of the X part (columns ks_col[i]); the attention table was finished by the last
+            // score epilogue (ordered by the named barrier of the jobs in between).  fp32 throughout: the mix
+            // is never re-quantised to fp16 operands, and the tensor pipe never waits for it.
+            const int jv = jb.view;
+            const float s_y = __ldg(jb.acc_scale2);
+            float am[CHAIN_MAX_V];
+#pragma unroll
+            for (int i = 0; i < CHAIN_MAX_V; ++i) am[i] = i < V ? atab[i * V + jv] * s_y : 0.f;
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 32) {
+              tmem_ld32(taddr + c0, va);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              tmem_ld32(lane_addr + (((uint32_t)pg.ks_col[0] + flip) & 511u) + c0, vb);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) va[e] = __float_as_uint(__uint_as_float(va[e]) * acc_s);
+#pragma unroll
+              for (int i = 0; i < CHAIN_MAX_V; ++i)
+                if (i < V) {
+                  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                  const float a_i = am[i];
+#pragma unroll
+                  for (int e = 0; e < 32; ++e) va[e] = __float_as_uint(fmaf(a_i, __uint_as_float(vb[e]), __uint_as_float(va[e])));
+                  if (i + 1 < V) tmem_ld32(lane_addr + (((uint32_t)pg.ks_col[i + 1] + flip) & 511u) + c0, vb);
+                }
+              emit(va, c0);
+            }
           }
           // Publication: a CTA-scope release of a counter, nothing else.  The loader, having acquired
           // it, executes the gpu-scope fence (cumulative over the stores it has thereby observed) and the
@@ -707,7 +742,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           }
         }
         // this warp is done with the accumulator of job G
-        if (stats) tw[3 + (epi == EPI_IMG ? 0 : epi == EPI_SCORES ? 1 : 2)] += clock64() - t_work;
+        if (stats) tw[3 + ((epi == EPI_IMG || epi == EPI_MIX) ? 0 : epi == EPI_SCORES ? 1 : 2)] += clock64() - t_work;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -785,6 +820,7 @@ struct Builder {
     jb.view = view;
     jb.tmem_col = col >= 0 ? col : (j & 1) * 256;
     jb.wait_back = wait_back;
+    jb.reader = -1;
     return j;
   }
 };
@@ -873,28 +909,70 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     B.pg.ks_col[2] = 0;
     B.pg.kp_col = 128;
   }
+  // TMEM-side attention mix (pre-mapped program; TH_CHAIN_INPLACE_MIX=1 keeps the in-place operand mix by the idle
+  // warps for A/B measurements): see the job list below
+  static const bool inplace_mix = getenv("TH_CHAIN_INPLACE_MIX") && atoi(getenv("TH_CHAIN_INPLACE_MIX"));
+  const bool tmix = x_in_chunk && !inplace_mix;
+  uint64_t mix_y_img[MAX_JOBS] = {0};  // EPI_MIX jobs: weight image of the Y jobs they combine (for acc_scale2)
+  int j_ks[TH_MAX_VIEWS];
   for (int v = 0; v < V; ++v)
-    B.add({Builder::scr(B.slotA(v), 256, j_s[v])}, wimg(h.h_k1), nullptr, 128, 0, EPI_KEEP, 0, v, B.pg.ks_col[v], 2);
+    j_ks[v] = B.add({Builder::scr(B.slotA(v), 256, j_s[v])}, wimg(h.h_k1), nullptr, 128, 0, EPI_KEEP, 0, v,
+                    B.pg.ks_col[v], 2);
   for (int v = 0; v < V; ++v) {
-    const int j = B.add({x_in_chunk ? B.in_view(b.pix, 256, v) : Builder::scr(B.slotB(v), 256, j_x[v])}, wimg(h.h_k0),
-                        wf(h.k0_b), 128, 0, EPI_SCORES, 0, v, B.pg.kp_col, v == 0 ? 2 : 1);
+    Seg x = x_in_chunk ? B.in_view(b.pix, 256, v) : Builder::scr(B.slotB(v), 256, j_x[v]);
+    x.keep = tmix ? 1 : 0;  // X is read again by the Y jobs
+    const int j = B.add({x}, wimg(h.h_k0), wf(h.k0_b), 128, 0, EPI_SCORES, 0, v, B.pg.kp_col, v == 0 ? 2 : 1);
     B.pg.job[j].bias2 = wf(h.k1_b);
+    if (v == V - 1)
+      for (int u = 0; u < V; ++u) B.pg.job[j_ks[u]].reader = j;  // the kept key embeds are read by every score job
   }
-  B.pg.has_mix = 1;
-  // N1_v = relu([S_v | XT_v] W_fc1f^T) in place of S_v; INTER_v = relu(fc_2 N1_v) in place again
-  for (int v = 0; v < V; ++v) {
-    Seg xt = x_in_chunk ? B.in_view(b.pix, 256, v) : Builder::scr(B.slotB(v), 256, -1, 1);
-    xt.dep_mix = 1;  // mixed in place (scratch slot B, or the chunk image), released per k-block
-    j_n1[v] = B.add({Builder::scr(B.slotA(v), 256, -1), xt}, wimg(h.h_fc1f), wf(h.fc1f_b), 256, 1, EPI_IMG,
-                    B.slotA(v), v, -1, v == 0 ? 1 : 2);
+  if (tmix) {
+    // N1_j = relu(W_s S_j + sum_i A[i][j] (W_x X_i) + b): the X part of fc_1' applied BEFORE the mix, so the mix
+    // becomes an fp32 combination of accumulators in the epilogue instead of a rewrite of fp16 operands that the
+    // tensor pipe has to wait for (TH_CHAIN_STATS, in-place mix: fc_1' of view 0 waited 51 of the unit's 274
+    // kcycles; without any mix the launch is 18 % shorter).  512 TMEM columns hold three kept Y_i = W_x X_i and one
+    // Z_j = W_s S_j of 128 output channels each, so fc_1' runs as two halves of 128 rows: per half
+    //   Y_0h Y_1h Y_2h (N = 128, K = 256, kept at the key-embed columns), then Z_0h Z_1h Z_2h (N = 128, K = 256, at the
+    //   score column) whose epilogue (EPI_MIX) writes channels [128h, 128h + 128) of N1_j into slot B(j).
+    // Same MACs as fc_1' with K = 512; X stays pristine in the chunk image (no in-place writes, no mix fences).
+    B.pg.has_mix = 0;
+    const uint64_t hs[2] = {h.h_fc1s0, h.h_fc1s1}, hx[2] = {h.h_fc1x0, h.h_fc1x1}, bs[2] = {h.fc1s0_b, h.fc1s1_b};
+    int j_z[TH_MAX_VIEWS][2];
+    for (int hh = 0; hh < 2; ++hh) {
+      int j_y[TH_MAX_VIEWS];
+      for (int i = 0; i < V; ++i) {
+        Seg x = B.in_view(b.pix, 256, i);
+        x.keep = hh == 0 ? 1 : 0;
+        j_y[i] = B.add({x}, wimg(hx[hh]), nullptr, 128, 0, EPI_KEEP, 0, i, B.pg.ks_col[i], 2);
+      }
+      for (int jv = 0; jv < V; ++jv) {
+        j_z[jv][hh] = B.add({Builder::scr(B.slotA(jv), 256, j_s[jv])}, wimg(hs[hh]), wf(bs[hh]), 128, 1, EPI_MIX,
+                            B.slotB(jv) + 2u * (uint32_t)hh * TILE_IMG, jv, B.pg.kp_col, 1);
+        mix_y_img[j_z[jv][hh]] = hx[hh];
+      }
+      for (int i = 0; i < V; ++i) B.pg.job[j_y[i]].reader = j_z[V - 1][hh];
+    }
+    // INTER_v = relu(fc_2 N1_v): N1_v from slot B(v) (two halves, two producers), INTER_v over the dead S_v
+    for (int v = 0; v < V; ++v)
+      j_int[v] = B.add({Builder::scr(B.slotB(v), 128, j_z[v][0]), Builder::scr(B.slotB(v) + 2u * TILE_IMG, 128, j_z[v][1])},
+                       wimg(h.h_fc2), wf(h.fc2_b), 256, 1, EPI_IMG, B.slotA(v));
+  } else {
+    B.pg.has_mix = 1;
+    // N1_v = relu([S_v | XT_v] W_fc1f^T) in place of S_v; INTER_v = relu(fc_2 N1_v) in place again
+    for (int v = 0; v < V; ++v) {
+      Seg xt = x_in_chunk ? B.in_view(b.pix, 256, v) : Builder::scr(B.slotB(v), 256, -1, 1);
+      xt.dep_mix = 1;  // mixed in place (scratch slot B, or the chunk image), released per k-block
+      j_n1[v] = B.add({Builder::scr(B.slotA(v), 256, -1), xt}, wimg(h.h_fc1f), wf(h.fc1f_b), 256, 1, EPI_IMG,
+                      B.slotA(v), v, -1, v == 0 ? 1 : 2);
+    }
+    if (x_in_chunk) {
+      B.pg.x_img = reinterpret_cast<unsigned char*>(const_cast<float*>(b.pix));
+      B.pg.x_view_stride = (int64_t)(Pp / 128) * 4 * TILE_IMG;
+    }
+    for (int v = 0; v < V; ++v)
+      j_int[v] = B.add({Builder::scr(B.slotA(v), 256, j_n1[v])}, wimg(h.h_fc2), wf(h.fc2_b), 256, 1, EPI_IMG,
+                       B.slotA(v));
   }
-  if (x_in_chunk) {
-    B.pg.x_img = reinterpret_cast<unsigned char*>(const_cast<float*>(b.pix));
-    B.pg.x_view_stride = (int64_t)(Pp / 128) * 4 * TILE_IMG;
-  }
-  for (int v = 0; v < V; ++v)
-    j_int[v] = B.add({Builder::scr(B.slotA(v), 256, j_n1[v])}, wimg(h.h_fc2), wf(h.fc2_b), 256, 1, EPI_IMG,
-                     B.slotA(v));
   auto add_fc3 = [&]() {
     const int j = B.pg.njobs++;
     Job& jb = B.pg.job[j];
@@ -910,6 +988,7 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     jb.epi = EPI_ALPHA;
     jb.tmem_col = (j & 1) * 256;
     jb.wait_back = 2;
+    jb.reader = -1;
   };
   if (run.alpha_only) {
     add_fc3();
@@ -942,12 +1021,13 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
       jb.epi = EPI_RGB;
       jb.tmem_col = (j & 1) * 256;
       jb.wait_back = 2;
+      jb.reader = -1;
     }
   }
   Program& pg = B.pg;
   for (int j = 0; j < pg.njobs; ++j) {  // accumulator scales of the weight images (PackedHeader::img_inv_scale)
     pg.job[j].acc_scale = img_inv_scale_ptr(run.weights, h, (uint64_t)(pg.job[j].wimg - run.weights));
-    pg.job[j].acc_scale2 = img_inv_scale_ptr(run.weights, h, h.h_k1);
+    pg.job[j].acc_scale2 = img_inv_scale_ptr(run.weights, h, mix_y_img[j] ? mix_y_img[j] : h.h_k1);
     if (!pg.job[j].acc_scale || !pg.job[j].acc_scale2) {
       set_error("mlp_forward_chain: job %d reads a weight image the blob header does not list", j);
       return TH_EINVAL;
@@ -959,9 +1039,6 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     // whose epilogue still reads columns that G overwrites); kept key embeds are read by every score job.
     const int n = pg.njobs;
     const uint32_t flip_on_h = (n & 1) ? 256u : 0u;
-    int last_scores = -1;
-    for (int j = 0; j < n; ++j)
-      if (pg.job[j].epi == EPI_SCORES) last_scores = j;
     for (int j = 0; j < n; ++j) {
       int wb = n;  // nothing to wait for
       for (int u = 1; u <= 2; ++u) {  // steady state: two consecutive units with their column flips
@@ -971,8 +1048,8 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
           const int ja = A % n, ua = A / n;
           const uint32_t a0 = ((uint32_t)pg.job[ja].tmem_col + ((ua & 1) ? flip_on_h : 0u)) & 511u, a1 = a0 + pg.job[ja].N;
           if (a0 < c1 && c0 < a1) {
-            const int reader = ua * n + (pg.job[ja].epi == EPI_KEEP ? last_scores : ja);
-            if (G - reader < wb) wb = G - reader;
+            const int reader = ua * n + (pg.job[ja].reader >= 0 ? pg.job[ja].reader : ja);
+            if (reader < G && G - reader < wb) wb = G - reader;
           }
         }
       }
@@ -1082,7 +1159,7 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
 // (the chunk block of mlp_carve) and to the start of the packed weight blob.
 //   header: [njobs, V, has_mix, alpha_only, Pp, scr_act_bytes, tile_img_bytes, 0]
 //   job (16 + 6 * MAX_SEG words): N, relu, epi, out_off, tmem_col, wait_back, view, nseg, nkb, wimg_off,
-//        bias_off (-1 = none), bias2_off (-1 = none), 0, 0, 0, 0, then per segment:
+//        bias_off (-1 = none), bias2_off (-1 = none), reader (-1 = own epilogue), 0, 0, 0, then per segment:
 //        kind (0 scratch / 1 chunk image), offset (scratch bytes / image byte offset from the chunk base),
 //        tile_off, kbs, dep, dep_mix
 extern "C" int64_t th_debug_chain_program(const void* packed_host, int32_t n_views, int64_t n_points,
@@ -1121,7 +1198,7 @@ extern "C" int64_t th_debug_chain_program(const void* packed_host, int32_t n_vie
     const Job& jb = pg.job[j];
     t[0] = jb.N; t[1] = jb.relu; t[2] = jb.epi; t[3] = jb.out_off; t[4] = jb.tmem_col; t[5] = jb.wait_back;
     t[6] = jb.view; t[7] = jb.nseg; t[8] = jb.nkb; t[9] = woff(jb.wimg); t[10] = woff(jb.bias); t[11] = woff(jb.bias2);
-    t[12] = t[13] = t[14] = t[15] = 0;
+    t[12] = jb.reader; t[13] = t[14] = t[15] = 0;
     for (int sgi = 0; sgi < MAX_SEG; ++sgi) {
       const Seg& sg = jb.seg[sgi];
       int64_t* q = t + 16 + 6 * sgi;
