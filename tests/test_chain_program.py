@@ -178,17 +178,21 @@ def _interpret(blob, head, jobs, data):
 
 
 @pytest.mark.parametrize("V", [1, 2, 3])
-@pytest.mark.parametrize("variant", ["default", "alpha_only", "premapped", "premapped_alpha_only"])
+@pytest.mark.parametrize("variant", ["default", "alpha_only", "premapped", "premapped_alpha_only", "premapped_tmem",
+                                     "premapped_tmem_alpha_only"])
 def test_chain_program(lib, V, variant):
     from oracle import transhuman_oracle as orc
     w = synth.make_weights(seed=9)
     blob = _pack(lib, w, V)
     P = 200
     premapped, alpha_only = variant.startswith("premapped"), variant.endswith("alpha_only")
-    head, jobs = _program(lib, blob, V, P, int(alpha_only), int(premapped))
+    # th_debug_chain_program's `premapped`: 2 = TMEM-side mix, 3 = in-place mix by the mix warps
+    head, jobs = _program(lib, blob, V, P, int(alpha_only), (2 if "tmem" in variant else 3) if premapped else 0)
     assert head["V"] == V and head["Pp"] == 256 and head["njobs"] == len(jobs) <= 32
-    if premapped:    # the pre-mapped program mixes on the accumulator side: no mix warps, X never rewritten
+    if "tmem" in variant:    # mix on the accumulator side: no mix warps, X never rewritten
         assert head["has_mix"] == 0 and sum(jb["epi"] == EPI_MIX for jb in jobs) == 2 * V
+    elif premapped:
+        assert head["has_mix"] == 1 and not any(jb["epi"] == EPI_MIX for jb in jobs)
     _check_tmem(head, jobs)
 
     g = torch.Generator().manual_seed(4)

@@ -78,3 +78,30 @@ def test_premapped_density_query():
     a1, m1 = ops.query_density(f1, pts.contiguous())
     assert torch.equal(m0, m1)
     assert (a0 - a1).abs().max().item() <= 1e-5 * max(1.0, a0.abs().max().item())
+
+
+@pytest.mark.parametrize("mode", ["dense", "culled"])
+def test_tmem_side_mix_matches_in_place_mix_and_oracle(mode, monkeypatch):
+    """Both forms of the attention mix of the pre-mapped chain program (csrc/mlp_chain.cu): in place on the fp16
+    operands by the mix warps (default) and on the accumulator side in TMEM (TH_CHAIN_MIX=tmem, fp32 combination of
+    kept accumulators in the EPI_MIX epilogue)."""
+    fr, tf, tokens = _frame()
+    S = 16
+    want = orc.render(tf, S, tokens=tokens) if mode == "dense" else \
+        orc.render_fast(tf, S, tokens=tokens, train_branch_max_rays=0)
+    m = ops.TH_RENDER_DENSE if mode == "dense" else ops.TH_RENDER_MASKED
+    f1, rays = frame_to_device(fr, tokens, DEV, premapped=True)
+    a = ops.render_rays(f1, *rays, S, mode=m, want_raw=True)
+    monkeypatch.setenv("TH_CHAIN_MIX", "tmem")
+    b = ops.render_rays(f1, *rays, S, mode=m, want_raw=True)
+    monkeypatch.setenv("TH_CHAIN_DBG", "240")                 # and under role jitter: bit-identical
+    c = ops.render_rays(f1, *rays, S, mode=m, want_raw=True)
+    monkeypatch.delenv("TH_CHAIN_DBG")
+    monkeypatch.delenv("TH_CHAIN_MIX")
+    torch.cuda.synchronize()
+    scale = max(1.0, want["raw"].abs().max().item())
+    for name, got in (("in place", a), ("tmem", b)):
+        assert (got["raw"].cpu() - want["raw"]).abs().max().item() <= 2e-5 * scale, name
+        assert (got["rgb_map"].cpu() - want["rgb_map"][0]).abs().max().item() <= 1e-4, name
+    assert torch.equal(b["raw"], c["raw"])
+    assert (a["raw"] - b["raw"]).abs().max().item() <= 1e-5 * scale

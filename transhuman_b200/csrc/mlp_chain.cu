@@ -30,6 +30,7 @@
 // image format are those of mlp_tc.cu.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -117,10 +118,15 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(uint32_t addr) {
 }
 // `nap` nanoseconds between polls: a spinning single thread otherwise competes for issue slots with
 // the epilogue warp that shares its scheduler.
+// Polls with RELAXED loads and acquires once at the end: an acquire load at cluster scope makes ptxas emit an L1
+// invalidation (CCTL.IVALL) per poll -- 34 M of them per launch in the round-1 kernel (ncu source page).
 __device__ __forceinline__ void wait_counter(uint32_t addr, uint32_t target, int what, unsigned nap = 32) {
   if ((int32_t)(ld_acquire_u32(addr) - target) >= 0) return;
   const long long t0 = clock64();
-  while ((int32_t)(ld_acquire_u32(addr) - target) < 0) {
+  while (true) {
+    if ((int32_t)(ld_relaxed_u32(addr) - target) >= 0) {
+      if ((int32_t)(ld_acquire_u32(addr) - target) >= 0) break;  // the acquire that orders the data behind the count
+    }
     __nanosleep(nap);
     if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
       printf("k_chain: counter wait timed out (block %d thread %d what %d target %u have %u)\n", blockIdx.x,
@@ -159,6 +165,16 @@ __device__ __forceinline__ void st16_keep(void* p, uint4 v) {
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x),
                "r"(v.y), "r"(v.z), "r"(v.w), "l"(L2_EVICT_LAST)
                : "memory");
+}
+// 16-byte asynchronous copy global -> shared (generic proxy), L1 bypassed, kept in L2
+__device__ __forceinline__ void cp_async16_keep(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(L2_EVICT_LAST)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ float ldcg_f32(const float* p) {
   float v;
@@ -213,7 +229,9 @@ __device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
 
 constexpr int STATS_PER_CTA = 32 + 3 * MAX_JOBS;  // role totals + per-job MMA waits
 constexpr int ATAB_LD = 9;  // attention table row stride (floats): V x V <= 9 entries per point
-constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 2 * 256 * 4 + 128 * ATAB_LD * 4 + 128 * 4 * 4 + 256;
+// stages | bias (2 x 256) | attention table | partial scores | control (256 B) | mix staging (96 B per mix thread)
+constexpr uint32_t MIX_RING_OFF = NSTAGE * STAGE_BYTES + 2 * 256 * 4 + 128 * ATAB_LD * 4 + 128 * 4 * 4 + 256;
+constexpr size_t SMEM_BYTES = (size_t)MIX_RING_OFF + (size_t)MIX_THREADS * 96;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     k_chain(const __grid_constant__ Program pg) {
@@ -295,76 +313,102 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         TH_TIMED(0, if (lane == 0) wait_counter(cnt_scores, 4u * (uint32_t)(it + 1), 1, 256); __syncwarp());
         const long long t_mix = clock64();
         fence_proxy_async_all();
+        if (pg.dbg & 1) {  // timing experiment: no mix at all (results wrong)
+          __syncwarp();
+          if (lane == 0)
+            for (int kb = 0; kb < 4; ++kb) add_release_local(cnt_mix + 4 * kb);
+          if (stats) tw[1] += clock64() - t_mix;
+          continue;
+        }
+        jitter(pg.dbg, 128);
+        // One stream of 4096 positions per unit (4 k-blocks x 128 rows x 8 chunks of 16 bytes; thread t takes
+        // t, t + 192, ...), software pipelined TWO positions deep with no drain at the k-block boundaries:
+        // while position p is mixed, p + 192 already sits in registers and the 2V 16-byte loads of p + 384 are
+        // in flight as cp.async copies into this thread's private 96-byte slot of shared memory (the mix is bound
+        // by the latency of its loads and by its ALU work, ncu: 46 % of its samples wait for the first use of a
+        // loaded value with one position in flight).  A warp's 32 positions never straddle a k-block (1024
+        // positions), so the warp publishes k-block kb when it has stored its last position of it.
+        const uint32_t ring = base + MIX_RING_OFF + (uint32_t)tid * 96u;
+        auto src_off = [&](int pos) {
+          return (uint32_t)(pos >> 10) * TILE_IMG + (uint32_t)((pos & 1023) >> 3) * 128u + (uint32_t)(pos & 7) * 16u;
+        };
+        auto stage = [&](int pos) {  // global -> shared, asynchronous, L1 bypassed, kept in L2
+          const uint32_t off = src_off(pos);
+#pragma unroll
+          for (int i = 0; i < CHAIN_MAX_V; ++i)
+            if (i < V) {
+              cp_async16_keep(ring + 32u * i, xbase + (size_t)i * xstride + off);
+              cp_async16_keep(ring + 32u * i + 16u, xbase + (size_t)i * xstride + off + A_TILE_BYTES);
+            }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto unstage = [&](uint4 (&h)[CHAIN_MAX_V], uint4 (&l)[CHAIN_MAX_V]) {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < CHAIN_MAX_V; ++i)
+            if (i < V) {
+              h[i] = lds16(ring + 32u * i);
+              l[i] = lds16(ring + 32u * i + 16u);
+            }
+        };
+        uint4 ch[CHAIN_MAX_V], cl[CHAIN_MAX_V], nh[CHAIN_MAX_V], nl[CHAIN_MAX_V];
+        stage(tid);
+        unstage(ch, cl);
+        if (tid + MIX_THREADS < 4096) stage(tid + MIX_THREADS);
 #pragma unroll 1
-        for (int kb = 0; kb < 4; ++kb) {
-          if (pg.dbg & 1) {
-            __syncwarp();
-            if (lane == 0) add_release_local(cnt_mix + 4 * kb);
-            continue;
+        for (int pos = tid; pos < 4096; pos += MIX_THREADS) {
+          const bool more = pos + MIX_THREADS < 4096;
+          if (more) {
+            unstage(nh, nl);                                              // p + 192: arrived during the last position
+            if (pos + 2 * MIX_THREADS < 4096) stage(pos + 2 * MIX_THREADS);  // p + 384: in flight during this one
           }
-          jitter(pg.dbg, 128);
-          // software pipelined over positions: the next position's 2V loads are in flight while
-          // this one is mixed and stored (positions are disjoint, so the order is free)
-          uint4 ch[CHAIN_MAX_V], cl[CHAIN_MAX_V], nh[CHAIN_MAX_V], nl[CHAIN_MAX_V];
-          auto fetch = [&](int pos, uint4 (&h)[CHAIN_MAX_V], uint4 (&l)[CHAIN_MAX_V]) {
-            const uint32_t off = (uint32_t)kb * TILE_IMG + (uint32_t)(pos >> 3) * 128 + (pos & 7) * 16;
+          const int row = (pos & 1023) >> 3;
+          const uint32_t off = src_off(pos);
+          float2 x[CHAIN_MAX_V][4];
 #pragma unroll
-            for (int i = 0; i < CHAIN_MAX_V; ++i)
-              if (i < V) {
-                h[i] = ldcg16(xbase + (size_t)i * xstride + off);
-                l[i] = ldcg16(xbase + (size_t)i * xstride + off + A_TILE_BYTES);
+          for (int i = 0; i < CHAIN_MAX_V; ++i)
+            if (i < V) {
+              x[i][0] = join2(ch[i].x, cl[i].x);
+              x[i][1] = join2(ch[i].y, cl[i].y);
+              x[i][2] = join2(ch[i].z, cl[i].z);
+              x[i][3] = join2(ch[i].w, cl[i].w);
+            }
+          const float* A = s_atab + row * ATAB_LD;
+#pragma unroll
+          for (int j = 0; j < CHAIN_MAX_V; ++j)
+            if (j < V) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 o = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < CHAIN_MAX_V; ++i)
+                  if (i < V) {
+                    const float a = A[i * V + j];
+                    o = fma2(make_float2(a, a), x[i][e], o);
+                  }
+                split2(o, hi[e], lo[e]);
               }
-          };
-          fetch(tid, ch, cl);
-#pragma unroll 1
-          for (int pos = tid; pos < 1024; pos += MIX_THREADS) {
-            const bool more = pos + MIX_THREADS < 1024;
-            if (more) fetch(pos + MIX_THREADS, nh, nl);
-            const int row = pos >> 3;
-            const uint32_t off = (uint32_t)kb * TILE_IMG + (uint32_t)row * 128 + (pos & 7) * 16;
-            float2 x[CHAIN_MAX_V][4];
+              unsigned char* dst = xbase + (size_t)j * xstride + off;
+              st16_keep(dst, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+              st16_keep(dst + A_TILE_BYTES, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            }
+          // last position of this warp in its k-block -> publish the k-block (one counter per k-block)
+          if (!more || ((pos + MIX_THREADS) >> 10) != (pos >> 10)) {
+            if (pg.dbg & 512) {
+              __threadfence();
+              fence_proxy_async_all();
+            }
+            __syncwarp();
+            if (lane == 0) add_release_local(cnt_mix + 4 * (pos >> 10));
+          }
+          if (more) {
 #pragma unroll
-            for (int i = 0; i < CHAIN_MAX_V; ++i)
-              if (i < V) {
-                x[i][0] = join2(ch[i].x, cl[i].x);
-                x[i][1] = join2(ch[i].y, cl[i].y);
-                x[i][2] = join2(ch[i].z, cl[i].z);
-                x[i][3] = join2(ch[i].w, cl[i].w);
-              }
-            const float* A = s_atab + row * ATAB_LD;
-#pragma unroll
-            for (int j = 0; j < CHAIN_MAX_V; ++j)
-              if (j < V) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 o = make_float2(0.f, 0.f);
-#pragma unroll
-                  for (int i = 0; i < CHAIN_MAX_V; ++i)
-                    if (i < V) {
-                      const float a = A[i * V + j];
-                      o = fma2(make_float2(a, a), x[i][e], o);
-                    }
-                  split2(o, hi[e], lo[e]);
-                }
-                unsigned char* dst = xbase + (size_t)j * xstride + off;
-                st16_keep(dst, make_uint4(hi[0], hi[1], hi[2], hi[3]));
-                st16_keep(dst + A_TILE_BYTES, make_uint4(lo[0], lo[1], lo[2], lo[3]));
-              }
-            if (more) {
-#pragma unroll
-              for (int i = 0; i < CHAIN_MAX_V; ++i) {
-                ch[i] = nh[i];
-                cl[i] = nl[i];
-              }
+            for (int i = 0; i < CHAIN_MAX_V; ++i) {
+              ch[i] = nh[i];
+              cl[i] = nl[i];
             }
           }
-          if (pg.dbg & 512) {
-            __threadfence();
-            fence_proxy_async_all();
-          }
-          __syncwarp();
-          if (lane == 0) add_release_local(cnt_mix + 4 * kb);
         }
         if (stats) tw[1] += clock64() - t_mix;
       }
@@ -909,10 +953,13 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     B.pg.ks_col[2] = 0;
     B.pg.kp_col = 128;
   }
-  // TMEM-side attention mix (pre-mapped program; TH_CHAIN_INPLACE_MIX=1 keeps the in-place operand mix by the idle
-  // warps for A/B measurements): see the job list below
-  static const bool inplace_mix = getenv("TH_CHAIN_INPLACE_MIX") && atoi(getenv("TH_CHAIN_INPLACE_MIX"));
-  const bool tmix = x_in_chunk && !inplace_mix;
+  // Two forms of the attention mix in the pre-mapped program (both parity-green, measured in profiles/README.md):
+  // in place on the fp16 operands by the six mix warps (default: 3 % fewer cycles), or on the accumulator side in
+  // TMEM (TH_CHAIN_MIX=tmem): see the job list below
+  // run.premapped: 1 = default (env TH_CHAIN_MIX = "tmem" | "inplace" decides, read per call so that tests can
+  // toggle it), 2 = TMEM-side mix, 3 = in-place mix
+  const char* mix_env = getenv("TH_CHAIN_MIX");
+  const bool tmix = x_in_chunk && (run.premapped == 2 || (run.premapped == 1 && mix_env && !strcmp(mix_env, "tmem")));
   uint64_t mix_y_img[MAX_JOBS] = {0};  // EPI_MIX jobs: weight image of the Y jobs they combine (for acc_scale2)
   int j_ks[TH_MAX_VIEWS];
   for (int v = 0; v < V; ++v)
