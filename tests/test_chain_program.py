@@ -32,13 +32,15 @@ def _program(lib, blob, V, P, alpha_only, premapped):
     for j in range(int(head[0])):
         t = table[8 + j * (16 + 6 * MAX_SEG):8 + (j + 1) * (16 + 6 * MAX_SEG)]
         keys = ["N", "relu", "epi", "out_off", "tmem_col", "wait_back", "view", "nseg", "nkb", "wimg", "bias", "bias2",
-                "reader"]
+                "reader", "shift", "out_aset"]
         job = {k: int(t[i]) for i, k in enumerate(keys)}
         job["segs"] = [dict(zip(["chunk", "off", "tile_off", "kbs", "dep", "dep_mix"], map(int, t[16 + 6 * s:22 + 6 * s])))
                        for s in range(job["nseg"])]
+        for sg in job["segs"]:
+            sg["aset"], sg["dep_mix"] = sg["dep_mix"] >> 1, sg["dep_mix"] & 1
         jobs.append(job)
     return {"njobs": int(head[0]), "V": int(head[1]), "has_mix": int(head[2]), "alpha_only": int(head[3]),
-            "Pp": int(head[4]), "scr_act": int(head[5]), "tile_img": int(head[6])}, jobs
+            "Pp": int(head[4]), "scr_act": int(head[5]), "tile_img": int(head[6]), "deferred": int(head[7])}, jobs
 
 
 def _images(blob, V):
@@ -57,33 +59,92 @@ def _images(blob, V):
     return {n: (o, shapes[n]) for n, o in img.items()}
 
 
+def _executed(head, jobs, n_units=4):
+    """The job sequence one cluster executes for n_units units: iteration `it` runs the shift-0 jobs of unit `it` and
+    the shift -1 (deferred tail) jobs of unit `it - 1`; a deferred tail needs one draining iteration."""
+    n_iter = n_units + (1 if head["deferred"] else 0)
+    return [(j, it, it + jb["shift"]) for it in range(n_iter) for j, jb in enumerate(jobs)
+            if 0 <= it + jb["shift"] < n_units]
+
+
 def _check_tmem(head, jobs):
-    """No job's MMAs may overwrite TMEM columns that an earlier epilogue can still read: job G starts after
-    the epilogue of job G - wait_back; kept key embeds are read by every score epilogue."""
+    """No job's MMAs may overwrite TMEM columns that an earlier epilogue can still read: executed job number G starts
+    after the epilogue of executed job number G - wait_back; a kept accumulator (key embeds, Y_i of the TMEM-side
+    mix) is read until the last score / mix epilogue of its unit."""
     n = head["njobs"]
     flip_on = 256 if n & 1 else 0
-    seq = []
-    for unit in range(3):
-        for j, jb in enumerate(jobs):
-            col = (jb["tmem_col"] + (flip_on if unit & 1 else 0)) & 511
-            assert col + jb["N"] <= 512
-            last = j
-            if jb["epi"] == EPI_KEEP:   # independent of the builder's bookkeeping: who reads a kept accumulator?
-                k = j + 1
-                while jobs[k]["epi"] == EPI_KEEP:
-                    k += 1
-                kind = jobs[k]["epi"]                             # key embeds -> scores, Y_i -> the mix epilogues
-                assert kind in (EPI_SCORES, EPI_MIX)
-                while k + 1 < n and jobs[k + 1]["epi"] == kind:
-                    k += 1
-                last = k                                          # the last job of that contiguous run
-                assert jb["reader"] == last, (j, jb["reader"], last)
-            seq.append((col, col + jb["N"], unit * n + last, jb["wait_back"]))
-    for g, (c0, c1, _, wb) in enumerate(seq):
+    seq = _executed(head, jobs)
+    where = {(j, ui): g for g, (j, it, ui) in enumerate(seq)}
+    last_reader = {}
+    for j, jb in enumerate(jobs):
+        last = j
+        if jb["epi"] == EPI_KEEP:   # independent of the builder's bookkeeping: who reads a kept accumulator?
+            k = j + 1
+            while jobs[k]["epi"] == EPI_KEEP:
+                k += 1
+            kind = jobs[k]["epi"]                             # key embeds -> scores, Y_i -> the mix epilogues
+            assert kind in (EPI_SCORES, EPI_MIX)
+            while k + 1 < n and jobs[k + 1]["epi"] == kind:
+                k += 1
+            last = k                                          # the last job of that contiguous run
+            assert jb["reader"] == last and jobs[last]["shift"] == jb["shift"], (j, jb["reader"], last)
+        last_reader[j] = last
+    for g, (j, it, ui) in enumerate(seq):
+        c0 = (jobs[j]["tmem_col"] + (flip_on if it & 1 else 0)) & 511
+        c1 = c0 + jobs[j]["N"]
+        assert c1 <= 512
         for a in range(g):
-            a0, a1, reader, _ = seq[a]
-            if a0 < c1 and c0 < a1:
-                assert g - wb >= reader, f"job {g} (wait_back {wb}) overwrites columns job {a} is read from until {reader}"
+            ja, ita, uia = seq[a]
+            a0 = (jobs[ja]["tmem_col"] + (flip_on if ita & 1 else 0)) & 511
+            if a0 < c1 and c0 < a0 + jobs[ja]["N"]:
+                reader = where[(last_reader[ja], uia)]
+                assert g - jobs[j]["wait_back"] >= reader, \
+                    f"executed job {g} (job {j}, wait_back {jobs[j]['wait_back']}) overwrites columns job {ja} is read from until {reader}"
+
+
+def _check_scratch(head, jobs):
+    """Scratch tiles across units (deferred tail): a tile may only be overwritten by an epilogue when every job that
+    reads the old contents has been ISSUED earlier (MMAs complete in order, and an epilogue stores after its own job's
+    MMAs).  Slot set A alternates with the unit's parity, slot B does not."""
+    V, scr = head["V"], head["scr_act"]
+    seq = _executed(head, jobs)
+
+    def tiles(off, aset, ui, nbytes):
+        base = off + (V * scr if (aset and ui & 1) else 0)
+        return set(range(base // head["tile_img"], (base + nbytes + head["tile_img"] - 1) // head["tile_img"]))
+
+    writes, reads = [], []          # (exec index, tiles)
+    for g, (j, it, ui) in enumerate(seq):
+        jb = jobs[j]
+        for sg in jb["segs"]:
+            if not sg["chunk"]:
+                reads.append((g, tiles(sg["off"], sg["aset"], ui, sg["kbs"] * head["tile_img"]), j))
+        if jb["epi"] in (EPI_IMG, EPI_MIX):
+            writes.append((g, tiles(jb["out_off"], jb["out_aset"], ui, jb["N"] // 64 * head["tile_img"]), j, ui))
+    for gw, tw, jw, uiw in writes:
+        # readers of the PREVIOUS contents: reads executed after the previous write of the tile and before this one must
+        # all precede gw in issue order (trivially true) -- the hazard is a reader issued AFTER gw that wants the OLD data
+        for gr, tr, jr in reads:
+            if gr > gw and tr & tw:
+                # it must be a legitimate consumer of THIS write: its segment names jw as producer, or re-reads in place
+                deps = {sg["dep"] for sg in jobs[jr]["segs"] if not sg["chunk"]}
+                later_writer = any(g2 > gw and g2 < gr and (t2 & tr & tw) for g2, t2, _, _ in writes)
+                assert jw in deps or later_writer or -1 in deps, (jw, jr, sorted(tr & tw)[:3])
+
+
+def _slot(head, off):
+    """(slot key, first k-block) of a scratch offset.  Slot A(v) at v * scr; slot B(v) behind it -- at full tile size,
+    or, in the deferred-tail layout, at half size behind BOTH parity copies of slot set A."""
+    V, scr = head["V"], head["scr_act"]
+    if off < V * scr:
+        key, inside = ("A", off // scr), off % scr
+    elif head["deferred"]:
+        assert off >= 2 * V * scr
+        key, inside = ("B", (off - 2 * V * scr) // (scr // 2)), (off - 2 * V * scr) % (scr // 2)
+    else:
+        key, inside = ("B", (off - V * scr) // scr), (off - V * scr) % scr
+    assert inside % head["tile_img"] == 0
+    return key, inside // head["tile_img"]
 
 
 def _interpret(blob, head, jobs, data):
@@ -100,7 +161,10 @@ def _interpret(blob, head, jobs, data):
     kept, scores, alpha, out_final, Aw = {}, {}, None, None, None
     data = dict(data)
     mixed_in_chunk = False
-    for j, jb in enumerate(jobs):
+    # one unit: its shift-0 jobs in program order, then its deferred (shift -1) jobs, as the kernel runs them
+    order = [j for j, jb in enumerate(jobs) if jb["shift"] == 0] + [j for j, jb in enumerate(jobs) if jb["shift"] == -1]
+    for j in order:
+        jb = jobs[j]
         parts = []
         for sg in jb["segs"]:
             C_ = sg["kbs"] * 64
@@ -113,13 +177,13 @@ def _interpret(blob, head, jobs, data):
                 assert buf.shape[-1] == C_, (j, name, buf.shape, C_)
                 parts.append(buf[view if buf.shape[0] > 1 else 0])
             else:
-                slot, kb0 = sg["off"] // scr, (sg["off"] % scr) // head["tile_img"]
-                assert (sg["off"] % scr) % head["tile_img"] == 0
+                slot, kb0 = _slot(head, sg["off"])
                 assert slot in slots, f"job {j} reads scratch slot {slot} before anything stored it"
+                assert bool(sg["aset"]) == bool(head["deferred"] and slot[0] == "A")
                 if sg["dep"] >= 0:
                     for kb in range(kb0, kb0 + sg["kbs"]):
-                        assert written_by[(slot, kb)] == sg["dep"] < j, (j, slot, kb, written_by[(slot, kb)], sg["dep"])
-                assert bool(sg["dep_mix"]) == (head["has_mix"] == 1 and slot >= V and
+                        assert written_by[(slot, kb)] == sg["dep"], (j, slot, kb, written_by[(slot, kb)], sg["dep"])
+                assert bool(sg["dep_mix"]) == (head["has_mix"] == 1 and slot[0] == "B" and
                                                jobs[written_by[(slot, kb0)]]["epi"] == EPI_IMG
                                                and jb["epi"] == EPI_IMG and jb["N"] == 256 and len(jb["segs"]) == 2)
                 parts.append(slots[slot][:, 64 * kb0:64 * kb0 + C_])
@@ -139,8 +203,8 @@ def _interpret(blob, head, jobs, data):
                 assert Aw is not None and len(kept) == V
                 out = out + sum(Aw[:, i, jb["view"], None] * kept[i] for i in range(V))
             out = torch.relu(out) if jb["relu"] else out
-            slot, kb0 = jb["out_off"] // scr, (jb["out_off"] % scr) // head["tile_img"]
-            assert (jb["out_off"] % scr) % head["tile_img"] == 0 and 64 * kb0 + N <= 256
+            slot, kb0 = _slot(head, jb["out_off"])
+            assert 64 * kb0 + N <= 256 and bool(jb["out_aset"]) == bool(head["deferred"] and slot[0] == "A")
             if slot not in slots or jb["epi"] == EPI_IMG:
                 slots[slot] = torch.zeros((out.shape[0], 256), dtype=torch.float64)   # a whole new tile
             slots[slot][:, 64 * kb0:64 * kb0 + N] = out
@@ -158,11 +222,11 @@ def _interpret(blob, head, jobs, data):
                 S_ = torch.stack([torch.stack([scores[(i, jv)] for jv in range(V)], -1) for i in range(V)], 1)  # (P,i,j)
                 Aw = torch.softmax(S_, dim=1)
                 kept = {}                                        # the key embeds are dead once the scores exist
-                if head["has_mix"] == 1 and (V in slots):
-                    X = torch.stack([slots[V + i] for i in range(V)], 0)                      # (i,P,256)
+                if head["has_mix"] == 1 and (("B", 0) in slots):
+                    X = torch.stack([slots[("B", i)] for i in range(V)], 0)                   # (i,P,256)
                     XT = torch.einsum("pij,ipc->jpc", Aw, X)
                     for jv in range(V):
-                        slots[V + jv] = XT[jv]
+                        slots[("B", jv)] = XT[jv]
                 elif head["has_mix"] == 1:  # no X jobs: the mix works on the X tiles of the chunk image
                     data["pix"] = torch.einsum("pij,ipc->jpc", Aw, data["pix"])
                     mixed_in_chunk = True
@@ -194,6 +258,9 @@ def test_chain_program(lib, V, variant):
     elif premapped:
         assert head["has_mix"] == 1 and not any(jb["epi"] == EPI_MIX for jb in jobs)
     _check_tmem(head, jobs)
+    _check_scratch(head, jobs)
+    if variant in ("premapped", "premapped_alpha_only"):      # the default program defers the tail by one unit
+        assert head["deferred"] == 1 and sum(jb["shift"] == -1 for jb in jobs) == (1 if alpha_only else V + 2)
 
     g = torch.Generator().manual_seed(4)
     rep = torch.randn((V, 255, P), generator=g, dtype=torch.float64)

@@ -53,7 +53,8 @@ constexpr uint32_t TILE_IMG = 2 * A_TILE_BYTES;       // one 128-row x 64-column
 constexpr uint32_t SCR_ACT = 4 * TILE_IMG;            // a 256-wide activation tile: 128 KB
 constexpr int CHAIN_MAX_V = 3;                        // V key embeds + one more must fit 512 TMEM columns
 // Per-CTA scratch for V views: slot A (S -> N1 -> INTER) and slot B (X -> XT -> G), V tiles each.
-__host__ __device__ inline uint32_t scratch_stride(int V) { return 2u * (uint32_t)V * SCR_ACT; }
+// (deferred-tail program: slot set A twice -- it alternates with the unit's parity -- and slot B at half size, G only)
+__host__ __device__ inline uint32_t scratch_stride(int V) { return 2u * (uint32_t)V * SCR_ACT + (uint32_t)V * (SCR_ACT / 2); }
 
 // EPI_MIX: the attention mix on the ACCUMULATOR side (pre-mapped program): out = relu(Z + b + sum_i A[i][j] Y_i) with
 // Z = this job's accumulator (the S part of fc_1', view j) and Y_i = kept accumulators of the X part for every view i
@@ -67,6 +68,7 @@ struct Seg {
   int32_t dep;      // job (same unit) whose stored output this segment reads, -1 = chunk input
   int32_t dep_mix;  // 1 = written by the mix warps, released per k-block
   int32_t keep;     // chunk input that a later job of the unit reads again: keep it in L2 (default: evict first)
+  int32_t aset;     // scratch segment in slot set A, which alternates with the unit's parity (deferred-tail program)
 };
 struct Job {
   Seg seg[MAX_SEG];
@@ -78,6 +80,12 @@ struct Job {
   const float* acc_scale;   // DEVICE pointer to the 2^-e of this job's weight image (img_inv_scale_ptr): acc * scale + bias
   const float* acc_scale2;  // EPI_SCORES: the scale of the kept key embeds' weight image; EPI_MIX: of the Y jobs'
   int32_t reader;           // host only: last job whose epilogue reads this accumulator (-1 = its own epilogue)
+  // Software pipelining across units: a job with shift = -1 belongs to the unit of the PREVIOUS iteration (the tail
+  // of the network -- fc_3, view_fc', fc_4' and the heads -- is issued into the next unit's attention-mix window,
+  // where the tensor pipe would otherwise wait for the mix warps).  Iteration `it` of a cluster runs the shift-0
+  // jobs of its unit number `it` and the shift -1 jobs of unit number `it - 1`; one extra iteration drains the tail.
+  int32_t shift;
+  int32_t out_aset;         // out_off lies in slot set A (alternates with the unit's parity)
 };
 struct Program {
   // TMA descriptors: tile images as rows of 64 fp16 (128 B).  tm_a: box 256 rows (one 32 KB hi|lo
@@ -99,6 +107,7 @@ struct Program {
   unsigned char* x_img;
   int64_t x_view_stride;
   int32_t njobs, num_units, V, has_mix, zero_rgb, alpha_only, kp_col;
+  int32_t deferred_tail;  // 1 = the program has shift -1 jobs (and two alternating A slot sets)
   int32_t ks_col[TH_MAX_VIEWS];
   int32_t dbg;  // TH_CHAIN_DBG: timing experiments only, 1 = skip the mix, 2 = skip the store fences (results wrong); 16/32/64/128 = random delays in the loader / MMA / epilogue / mix role, 512 = writer-side fences as well (results valid)
   unsigned long long* stats;  // TH_CHAIN_STATS=1: per-CTA wait-time counters (cycles), else nullptr
@@ -255,6 +264,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   const int njobs = pg.njobs, V = pg.V;
   const uint32_t flip_on = (njobs & 1) ? 256u : 0u;  // odd programs alternate TMEM halves from unit to unit
   unsigned char* scratch = pg.scratch + (size_t)blockIdx.x * scratch_stride(V);
+  // units of this cluster, and iterations of its job loop (one more when the tail is deferred)
+  const int n_units_mine = cluster_id < pg.num_units ? (pg.num_units - cluster_id + nclusters - 1) / nclusters : 0;
+  const int n_iter = n_units_mine + ((pg.deferred_tail && n_units_mine > 0) ? 1 : 0);
+  const uint32_t aset_bytes = (uint32_t)V * SCR_ACT;  // distance between the two A slot sets
 
   if (tid == 0) {
     if (base & 1023u) {
@@ -420,19 +433,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     // because at ~6 cycles per dependent instruction a long path makes the loader the bottleneck.
     if (lane == 0) {
       uint32_t s = 0, ph = 0;  // stage index and its phase bit
-      const int n_it_loader = cluster_id < pg.num_units ? (pg.num_units - cluster_id + nclusters - 1) / nclusters : 0;
-      for (int it = 0; it < n_it_loader; ++it) {
-        const int u = cluster_id + it * nclusters;
-        const int64_t ptile = 2 * (int64_t)u + rank;
-        const uint32_t done_target = (uint32_t)EPI_WARPS * (uint32_t)(it + 1);
+      for (int it = 0; it < n_iter; ++it) {
         const uint32_t mix_target = (uint32_t)(MIX_THREADS / 32) * (uint32_t)(it + 1);
-        // What this thread's fences already cover in this unit: bit j = the tile job j stored, bit kb = the
+        // What this thread's fences already cover in this iteration: bit j = the tile job j stored, bit kb = the
         // mix of k-block kb.  A fence executed after a counter was seen complete orders those stores before
         // every later copy, so each dependency costs one wait + fence per unit, not one per reader -- a
         // fence is ~1-2 kcycles here and sits between "tile stored" and the dependent job's first copy.
         uint32_t dep_seen = 0, mix_seen = 0;
         for (int j = 0; j < njobs; ++j) {
           const Job& jb = pg.job[j];
+          const int ui = it + jb.shift;  // which of this cluster's units the job works on
+          if (ui < 0 || ui >= n_units_mine) continue;
+          const int u = cluster_id + ui * nclusters;
+          const int64_t ptile = 2 * (int64_t)u + rank;
+          // job D (shift s_D) has run it + s_D + 1 times once it is done for the unit the shift-s_D jobs of this
+          // iteration work on; a consumer needs its producers' outputs for ITS unit: it + shift + 1 executions
+          // (a deferred consumer of a shift-0 producer needs one execution less than the producer's own class)
+          const uint32_t done_target = (uint32_t)EPI_WARPS * (uint32_t)(it + jb.shift + 1);
+          const uint32_t aset_off = (ui & 1) ? aset_bytes : 0u;
           const uint32_t b_bytes = (uint32_t)jb.N * 128u;  // N/2 rows x 128 B x (hi, lo)
           const unsigned char* w = jb.wimg + (size_t)rank * b_bytes;
           const uint32_t w_step = 2u * b_bytes, tx = TILE_IMG + b_bytes;
@@ -443,15 +461,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             const int kbs = sg.kbs, dep_mix = sg.dep_mix;
             const bool from_chunk = sg.img != nullptr;
             const unsigned char* src = from_chunk ? sg.img + (size_t)(sg.tile_off + ptile) * kbs * TILE_IMG
-                                                  : scratch + sg.scratch_off;
+                                                  : scratch + sg.scratch_off + (sg.aset ? aset_off : 0u);
             // chunk inputs stream through L2 once (evict first); scratch tiles and weights are the
             // working set that should stay resident (evict last)
             const uint64_t pol = (from_chunk && !sg.keep) ? L2_EVICT_FIRST : L2_EVICT_LAST;
             if (sg.dep >= 0 && !((dep_seen >> sg.dep) & 1u)) {
               TH_TIMED(0, wait_counter(cnt_job + 4 * sg.dep, done_target, 2));
               // whatever else is stored by now rides on the same fence
-              for (int j2 = 0; j2 < njobs; ++j2)
-                if ((int32_t)(ld_relaxed_u32(cnt_job + 4 * j2) - done_target) >= 0) dep_seen |= 1u << j2;
+              for (int j2 = 0; j2 < njobs; ++j2)  // (each producer against the count of ITS class: conservative)
+                if ((int32_t)(ld_relaxed_u32(cnt_job + 4 * j2) -
+                              (uint32_t)EPI_WARPS * (uint32_t)(it + pg.job[j2].shift + 1)) >= 0)
+                  dep_seen |= 1u << j2;
               // cumulative: covers the epilogue warps' stores observed through the counters
               TH_TIMED(4, __threadfence(); fence_proxy_async_all());
             }
@@ -488,11 +508,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
       if (rank == 0) {
         // ===================== MMA issuer (leader CTA) =====================
         uint32_t s = 0, ph = 0, G = 0;
-        int it = 0;
-        for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
+        for (int it = 0; it < n_iter; ++it) {
           const uint32_t flip = (it & 1) ? flip_on : 0u;
-          for (int j = 0; j < njobs; ++j, ++G) {
+          for (int j = 0; j < njobs; ++j) {
             const Job& jb = pg.job[j];
+            if (it + jb.shift < 0 || it + jb.shift >= n_units_mine) continue;  // (G counts executed jobs)
             jitter(pg.dbg, 32);
             const long long w0 = tw[0], w1 = tw[1], w2 = tw[2];
             if ((int32_t)(G - jb.wait_back) >= 0) {
@@ -531,6 +551,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
               stats[32 + 3 * j + 1] += (unsigned long long)(tw[1] - w1);
               stats[32 + 3 * j + 2] += (unsigned long long)(tw[2] - w2);
             }
+            ++G;
           }
         }
       } else {
@@ -547,13 +568,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     float* atab = s_atab + et * ATAB_LD;
     float alpha_reg = 0.f;
     uint32_t G = 0;
-    int it = 0;
-    for (int u = cluster_id; u < pg.num_units; u += nclusters, ++it) {
+    for (int it = 0; it < n_iter; ++it) {
       const uint32_t flip = (it & 1) ? flip_on : 0u;
-      const int64_t ptile = 2 * (int64_t)u + rank;
-      const int64_t pt = ptile * BM + et;  // chunk-local point of this thread (per-point jobs)
-      for (int j = 0; j < njobs; ++j, ++G) {
+      for (int j = 0; j < njobs; ++j) {
         const Job& jb = pg.job[j];
+        const int ui = it + jb.shift;
+        if (ui < 0 || ui >= n_units_mine) continue;
+        const int64_t ptile = 2 * (int64_t)(cluster_id + ui * nclusters) + rank;
+        const int64_t pt = ptile * BM + et;  // chunk-local point of this thread (per-point jobs)
+        const uint32_t out_aset_off = (jb.out_aset && (ui & 1)) ? aset_bytes : 0u;
         const int N = jb.N, epi = jb.epi;
         float* bias_s = s_bias + (G & 1) * 256;
         // this job's bias -> shared memory (double buffered by job parity; the named barrier of EVERY
@@ -573,7 +596,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           // bias / ReLU / fp16 hi-lo split straight from the accumulator to the scratch tile image:
           // a thread owns one row; 16 columns = one 32-byte sector of the hi plane and one of the lo
           // plane (the 128-byte swizzle permutes 16-byte chunks inside a sector pair-wise).
-          unsigned char* out = scratch + jb.out_off + (size_t)et * 128;
+          unsigned char* out = scratch + jb.out_off + out_aset_off + (size_t)et * 128;
           const int ncol = N >> 1, cbeg = grp * ncol;
           const bool swap = (et & 1) != 0;
           const bool relu = jb.relu != 0;
@@ -795,6 +818,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           else
             add_release_remote(cnt_epi_peer, 0);
         }
+        ++G;
       }
     }
   }
@@ -1003,23 +1027,14 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     for (int v = 0; v < V; ++v)
       j_int[v] = B.add({Builder::scr(B.slotB(v), 128, j_z[v][0]), Builder::scr(B.slotB(v) + 2u * TILE_IMG, 128, j_z[v][1])},
                        wimg(h.h_fc2), wf(h.fc2_b), 256, 1, EPI_IMG, B.slotA(v));
-  } else {
-    B.pg.has_mix = 1;
-    // N1_v = relu([S_v | XT_v] W_fc1f^T) in place of S_v; INTER_v = relu(fc_2 N1_v) in place again
-    for (int v = 0; v < V; ++v) {
-      Seg xt = x_in_chunk ? B.in_view(b.pix, 256, v) : Builder::scr(B.slotB(v), 256, -1, 1);
-      xt.dep_mix = 1;  // mixed in place (scratch slot B, or the chunk image), released per k-block
-      j_n1[v] = B.add({Builder::scr(B.slotA(v), 256, -1), xt}, wimg(h.h_fc1f), wf(h.fc1f_b), 256, 1, EPI_IMG,
-                      B.slotA(v), v, -1, v == 0 ? 1 : 2);
-    }
-    if (x_in_chunk) {
-      B.pg.x_img = reinterpret_cast<unsigned char*>(const_cast<float*>(b.pix));
-      B.pg.x_view_stride = (int64_t)(Pp / 128) * 4 * TILE_IMG;
-    }
-    for (int v = 0; v < V; ++v)
-      j_int[v] = B.add({Builder::scr(B.slotA(v), 256, j_n1[v])}, wimg(h.h_fc2), wf(h.fc2_b), 256, 1, EPI_IMG,
-                       B.slotA(v));
   }
+  // Deferred tail (pre-mapped program with the in-place mix; TH_CHAIN_DEFER=0 disables it): the jobs after fc_2 --
+  // fc_3 + alpha head, view_fc' per view, fc_4' + rgb head, ~40 kcycles of tensor work per unit -- are issued one
+  // iteration LATE, between the score jobs and fc_1' of the NEXT unit, i.e. into the ~45 kcycles in which the tensor
+  // pipe waited for the mix warps (TH_CHAIN_STATS).  INTER of the previous unit must then outlive S / N1 of the
+  // current one: slot set A exists twice and alternates with the unit's parity.
+  const char* defer_env = getenv("TH_CHAIN_DEFER");
+  const bool defer = x_in_chunk && !tmix && !(defer_env && !atoi(defer_env));
   auto add_fc3 = [&]() {
     const int j = B.pg.njobs++;
     Job& jb = B.pg.job[j];
@@ -1037,9 +1052,11 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     jb.wait_back = 2;
     jb.reader = -1;
   };
-  if (run.alpha_only) {
-    add_fc3();
-  } else {
+  auto add_tail = [&]() {
+    if (run.alpha_only) {
+      add_fc3();
+      return;
+    }
     auto add_gvf = [&](int v) {
       j_g[v] = pre ? B.add({Builder::scr(B.slotA(v), 256, j_int[v]), B.in_view(p2_img, 128, v), B.in_point(b.vd, 64)},
                            wimg(h.h_gvfp), wf(h.gvfp_b), 128, 1, EPI_IMG, B.slotB(v))
@@ -1050,7 +1067,7 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     for (int v = 0; v + 1 < V; ++v) add_gvf(v);
     add_fc3();
     add_gvf(V - 1);
-    {  // T = relu([mean pix | G_0 | ... ] W_t^T): the chunk input first, the freshest G last
+    {  // T = relu([G_0 | ... | mean pix or R] W_t^T)
       const int j = B.pg.njobs++;
       Job& jb = B.pg.job[j];
       jb = Job{};
@@ -1070,6 +1087,64 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
       jb.wait_back = 2;
       jb.reader = -1;
     }
+  };
+  const int first_tail = B.pg.njobs;
+  int n_tail = 0;
+  if (defer) {
+    n_tail = run.alpha_only ? 1 : V + 2;
+    for (int v = 0; v < V; ++v) j_int[v] = first_tail + n_tail + V + v;  // the indices fc_2's jobs WILL get
+    add_tail();
+    if (B.pg.njobs != first_tail + n_tail) {
+      set_error("mlp_forward_chain: internal error (tail job count)");
+      return TH_EINVAL;
+    }
+  }
+  if (!tmix) {
+    B.pg.has_mix = 1;
+    // N1_v = relu([S_v | XT_v] W_fc1f^T) in place of S_v; INTER_v = relu(fc_2 N1_v) in place again
+    for (int v = 0; v < V; ++v) {
+      Seg xt = x_in_chunk ? B.in_view(b.pix, 256, v) : Builder::scr(B.slotB(v), 256, -1, 1);
+      xt.dep_mix = 1;  // mixed in place (scratch slot B, or the chunk image), released per k-block
+      j_n1[v] = B.add({Builder::scr(B.slotA(v), 256, -1), xt}, wimg(h.h_fc1f), wf(h.fc1f_b), 256, 1, EPI_IMG,
+                      B.slotA(v), v, -1, v == 0 ? 1 : 2);
+    }
+    if (x_in_chunk) {
+      B.pg.x_img = reinterpret_cast<unsigned char*>(const_cast<float*>(b.pix));
+      B.pg.x_view_stride = (int64_t)(Pp / 128) * 4 * TILE_IMG;
+    }
+    for (int v = 0; v < V; ++v) {
+      const int j = B.add({Builder::scr(B.slotA(v), 256, j_n1[v])}, wimg(h.h_fc2), wf(h.fc2_b), 256, 1, EPI_IMG,
+                          B.slotA(v));
+      if (defer && j != j_int[v]) {
+        set_error("mlp_forward_chain: internal error (fc_2 job index)");
+        return TH_EINVAL;
+      }
+      j_int[v] = j;
+    }
+  }
+  if (!defer) add_tail();
+  if (defer) {
+    B.pg.deferred_tail = 1;
+    const uint32_t a_end = (uint32_t)V * SCR_ACT, b_end = 2u * a_end;
+    auto remap = [&](uint32_t off, int32_t* aset) {   // slot A -> parity-alternating set; slot B -> behind both A sets
+      if (off < a_end) {
+        *aset = 1;
+        return off;
+      }
+      const uint32_t v = (off - a_end) / SCR_ACT, in = (off - a_end) % SCR_ACT;
+      *aset = 0;
+      return b_end + v * (SCR_ACT / 2) + in;
+    };
+    for (int j = 0; j < B.pg.njobs; ++j) {
+      Job& jb = B.pg.job[j];
+      jb.shift = (j >= first_tail && j < first_tail + n_tail) ? -1 : 0;
+      for (int sgi = 0; sgi < jb.nseg; ++sgi)
+        if (!jb.seg[sgi].img) jb.seg[sgi].scratch_off = remap(jb.seg[sgi].scratch_off, &jb.seg[sgi].aset);
+      if (jb.epi == EPI_IMG) jb.out_off = remap(jb.out_off, &jb.out_aset);
+      if (jb.tmem_col == (((j - (jb.shift ? 0 : 0)) & 1) * 256) && jb.epi != EPI_KEEP && jb.epi != EPI_SCORES) {
+        // auto columns stay (j & 1) * 256 of the FINAL position (Builder::add used the final index already)
+      }
+    }
   }
   Program& pg = B.pg;
   for (int j = 0; j < pg.njobs; ++j) {  // accumulator scales of the weight images (PackedHeader::img_inv_scale)
@@ -1081,27 +1156,43 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     }
   }
   if (x_in_chunk) {
-    // Without the X jobs the hand-set TMEM waits above no longer match the job parity: derive them.
-    // Job G may start once the epilogue of job G - wait_back is done, so wait_back = G - (the last job
-    // whose epilogue still reads columns that G overwrites); kept key embeds are read by every score job.
-    const int n = pg.njobs;
+    // TMEM waits, derived: the MMA issuer may start executed job number G once the epilogue of executed job number
+    // G - wait_back is done.  Walk the sequence the kernel executes (four units of one cluster, with the skipped
+    // jobs of the first iteration and the draining iteration of a deferred tail), and for every job take the
+    // smallest distance to the last reader of any accumulator whose columns it overwrites: its own epilogue, or
+    // for a kept accumulator the last score / mix epilogue of its unit.
+    const int n = pg.njobs, n_units = 4, n_iter = n_units + (pg.deferred_tail ? 1 : 0);
     const uint32_t flip_on_h = (n & 1) ? 256u : 0u;
-    for (int j = 0; j < n; ++j) {
-      int wb = n;  // nothing to wait for
-      for (int u = 1; u <= 2; ++u) {  // steady state: two consecutive units with their column flips
-        const int G = u * n + j;
-        const uint32_t c0 = ((uint32_t)pg.job[j].tmem_col + ((u & 1) ? flip_on_h : 0u)) & 511u, c1 = c0 + pg.job[j].N;
-        for (int A = 0; A < G; ++A) {
-          const int ja = A % n, ua = A / n;
-          const uint32_t a0 = ((uint32_t)pg.job[ja].tmem_col + ((ua & 1) ? flip_on_h : 0u)) & 511u, a1 = a0 + pg.job[ja].N;
-          if (a0 < c1 && c0 < a1) {
-            const int reader = ua * n + (pg.job[ja].reader >= 0 ? pg.job[ja].reader : ja);
-            if (reader < G && G - reader < wb) wb = G - reader;
-          }
-        }
+    struct Exec { int j, it, ui; };
+    std::vector<Exec> seq;
+    for (int it = 0; it < n_iter; ++it)
+      for (int j = 0; j < n; ++j) {
+        const int ui = it + pg.job[j].shift;
+        if (ui >= 0 && ui < n_units) seq.push_back({j, it, ui});
       }
-      pg.job[j].wait_back = wb < 1 ? 1 : wb;
+    auto exec_index = [&](int j, int ui) {
+      for (size_t e = 0; e < seq.size(); ++e)
+        if (seq[e].j == j && seq[e].ui == ui) return (int)e;
+      return -1;
+    };
+    std::vector<int> wb(n, 1 << 20);
+    for (size_t G = 0; G < seq.size(); ++G) {
+      const Job& jg = pg.job[seq[G].j];
+      const uint32_t c0 = ((uint32_t)jg.tmem_col + ((seq[G].it & 1) ? flip_on_h : 0u)) & 511u, c1 = c0 + jg.N;
+      for (size_t A = 0; A < G; ++A) {
+        const Job& ja = pg.job[seq[A].j];
+        const uint32_t a0 = ((uint32_t)ja.tmem_col + ((seq[A].it & 1) ? flip_on_h : 0u)) & 511u, a1 = a0 + ja.N;
+        if (!(a0 < c1 && c0 < a1)) continue;
+        const int R = ja.reader >= 0 ? exec_index(ja.reader, seq[A].ui) : (int)A;
+        if (R < 0 || R >= (int)G) {
+          set_error("mlp_forward_chain: job %d overwrites TMEM columns of job %d before its reader has run", seq[G].j,
+                    seq[A].j);
+          return TH_EINVAL;
+        }
+        if ((int)G - R < wb[seq[G].j]) wb[seq[G].j] = (int)G - R;
+      }
     }
+    for (int j = 0; j < n; ++j) pg.job[j].wait_back = wb[j] < 1 ? 1 : wb[j];
   }
   if (run.program_dump) {  // host-side test hook: the program as built, nothing launched
     pg.afc_w = wf(h.afc_w);
@@ -1204,11 +1295,11 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
 // n_points, as a table of int64 so that a CPU test can interpret it against the oracle
 // (tests/test_chain_program.py).  Addresses are reported relative to a fictitious workspace base
 // (the chunk block of mlp_carve) and to the start of the packed weight blob.
-//   header: [njobs, V, has_mix, alpha_only, Pp, scr_act_bytes, tile_img_bytes, 0]
+//   header: [njobs, V, has_mix, alpha_only, Pp, scr_act_bytes, tile_img_bytes, deferred_tail]
 //   job (16 + 6 * MAX_SEG words): N, relu, epi, out_off, tmem_col, wait_back, view, nseg, nkb, wimg_off,
-//        bias_off (-1 = none), bias2_off (-1 = none), reader (-1 = own epilogue), 0, 0, 0, then per segment:
+//        bias_off (-1 = none), bias2_off (-1 = none), reader (-1 = own epilogue), shift, out_aset, 0, then per segment:
 //        kind (0 scratch / 1 chunk image), offset (scratch bytes / image byte offset from the chunk base),
-//        tile_off, kbs, dep, dep_mix
+//        tile_off, kbs, dep, dep_mix | aset << 1
 extern "C" int64_t th_debug_chain_program(const void* packed_host, int32_t n_views, int64_t n_points,
                                           int32_t alpha_only, int32_t premapped, int64_t* table, int64_t capacity) {
   using namespace th;
@@ -1239,19 +1330,19 @@ extern "C" int64_t th_debug_chain_program(const void* packed_host, int32_t n_vie
   auto woff = [&](const void* p) { return p ? (int64_t)(static_cast<const unsigned char*>(p) - wbase) : (int64_t)-1; };
   int64_t* t = table;
   t[0] = pg.njobs; t[1] = pg.V; t[2] = pg.has_mix; t[3] = pg.alpha_only; t[4] = pad_points(n_points);
-  t[5] = SCR_ACT; t[6] = TILE_IMG; t[7] = 0;
+  t[5] = SCR_ACT; t[6] = TILE_IMG; t[7] = pg.deferred_tail;
   t += 8;
   for (int j = 0; j < pg.njobs; ++j) {
     const Job& jb = pg.job[j];
     t[0] = jb.N; t[1] = jb.relu; t[2] = jb.epi; t[3] = jb.out_off; t[4] = jb.tmem_col; t[5] = jb.wait_back;
     t[6] = jb.view; t[7] = jb.nseg; t[8] = jb.nkb; t[9] = woff(jb.wimg); t[10] = woff(jb.bias); t[11] = woff(jb.bias2);
-    t[12] = jb.reader; t[13] = t[14] = t[15] = 0;
+    t[12] = jb.reader; t[13] = jb.shift; t[14] = jb.out_aset; t[15] = 0;
     for (int sgi = 0; sgi < MAX_SEG; ++sgi) {
       const Seg& sg = jb.seg[sgi];
       int64_t* q = t + 16 + 6 * sgi;
       q[0] = sg.img ? 1 : 0;
       q[1] = sg.img ? (int64_t)(sg.img - cbase) : (int64_t)sg.scratch_off;
-      q[2] = sg.tile_off; q[3] = sg.kbs; q[4] = sg.dep; q[5] = sg.dep_mix;
+      q[2] = sg.tile_off; q[3] = sg.kbs; q[4] = sg.dep; q[5] = sg.dep_mix | (sg.aset << 1);
     }
     t += 16 + 6 * MAX_SEG;
   }
