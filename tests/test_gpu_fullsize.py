@@ -106,6 +106,15 @@ def test_chain_kernel_is_insensitive_to_role_timing(monkeypatch):
         b = ops.render_rays(frame, *(r[sel] for r in rays), S, mode=ops.TH_RENDER_DENSE, want_raw=True)
         monkeypatch.delenv("TH_CHAIN_DBG")
         assert torch.equal(a["raw"], b["raw"]) and torch.equal(a["rgb_map"], b["rgb_map"])
+    # the opt-in schedule that issues the tail of the network one unit late (software pipelining across units,
+    # alternating scratch slot sets): same arithmetic in a different order of jobs -> bit-identical, also under jitter
+    monkeypatch.setenv("TH_CHAIN_DEFER", "1")
+    for bits in ("0", "240"):
+        monkeypatch.setenv("TH_CHAIN_DBG", bits)
+        c = ops.render_rays(frame, *(r[sel] for r in rays), S, mode=ops.TH_RENDER_DENSE, want_raw=True)
+        assert torch.equal(a["raw"], c["raw"]) and torch.equal(a["rgb_map"], c["rgb_map"])
+    monkeypatch.delenv("TH_CHAIN_DBG")
+    monkeypatch.delenv("TH_CHAIN_DEFER")
 
 
 def test_config_grid_6000_tokens_density():

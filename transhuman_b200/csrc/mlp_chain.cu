@@ -977,9 +977,9 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     B.pg.ks_col[2] = 0;
     B.pg.kp_col = 128;
   }
-  // Two forms of the attention mix in the pre-mapped program (both parity-green, measured in profiles/README.md):
-  // in place on the fp16 operands by the six mix warps (default: 3 % fewer cycles), or on the accumulator side in
-  // TMEM (TH_CHAIN_MIX=tmem): see the job list below
+  // Two forms of the attention mix in the pre-mapped program (both parity-green, equally fast within noise,
+  // profiles/README.md r2g-r2j): in place on the fp16 operands by the six mix warps (default: least DRAM traffic), or
+  // on the accumulator side in TMEM (TH_CHAIN_MIX=tmem): see the job list below
   // run.premapped: 1 = default (env TH_CHAIN_MIX = "tmem" | "inplace" decides, read per call so that tests can
   // toggle it), 2 = TMEM-side mix, 3 = in-place mix
   const char* mix_env = getenv("TH_CHAIN_MIX");
@@ -1028,13 +1028,17 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
       j_int[v] = B.add({Builder::scr(B.slotB(v), 128, j_z[v][0]), Builder::scr(B.slotB(v) + 2u * TILE_IMG, 128, j_z[v][1])},
                        wimg(h.h_fc2), wf(h.fc2_b), 256, 1, EPI_IMG, B.slotA(v));
   }
-  // Deferred tail (pre-mapped program with the in-place mix; TH_CHAIN_DEFER=0 disables it): the jobs after fc_2 --
+  // Deferred tail (pre-mapped program with the in-place mix; OPT-IN with TH_CHAIN_DEFER=1): the jobs after fc_2 --
   // fc_3 + alpha head, view_fc' per view, fc_4' + rgb head, ~40 kcycles of tensor work per unit -- are issued one
   // iteration LATE, between the score jobs and fc_1' of the NEXT unit, i.e. into the ~45 kcycles in which the tensor
-  // pipe waited for the mix warps (TH_CHAIN_STATS).  INTER of the previous unit must then outlive S / N1 of the
-  // current one: slot set A exists twice and alternates with the unit's parity.
+  // pipe waits for the mix warps (TH_CHAIN_STATS).  INTER of the previous unit must then outlive S / N1 of the
+  // current one: slot set A exists twice and alternates with the unit's parity.  Parity-green (also under role
+  // jitter) and it does close the window (fc_1' of view 0 waits 8 instead of 46 kcycles), but the launch is NOT
+  // faster: the kernel moves ~68 KB per point through L2 at ~85 % of the chip's L2 throughput cap, so the tail's
+  // operand stream and the mix now contend (mix 50 -> 68 kcycles per unit, fc_3 waits 20 kcycles for operands), and the
+  // larger scratch costs L2 hits (71 % -> 59 %, DRAM 6.8 -> 9.3 GB per launch).  Measured in profiles/README.md (r2h-r2j).
   const char* defer_env = getenv("TH_CHAIN_DEFER");
-  const bool defer = x_in_chunk && !tmix && !(defer_env && !atoi(defer_env));
+  const bool defer = x_in_chunk && !tmix && defer_env && atoi(defer_env);
   auto add_fc3 = [&]() {
     const int j = B.pg.njobs++;
     Job& jb = B.pg.job[j];
