@@ -242,6 +242,43 @@ int th_paint_group(const float* holder_map, int32_t n_views, int32_t h, int32_t 
                    const float* verts, int32_t n_verts, const float* cam_R, const float* cam_T, const float* cam_K,
                    const uint8_t* vizmap, const int32_t* cluster_start, const int32_t* cluster_members, int32_t n_tok,
                    float* painted, float* tokens, void* stream);
+/* ---- the encoder's tail without its full-resolution maps -------------------- */
+/* What SpatialEncoder.forward does AFTER the ResNet backbone (encoder.py:133-146): the three latents are bilinearly
+ * upsampled (align_corners=True) to the image size, concatenated with upsample_color(images) (a 1x1 convolution
+ * 3 -> 128) into pixel_feat_map (V,384,H,W), and reduction_layer (1x1, 384 -> 192) makes holder_feat_map.  The two
+ * entry points below take the LATENTS and evaluate that tail per pixel / per vertex on the fly, so neither
+ * pixel_feat_map (1.2 GB at 3 x 512 x 512), nor its channel-last transpose, nor holder_feat_map (0.6 GB) is ever
+ * written.  All pointers DEVICE fp32, contiguous; images NCHW, latents channel-last. */
+typedef struct ThEncoderTail {
+  const float* latent[3]; /* CHANNEL-LAST (V,lat_h[0],lat_w[0],64), (V,lat_h[1],lat_w[1],64), (V,lat_h[2],lat_w[2],128):
+                           * conv1/bn/relu, layer1, layer2 outputs (encoder.py:113-125, num_layers = 3); what a
+                           * torch backbone run in torch.channels_last memory format produces in place         */
+  int32_t lat_h[3], lat_w[3];
+  const float* images;    /* (V,3,H,W) the encoder's input                                                  */
+  const float* color_w;   /* upsample_color.weight (128,3) */
+  const float* color_b;   /* upsample_color.bias (128)     */
+  int32_t n_views, h, w;
+} ThEncoderTail;
+/* = th_premap_features(pixel_feat_map of these latents): pre-mapped maps (V,H,W,512) channel-last.  A 1x1
+ * convolution commutes with bilinear upsampling, so W_pre is applied to the LOW-RESOLUTION latents (tcgen05 GEMMs
+ * over 86,016 instead of 262,144 rows per 512 x 512 view, K = 64 / 64 / 128) and one kernel upsamples the three
+ * results, adds the folded colour convolution and writes the channel-last map.  workspace (DEVICE, 256-byte
+ * aligned) >= th_premap_from_latents_workspace_bytes(enc) holds the low-resolution maps of one view. */
+size_t th_premap_from_latents_workspace_bytes(const ThEncoderTail* enc);
+int th_premap_from_latents(const ThEncoderTail* enc, const void* packed_weights, float* out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* = th_paint_group(holder_feat_map of these latents, ...) without `painted`: reduction_w (192,384), reduction_b (192)
+ * = reduction_layer.  The reduction and the cluster mean are both linear, so the 384 pixel-feature channels are
+ * interpolated at each visible member vertex, summed per cluster and reduced once per (cluster, view): tokens equal
+ * the reference's to rounding (a few 1e-7 relative; not bit-equal -- th_paint_group is).  workspace (DEVICE,
+ * 256-byte aligned) >= th_paint_group_latents_workspace_bytes(n_views, n_verts, n_tok): the per-vertex 384-channel
+ * samples and the per-cluster sums. */
+size_t th_paint_group_latents_workspace_bytes(int32_t n_views, int32_t n_verts, int32_t n_tok);
+int th_paint_group_latents(const ThEncoderTail* enc, const float* reduction_w, const float* reduction_b,
+                           float uv_scale_x, float uv_scale_y, const float* verts, int32_t n_verts, const float* cam_R,
+                           const float* cam_T, const float* cam_K, const uint8_t* vizmap, const int32_t* cluster_start,
+                           const int32_t* cluster_members, int32_t n_tok, float* tokens, void* workspace,
+                           size_t workspace_bytes, void* stream);
 /* Renderer.voxelization (if_clight_renderer.py:356-371) of a per-vertex quantity x (n_verts, C), fp32 (is_f64 = 0)
  * or fp64 (blend_mtx, 543-544): out (n_tok, C) of the same type, bit-equal to torch-CPU's `x[idx].mean(0)`:
  * `outer_order` = 1 for wide rows (fp32 C >= 32, fp64 C >= 16: rows added sequentially with a 16-row cascade),

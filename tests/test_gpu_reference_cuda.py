@@ -167,8 +167,18 @@ def test_plugin_through_make_renderer_matches_reference_renderer():
     finally:
         restore()
     with torch.no_grad():
+        # the genuine SpatialEncoder is recognised: only its backbone runs, the tail is evaluated inside the kernels
+        # (th_paint_group_latents / th_premap_from_latents)
+        imgs = batch["input_imgs"][0].reshape(-1, *batch["input_imgs"][0].shape[2:])
+        assert ours.use_latents and ours._encoder_tail(imgs) is not None
         got_d = ours.render(dict(batch))
         got_f = ours.render_fast(dict(batch))
+        ours.use_latents = False          # net.encoder as a black box: full-resolution maps, th_paint_group
+        map_d = ours.render(dict(batch))
+        ours.use_latents = True
+    d_lat = float((got_d["rgb_map"] - map_d["rgb_map"]).abs().max())
+    print(f"[make_renderer] latents path vs full-map path: rgb max-abs {d_lat:.3e}")
+    assert d_lat <= 1e-4
     assert got_d["rgb_map"].shape == ref_d["rgb_map"].shape == (1, H * H, 3)
     far = float(fr["far"].max())
     for name, a, b in (("render", got_d, ref_d), ("render_fast", got_f, ref_f)):

@@ -60,6 +60,14 @@ WEIGHT_FIELDS = [
 ]
 
 
+class ThEncoderTail(C.Structure):
+    _fields_ = [
+        ("latent", _fp * 3), ("lat_h", C.c_int32 * 3), ("lat_w", C.c_int32 * 3),
+        ("images", _fp), ("color_w", _fp), ("color_b", _fp),
+        ("n_views", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+    ]
+
+
 class ThWeightsF32(C.Structure):
     _fields_ = [(f"{c}_{s}", _fp) for c, _ in WEIGHT_FIELDS for s in ("w", "b")]
 
@@ -90,6 +98,11 @@ SIGNATURES = {
     "th_premap_features": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp, _fp]),
     "th_paint_group": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _fp, C.c_int32, _fp, _fp, _fp,
                                  _fp, _fp, _fp, C.c_int32, _fp, _fp, _fp]),
+    "th_premap_from_latents_workspace_bytes": (C.c_size_t, [C.POINTER(ThEncoderTail)]),
+    "th_premap_from_latents": (C.c_int, [C.POINTER(ThEncoderTail), _fp, _fp, _fp, C.c_size_t, _fp]),
+    "th_paint_group_latents_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "th_paint_group_latents": (C.c_int, [C.POINTER(ThEncoderTail), _fp, _fp, C.c_float, C.c_float, _fp, C.c_int32, _fp,
+                                         _fp, _fp, _fp, _fp, _fp, C.c_int32, _fp, _fp, C.c_size_t, _fp]),
     "th_group_mean": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     "th_near_far": (C.c_int, [_fp, _fp, C.c_int64, _fp, _fp, _fp, _fp, _fp]),
     "th_generate_rays_workspace_bytes": (C.c_size_t, [C.c_int64]),

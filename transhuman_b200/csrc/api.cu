@@ -851,6 +851,87 @@ int th_paint_group(const float* holder_map, int32_t n_views, int32_t h, int32_t 
                             static_cast<cudaStream_t>(stream));
 }
 
+// one EncTail per view from the C-ABI struct
+static int enc_views(const ThEncoderTail* enc, EncTail* ev) {
+  TH_CHECK_ARG(enc && enc->images && enc->color_w && enc->color_b, "null pointer");
+  TH_CHECK_ARG(enc->n_views >= 1 && enc->n_views <= TH_MAX_VIEWS && enc->h >= 1 && enc->w >= 1, "bad sizes");
+  static const int chans[3] = {64, 64, 128};
+  for (int i = 0; i < 3; ++i)
+    TH_CHECK_ARG(enc->latent[i] && enc->lat_h[i] >= 1 && enc->lat_w[i] >= 1, "bad latent");
+  for (int v = 0; v < enc->n_views; ++v) {
+    EncTail& e = ev[v];
+    for (int i = 0; i < 3; ++i) {
+      e.lat[i] = enc->latent[i] + (int64_t)v * chans[i] * enc->lat_h[i] * enc->lat_w[i];
+      e.lh[i] = enc->lat_h[i];
+      e.lw[i] = enc->lat_w[i];
+    }
+    e.img = enc->images + (int64_t)v * 3 * enc->h * enc->w;
+    e.wc = enc->color_w;
+    e.bc = enc->color_b;
+    e.H = enc->h;
+    e.W = enc->w;
+  }
+  return TH_OK;
+}
+
+size_t th_premap_from_latents_workspace_bytes(const ThEncoderTail* enc) {
+  if (!enc) return 0;
+  int lh[3], lw[3];
+  for (int i = 0; i < 3; ++i) lh[i] = enc->lat_h[i] > 0 ? enc->lat_h[i] : 1, lw[i] = enc->lat_w[i] > 0 ? enc->lat_w[i] : 1;
+  return premap_latents_scratch_bytes(lh, lw);
+}
+
+int th_premap_from_latents(const ThEncoderTail* enc, const void* packed_weights, float* out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TH_CHECK_ARG(packed_weights && out && workspace, "null pointer");
+  EncTail ev[TH_MAX_VIEWS];
+  int rc = enc_views(enc, ev);
+  if (rc) return rc;
+  TH_CHECK_ARG(workspace_bytes >= th_premap_from_latents_workspace_bytes(enc), "workspace too small");
+  TH_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  PackedHeader hdr;
+  TH_CUDA(cudaMemcpyAsync(&hdr, packed_weights, sizeof(PackedHeader), cudaMemcpyDeviceToHost, st));
+  TH_CUDA(cudaStreamSynchronize(st));
+  if (hdr.magic != PACK_MAGIC) {
+    set_error("th_premap_from_latents: bad weights blob");
+    return TH_EINVAL;
+  }
+  return launch_premap_latents(ev, static_cast<const unsigned char*>(packed_weights), hdr, out, enc->n_views, workspace,
+                               st);
+}
+
+size_t th_paint_group_latents_workspace_bytes(int32_t n_views, int32_t n_verts, int32_t n_tok) {
+  const int v = n_views > 0 ? n_views : 1;
+  return align_up((size_t)v * sizeof(EncTail), 256) +
+         paint_latents_scratch_bytes(v, n_verts > 0 ? n_verts : 1, n_tok > 0 ? n_tok : 1);
+}
+
+int th_paint_group_latents(const ThEncoderTail* enc, const float* reduction_w, const float* reduction_b,
+                           float uv_scale_x, float uv_scale_y, const float* verts, int32_t n_verts, const float* cam_R,
+                           const float* cam_T, const float* cam_K, const uint8_t* vizmap, const int32_t* cluster_start,
+                           const int32_t* cluster_members, int32_t n_tok, float* tokens, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TH_CHECK_ARG(reduction_w && reduction_b && verts && cam_R && cam_T && cam_K && cluster_start && cluster_members &&
+                   tokens && workspace,
+               "null pointer");
+  TH_CHECK_ARG(n_verts >= 1 && n_tok >= 1, "bad sizes");
+  EncTail ev[TH_MAX_VIEWS];
+  int rc = enc_views(enc, ev);
+  if (rc) return rc;
+  TH_CHECK_ARG(workspace_bytes >= th_paint_group_latents_workspace_bytes(enc->n_views, n_verts, n_tok),
+               "workspace too small");
+  TH_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  void* scratch = static_cast<unsigned char*>(workspace) + align_up((size_t)enc->n_views * sizeof(EncTail), 256);
+  // the per-view descriptors travel through the caller's workspace (stream-ordered copy from a pageable buffer:
+  // cudaMemcpyAsync stages it before returning, so `ev` may die with this frame)
+  TH_CUDA(cudaMemcpyAsync(workspace, ev, (size_t)enc->n_views * sizeof(EncTail), cudaMemcpyHostToDevice, st));
+  return launch_paint_group_latents(static_cast<const EncTail*>(workspace), enc->n_views, reduction_w, reduction_b,
+                                    uv_scale_x, uv_scale_y, verts, cam_R, cam_T, cam_K, vizmap, n_verts, cluster_start,
+                                    cluster_members, n_tok, scratch, tokens, st);
+}
+
 int th_group_mean(const void* x, int32_t is_f64, int32_t n_cols, const int32_t* cluster_start,
                   const int32_t* cluster_members, int32_t n_tok, int32_t outer_order, void* out, void* stream) {
   TH_CHECK_ARG(x && cluster_start && cluster_members && out, "null pointer");

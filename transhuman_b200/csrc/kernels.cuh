@@ -239,6 +239,46 @@ struct GemmSeg {
   // (pixels, channels) matrix without a transpose pass (th_premap_features)
   int64_t col_stride;
 };
+// SpatialEncoder.forward after the backbone (encoder.py:133-146): pixel_feat_map = [up(latent_0) 64 | up(latent_1) 64 |
+// up(latent_2) 128 | upsample_color(image) 128], `up` = bilinear, align_corners=True (PyTorch's CUDA formula), evaluated
+// where it is consumed: th_premap_from_latents applies W_pre to the LOW-RESOLUTION latents (1x1 convolutions commute with
+// bilinear upsampling) and upsamples the results, th_paint_group_latents interpolates per vertex.  Neither the
+// (V,384,H,W) map, nor a transpose of it, nor the (V,192,H,W) holder map ever exists.  Pointers of ONE view.
+struct EncTail {
+  const float* lat[3];  // (lh, lw, 64 | 64 | 128) latents of the view, CHANNEL-LAST
+  int lh[3], lw[3];
+  const float* img;     // (3, H, W)
+  const float* wc;      // upsample_color.weight (128, 3)
+  const float* bc;      // upsample_color.bias (128)
+  int H, W;
+};
+// value of the upsampled plane at full-resolution texel (y, x): src = dst * (in - 1) / (out - 1), i0 = (int)src,
+// l1 = src - i0, val = h0 (w0 v00 + w1 v01) + h1 (w0 v10 + w1 v11) (UpSampleBilinear2d.cu, align_corners=True)
+struct UpTap {
+  int o00, o01, o10, o11;
+  float h0, h1, w0, w1;
+};
+__device__ __forceinline__ UpTap up_tap(int lh, int lw, int H, int W, int y, int x) {
+  const float rh = H > 1 ? (float)(lh - 1) / (float)(H - 1) : 0.f;
+  const float rw = W > 1 ? (float)(lw - 1) / (float)(W - 1) : 0.f;
+  const float sy = rh * (float)y, sx = rw * (float)x;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < lh - 1 ? 1 : 0), x1 = x0 + (x0 < lw - 1 ? 1 : 0);
+  UpTap t;
+  t.h1 = sy - (float)y0, t.h0 = 1.f - t.h1, t.w1 = sx - (float)x0, t.w0 = 1.f - t.w1;
+  t.o00 = y0 * lw + x0, t.o01 = y0 * lw + x1, t.o10 = y1 * lw + x0, t.o11 = y1 * lw + x1;
+  return t;
+}
+// paint + group straight from the latents (th_paint_group_latents): holder_feat_map = reduction_layer(pixel_feat_map)
+// is linear, and so is the cluster mean, so the 384 pixel-feature channels are interpolated at every visible vertex
+// (-> painted (V, n_verts, 384), scratch), summed per cluster, and the 192 x 384 reduction is applied ONCE per
+// (cluster, view).  enc = V views (device array); red_w (192,384), red_b (192) = reduction_layer; scratch >=
+// paint_latents_scratch_bytes.
+size_t paint_latents_scratch_bytes(int V, int n_verts, int n_tok);
+int launch_paint_group_latents(const EncTail* enc_dev, int V, const float* red_w, const float* red_b, float sx, float sy,
+                               const float* verts, const float* cam_R, const float* cam_T, const float* cam_K,
+                               const uint8_t* viz, int n_verts, const int32_t* start, const int32_t* members, int n_tok,
+                               void* scratch, float* out, cudaStream_t st);
 struct GemmArgs {
   GemmSeg seg[TH_MAX_VIEWS + 1];
   int nseg;
@@ -261,6 +301,11 @@ int launch_gemm_tc(const GemmArgs& a, const void* w_hi_lo, cudaStream_t st, int 
 // three 1x1 convolutions that read the blended maps, as tcgen05 GEMMs over the maps (2 launches of N = 256 per view).
 int launch_premap(const float* src_nchw, const unsigned char* weights, const PackedHeader& hdr, float* dst, int n_views,
                   int h, int w, cudaStream_t st);
+// the same maps straight from the encoder's latents (prologue.cu): enc[v] describes view v; `scratch`
+// holds the low-resolution pre-mapped maps of ONE view, premap_latents_scratch_bytes(enc[0])
+size_t premap_latents_scratch_bytes(const int* lh, const int* lw);
+int launch_premap_latents(const EncTail* enc_host, const unsigned char* weights, const PackedHeader& hdr, float* dst,
+                          int n_views, void* scratch, cudaStream_t st);
 int launch_pack_inputs(const float* human_rep, const float* pixel_feat, const float* viewdir, int64_t P, int V,
                        const MlpBuffers& b, cudaStream_t st);
 

@@ -18,7 +18,8 @@ from ._lib import (TH_FLAG_LAYERWISE, TH_FLAG_PREMAPPED, TH_FLAG_SIMT_MLP, TH_FL
 
 __all__ = ["PackedWeights", "Frame", "render_rays", "query_density", "sample_points", "cull_knn1", "cull_grid",
            "world2smpl", "view_embed", "pixel_gather", "knn_dparf", "mlp_raw", "integrate", "nchw_to_nhwc",
-           "premap_features", "ClusterIndex", "paint_group", "group_mean", "generate_rays", "near_far",
+           "premap_features", "EncoderTail", "premap_from_latents", "paint_group_latents", "ClusterIndex", "paint_group",
+           "group_mean", "generate_rays", "near_far",
            "launch_count", "TH_RENDER_DENSE", "TH_RENDER_MASKED", "TH_RENDER_FAST"]
 
 
@@ -400,6 +401,78 @@ def paint_group(holder_map, uv_scale, verts, cam_R, cam_T, cam_K, vizmap, cluste
                                   _ptr(T), _ptr(K), _ptr(viz), _ptr(clusters.start), _ptr(clusters.members),
                                   clusters.n_tok, _ptr(painted), _ptr(out), _stream()), "th_paint_group")
     return (out, painted) if want_painted else out
+
+
+class EncoderTail:
+    """The inputs of ``SpatialEncoder.forward``'s tail (encoder.py:133-146) for ``th_premap_from_latents`` /
+    ``th_paint_group_latents``: the three backbone latents (V,64|64|128,lh,lw), the input images (V,3,H,W) and the
+    ``upsample_color`` 1x1 convolution.  The C ABI takes the latents channel-last: tensors in
+    ``torch.channels_last`` memory format (what a backbone run in that format returns) are passed as they are,
+    NCHW-contiguous ones are converted here (22 MB per 512 x 512 view).  Keeps the tensors alive next to the C struct."""
+
+    def __init__(self, latents, images, color_w, color_b):
+        assert len(latents) == 3
+        self.images = _f32(images, "images")
+        self.color_w = _f32(color_w, "color_w").reshape(128, 3)
+        self.color_b = _f32(color_b, "color_b").reshape(128)
+        V, c, H, W = self.images.shape
+        assert c == 3
+        self.latents = []
+        for l, ch in zip(latents, (64, 64, 128)):
+            assert l.dim() == 4 and l.shape[0] == V and l.shape[1] == ch, "latents must be (V,64|64|128,lh,lw)"
+            if not l.is_cuda:
+                raise ValueError("latent: expected a CUDA tensor (the query path has no CPU implementation)")
+            nhwc = l.float().permute(0, 2, 3, 1)          # a view; contiguous already for channels_last tensors
+            self.latents.append(nhwc.contiguous())
+        self.n_views, self.h, self.w = V, H, W
+        self.c = _lib.ThEncoderTail()
+        for i, l in enumerate(self.latents):
+            self.c.latent[i] = l.data_ptr()
+            self.c.lat_h[i], self.c.lat_w[i] = l.shape[1], l.shape[2]
+        self.c.images, self.c.color_w, self.c.color_b = self.images.data_ptr(), self.color_w.data_ptr(), self.color_b.data_ptr()
+        self.c.n_views, self.c.h, self.c.w = V, H, W
+
+    @property
+    def device(self):
+        return self.images.device
+
+
+def premap_from_latents(enc: EncoderTail, weights: PackedWeights, out=None):
+    """8f-2: pre-mapped maps (V,H,W,512) straight from the encoder's latents (``th_premap_from_latents``): equals
+    ``premap_features(pixel_feat_map)`` without the 1.2 GB ``pixel_feat_map`` ever being written."""
+    lib = _lib.load()
+    assert enc.n_views == weights.n_views
+    if out is None:
+        out = torch.empty((enc.n_views, enc.h, enc.w, 512), device=enc.device)
+    assert out.shape == (enc.n_views, enc.h, enc.w, 512) and out.is_contiguous() and out.dtype == torch.float32
+    nbytes = lib.th_premap_from_latents_workspace_bytes(C.byref(enc.c))
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=enc.device)
+    _lib.check(lib.th_premap_from_latents(C.byref(enc.c), weights.blob.data_ptr(), _ptr(out), _ptr(ws), nbytes,
+                                          _stream()), "th_premap_from_latents")
+    return out
+
+
+def paint_group_latents(enc: EncoderTail, reduction_w, reduction_b, uv_scale, verts, cam_R, cam_T, cam_K, vizmap,
+                        clusters: ClusterIndex):
+    """8f-1 + 8f-2: tokens (V,n_tok,192) from the latents (``th_paint_group_latents``); ``reduction_w`` (192,384[,1,1]),
+    ``reduction_b`` (192) = ``encoder.reduction_layer``.  No holder map is built."""
+    lib = _lib.load()
+    V, dev = enc.n_views, enc.device
+    rw, rb = _f32(reduction_w, "reduction_w").reshape(192, 384), _f32(reduction_b, "reduction_b").reshape(192)
+    verts = _f32(verts, "verts").view(-1, 3)
+    nv = verts.shape[0]
+    clusters.to(dev)
+    assert clusters.n_verts == nv
+    R, T, K = _f32(cam_R, "cam_R").view(V, 3, 3), _f32(cam_T, "cam_T").view(V, 3), _f32(cam_K, "cam_K").view(V, 3, 3)
+    viz = None if vizmap is None else vizmap.to(torch.uint8).contiguous().view(V, nv)
+    out = torch.empty((V, clusters.n_tok, 192), device=dev)
+    nbytes = lib.th_paint_group_latents_workspace_bytes(V, nv, clusters.n_tok)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    _lib.check(lib.th_paint_group_latents(C.byref(enc.c), _ptr(rw), _ptr(rb), float(uv_scale[0]), float(uv_scale[1]),
+                                          _ptr(verts), nv, _ptr(R), _ptr(T), _ptr(K), _ptr(viz), _ptr(clusters.start),
+                                          _ptr(clusters.members), clusters.n_tok, _ptr(out), _ptr(ws), nbytes,
+                                          _stream()), "th_paint_group_latents")
+    return out
 
 
 def group_mean(x, clusters: ClusterIndex, outer_order=None):

@@ -11,10 +11,14 @@ Select it from the reference's YAML (no reference file edited)::
 return dict (``rgb_map (1,N,3)``, ``acc_map (1,N)``, ``depth_map (1,N)``) and
 batch keys as ``lib/networks/renderer/if_clight_renderer.py``.
 
-Per frame, the image encoder and the ViT stay the reference's torch modules (``net.encoder``, ``net.ViT``);
-everything else runs in ``libtranshuman_b200.so`` through :mod:`transhuman_b200.ops`: SMPL painting + cluster
-grouping (``th_paint_group`` / ``th_group_mean``), the pre-map GEMM over the encoder's maps
-(``th_premap_features``, 8f-2) and the whole per-sample-point path (``th_render_rays``).
+Per frame, the encoder's ResNet backbone and the ViT stay the reference's torch modules (``net.encoder.model``,
+``net.ViT``); everything else runs in ``libtranshuman_b200.so`` through :mod:`transhuman_b200.ops`: the encoder's tail
+(upsample + cat + 1x1 convolutions, encoder.py:133-146) is evaluated inside the kernels that consume it -- SMPL
+painting + cluster grouping from the latents (``th_paint_group_latents`` / ``th_group_mean``) and the
+pre-mapped feature maps from the latents (``th_premap_from_latents``, 8f-2), so neither ``pixel_feat_map`` nor
+``holder_feat_map`` is ever written -- then the whole per-sample-point path (``th_render_rays``).  An encoder that is
+not the reference's ``SpatialEncoder`` in its default configuration is called as a black box and its maps go through
+``th_paint_group`` / ``th_premap_features``.
 Forward only: training (autograd + stratified jitter) keeps the reference path.
 """
 from __future__ import annotations
@@ -98,6 +102,9 @@ class Renderer:
         self._weights = None
         self._weights_key = None
         self.last_counters = None
+        # 8f-2: run only the encoder's backbone and evaluate its tail inside the CUDA kernels (see prepare_frame);
+        # False = call net.encoder as a black box (any encoder with the reference's four outputs)
+        self.use_latents = True
         # set `profile = True` to have every prologue stage bracketed by CUDA events; `last_prologue_ms` then
         # holds {stage: milliseconds} of the last prepare_frame (bench.py's `plugin` record)
         self.profile = False
@@ -116,6 +123,31 @@ class Renderer:
             self._weights = ops.PackedWeights(self.net.state_dict(), V, device=device)
             self._weights_key = key
         return self._weights
+
+    def _encoder_tail(self, images):
+        """The reference SpatialEncoder's backbone (encoder.py:100-131) -> ops.EncoderTail, or None when
+        ``net.encoder`` is not that module in its default configuration (then the caller runs it whole)."""
+        enc = self.net.encoder
+        m = getattr(enc, 'model', None)
+        ok = (m is not None and all(hasattr(m, a) for a in ('conv1', 'bn1', 'relu', 'maxpool', 'layer1', 'layer2'))
+              and getattr(enc, 'num_layers', None) == 3 and getattr(enc, 'feature_scale', None) == 1.0
+              and getattr(enc, 'upsample_interp', None) == 'bilinear' and getattr(enc, 'index_interp', '') != 'nearest '
+              and hasattr(enc, 'upsample_color') and hasattr(enc, 'reduction_layer')
+              and tuple(enc.reduction_layer.weight.shape[:2]) == (192, 384))
+        if not ok:
+            return None
+        # channels_last memory format: cuDNN's native layout, and the latents come out channel-last in place -- the
+        # layout th_premap_from_latents / th_paint_group_latents read (same values; only the strides differ)
+        x = m.relu(m.bn1(m.conv1(images.contiguous(memory_format=torch.channels_last))))
+        latents = [x]
+        if enc.use_first_pool:
+            x = m.maxpool(x)
+        x = m.layer1(x)
+        latents.append(x)
+        latents.append(m.layer2(x))
+        if [l.shape[1] for l in latents] != [64, 64, 128]:
+            return None
+        return ops.EncoderTail(latents, images, enc.upsample_color.weight, enc.upsample_color.bias)
 
     def refresh_weights(self):
         """Call after loading a new checkpoint into ``net``."""
@@ -147,18 +179,33 @@ class Renderer:
         self._stage("pack_weights")
         images = batch['input_imgs'][0].reshape(-1, *batch['input_imgs'][0].shape[2:])
         weights = self._packed_weights(images.shape[0], dev)
-        self._stage("encoder")
-        holder_map, holder_scale, pixel_map, pixel_scale = self.net.encoder(images)
-        V = pixel_map.shape[0]
-        # 8f-1: project + sample + visibility + cluster mean in ONE kernel (th_paint_group); token coordinates and
-        # blend matrices through th_group_mean (bit-equal to the reference's voxelization on the CPU)
-        self._stage("paint_group")
         image_shape = batch['input_imgs'][0].shape[-2:]
-        hs = np.asarray(holder_scale, dtype=np.float64) / np.array(image_shape)
+        V = images.shape[0]
         viz = batch['input_vizmaps'][0][0] if (getattr(self.cfg, 'rasterize', True) and 'input_vizmaps' in batch) else None
-        grouped = ops.paint_group(holder_map, (np.float32(hs[0]), np.float32(hs[1])), batch['input_smpl_vertice'][0][0],
-                                  batch['input_R'][0].reshape(-1, 3, 3), batch['input_T'][0].reshape(-1, 3),
-                                  batch['input_K'][0].reshape(-1, 3, 3), viz, self.clusters)
+        cams = (batch['input_R'][0].reshape(-1, 3, 3), batch['input_T'][0].reshape(-1, 3),
+                batch['input_K'][0].reshape(-1, 3, 3))
+        self._stage("encoder")
+        tail = self._encoder_tail(images) if (self.use_latents and V <= 3) else None
+        if tail is not None:
+            # 8f-2: the encoder stops after its backbone; the upsample + cat + 1x1 convolutions of its tail
+            # (encoder.py:133-146) are evaluated per vertex / per pixel inside th_paint_group_latents and the pre-map
+            # GEMM, so neither pixel_feat_map (V,384,H,W) nor holder_feat_map (V,192,H,W) is written
+            enc = self.net.encoder
+            scale = np.array([images.shape[-1], images.shape[-2]], dtype=np.float64)
+            holder_scale = pixel_scale = scale / (scale - 1) * 2.0   # encoder.py:149-153 (both maps are image-sized)
+            hs = holder_scale / np.array(image_shape)
+            self._stage("paint_group")
+            grouped = ops.paint_group_latents(tail, enc.reduction_layer.weight, enc.reduction_layer.bias,
+                                              (np.float32(hs[0]), np.float32(hs[1])),
+                                              batch['input_smpl_vertice'][0][0], *cams, viz, self.clusters)
+        else:
+            holder_map, holder_scale, pixel_map, pixel_scale = self.net.encoder(images)
+            # 8f-1: project + sample + visibility + cluster mean in ONE kernel (th_paint_group); token coordinates
+            # and blend matrices through th_group_mean (bit-equal to the reference's voxelization on the CPU)
+            self._stage("paint_group")
+            hs = np.asarray(holder_scale, dtype=np.float64) / np.array(image_shape)
+            grouped = ops.paint_group(holder_map, (np.float32(hs[0]), np.float32(hs[1])),
+                                      batch['input_smpl_vertice'][0][0], *cams, viz, self.clusters)
         pe = self.voxel_PE_can.to(dev).unsqueeze(0).repeat(V, 1, 1)
         tok_xyz = ops.group_mean(batch['tar_smpl_vertice_smplcoord'][0].float().contiguous(), self.clusters)
         blend = batch['blend_mtx'][0]
@@ -172,7 +219,10 @@ class Renderer:
         # the encoder's NCHW output) wherever the layer-chained schedule exists; plain channel-last maps otherwise
         self._stage("premap")
         premapped = V <= 3
-        feat = ops.premap_features(pixel_map, weights) if premapped else ops.nchw_to_nhwc(pixel_map)
+        if tail is not None:
+            feat = ops.premap_from_latents(tail, weights)
+        else:
+            feat = ops.premap_features(pixel_map, weights) if premapped else ops.nchw_to_nhwc(pixel_map)
         self._stages_done()
         return ops.Frame(
             holder=holder, tok_xyz=tok_xyz, tok_rot=tok_rot, verts=batch['tar_smpl_vertice'][0],
