@@ -279,6 +279,16 @@ int th_paint_group_latents(const ThEncoderTail* enc, const float* reduction_w, c
                            const float* cam_T, const float* cam_K, const uint8_t* vizmap, const int32_t* cluster_start,
                            const int32_t* cluster_members, int32_t n_tok, float* tokens, void* workspace,
                            size_t workspace_bytes, void* stream);
+/* ---- token transformer attention ---------------------------------------------- */
+/* Attention.forward between its two Linear layers (vision_transformer.py:267-275) for vit_tiny (3 heads of 64):
+ * qkv (B,N,3,H,64) fp32 = the output of `self.qkv` viewed as in line 269; out (B,N,H*64) fp32 = the input of
+ * `self.proj`: softmax(q k^T * scale, dim=-1) v per head, flash-style -- the (B,H,N,N) attention matrix (1.3 GB per
+ * layer at 6000 tokens) is never formed.  fp32-equivalent arithmetic (fp16 hi/lo operand split, three tensor-core
+ * products, fp32 accumulation and softmax).  head_dim must be 64.  workspace (DEVICE, 256-byte aligned) >=
+ * th_vit_attention_workspace_bytes(B, N, H). */
+size_t th_vit_attention_workspace_bytes(int32_t batch, int32_t n_tokens, int32_t n_heads);
+int th_vit_attention(const float* qkv, int32_t batch, int32_t n_tokens, int32_t n_heads, int32_t head_dim, float scale,
+                     float* out, void* workspace, size_t workspace_bytes, void* stream);
 /* Renderer.voxelization (if_clight_renderer.py:356-371) of a per-vertex quantity x (n_verts, C), fp32 (is_f64 = 0)
  * or fp64 (blend_mtx, 543-544): out (n_tok, C) of the same type, bit-equal to torch-CPU's `x[idx].mean(0)`:
  * `outer_order` = 1 for wide rows (fp32 C >= 32, fp64 C >= 16: rows added sequentially with a 16-row cascade),

@@ -190,3 +190,27 @@ def test_plugin_through_make_renderer_matches_reference_renderer():
         # neighbour swap or an alpha_S step can move a handful of rays -- everything else is inside the bar
         assert int(bad.sum()) <= max(2, H * H // 2000), name
     assert float(ref_d["acc_map"].max()) > 0.2 and float(ref_f["acc_map"].max()) > 0.2
+
+
+@pytest.mark.parametrize("n_tok", [300, 1500])
+def test_plugin_vit_forward_matches_reference_vit(n_tok):
+    """the genuine vit_tiny (depth 12) run whole against the plugin's forward of the same module with
+    every block's attention through th_vit_attention."""
+    from oracle.make_golden import build_reference
+    from transhuman_b200.renderer import Renderer
+    fr = synth.make_frame(H=8, W=8, n_class=300, V=3, feat_hw=16, seed=3, with_feature_maps=False)
+    ns, net, renderer, batch = build_reference(fr, 8, device="cuda", knn=_knn_cuda, fake_prologue=False)
+    ours = Renderer.__new__(Renderer)
+    ours.net, ours.use_flash_vit = net, True
+    g = torch.Generator("cpu").manual_seed(n_tok)
+    tokens = torch.randn((3, n_tok, 192), generator=g).to(DEV)
+    pe = (torch.rand((3, n_tok, 3), generator=g) * 2 - 1).to(DEV)
+    with torch.no_grad():
+        want = net.ViT(tokens.clone(), pe, mask=None)
+        got = ours._vit_forward(tokens.clone(), pe)
+        ours.use_flash_vit = False
+        same = ours._vit_forward(tokens.clone(), pe)
+    assert torch.equal(same, want)
+    err = float((got - want).abs().max())
+    print(f"[vit] {n_tok} tokens: max-abs {err:.3e} at output scale {float(want.abs().max()):.1f}")
+    assert err <= 2e-5

@@ -932,6 +932,23 @@ int th_paint_group_latents(const ThEncoderTail* enc, const float* reduction_w, c
                                     cluster_members, n_tok, scratch, tokens, st);
 }
 
+size_t th_vit_attention_workspace_bytes(int32_t batch, int32_t n_tokens, int32_t n_heads) {
+  if (batch < 1 || n_tokens < 1 || n_heads < 1) return 256;
+  return vit_attention_workspace_bytes(batch, n_tokens, n_heads);
+}
+
+int th_vit_attention(const float* qkv, int32_t batch, int32_t n_tokens, int32_t n_heads, int32_t head_dim, float scale,
+                     float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  TH_CHECK_ARG(qkv && out && workspace, "null pointer");
+  TH_CHECK_ARG(batch >= 1 && n_tokens >= 1 && n_heads >= 1 && (int64_t)batch * n_heads <= 65535, "bad sizes");
+  TH_CHECK_ARG(head_dim == 64, "head_dim must be 64 (vit_tiny)");
+  TH_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "misaligned pointer");
+  TH_CHECK_ARG(workspace_bytes >= th_vit_attention_workspace_bytes(batch, n_tokens, n_heads), "workspace too small");
+  return launch_vit_attention(qkv, batch, n_tokens, n_heads, scale, out, workspace, static_cast<cudaStream_t>(stream));
+}
+
 int th_group_mean(const void* x, int32_t is_f64, int32_t n_cols, const int32_t* cluster_start,
                   const int32_t* cluster_members, int32_t n_tok, int32_t outer_order, void* out, void* stream) {
   TH_CHECK_ARG(x && cluster_start && cluster_members && out, "null pointer");

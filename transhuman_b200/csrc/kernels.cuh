@@ -73,6 +73,10 @@ int launch_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w
 int launch_paint_group(const float* map, int V, int H, int W, float sx, float sy, const float* verts, const float* cam_R,
                        const float* cam_T, const float* cam_K, const uint8_t* viz, int n_verts, const int32_t* start,
                        const int32_t* members, int n_tok, float* painted, float* out, cudaStream_t st);
+// vit_attn.cu: flash-style self-attention of the token transformer (th_vit_attention), head_dim 64
+size_t vit_attention_workspace_bytes(int B, int N, int H);
+int launch_vit_attention(const float* qkv, int B, int N, int H, float scale, float* out, void* workspace,
+                         cudaStream_t st);
 int launch_group_mean(const void* x, int is_f64, int C, const int32_t* start, const int32_t* members, int n_tok, int outer,
                       void* out, cudaStream_t st);
 int launch_near_far(const float* ray_o, float* ray_d, int64_t n, const float* bounds, float* near_, float* far_,

@@ -18,7 +18,7 @@ from ._lib import (TH_FLAG_LAYERWISE, TH_FLAG_PREMAPPED, TH_FLAG_SIMT_MLP, TH_FL
 
 __all__ = ["PackedWeights", "Frame", "render_rays", "query_density", "sample_points", "cull_knn1", "cull_grid",
            "world2smpl", "view_embed", "pixel_gather", "knn_dparf", "mlp_raw", "integrate", "nchw_to_nhwc",
-           "premap_features", "EncoderTail", "premap_from_latents", "paint_group_latents", "ClusterIndex", "paint_group",
+           "premap_features", "vit_attention", "EncoderTail", "premap_from_latents", "paint_group_latents", "ClusterIndex", "paint_group",
            "group_mean", "generate_rays", "near_far",
            "launch_count", "TH_RENDER_DENSE", "TH_RENDER_MASKED", "TH_RENDER_FAST"]
 
@@ -472,6 +472,22 @@ def paint_group_latents(enc: EncoderTail, reduction_w, reduction_b, uv_scale, ve
                                           _ptr(verts), nv, _ptr(R), _ptr(T), _ptr(K), _ptr(viz), _ptr(clusters.start),
                                           _ptr(clusters.members), clusters.n_tok, _ptr(out), _ptr(ws), nbytes,
                                           _stream()), "th_paint_group_latents")
+    return out
+
+
+def vit_attention(qkv, n_heads: int, scale: float):
+    """8f-3: ``Attention.forward`` between ``self.qkv`` and ``self.proj`` (vision_transformer.py:267-275):
+    qkv (B,N,3*H*64) fp32 -> (B,N,H*64), flash-style (``th_vit_attention``)."""
+    lib = _lib.load()
+    qkv = _f32(qkv, "qkv")
+    B, N, C3 = qkv.shape
+    hd = C3 // (3 * n_heads)
+    assert C3 == 3 * n_heads * hd
+    out = torch.empty((B, N, n_heads * hd), device=qkv.device)
+    nbytes = lib.th_vit_attention_workspace_bytes(B, N, n_heads)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=qkv.device)
+    _lib.check(lib.th_vit_attention(_ptr(qkv), B, N, n_heads, hd, float(scale), _ptr(out), _ptr(ws), nbytes, _stream()),
+               "th_vit_attention")
     return out
 
 

@@ -105,6 +105,8 @@ class Renderer:
         # 8f-2: run only the encoder's backbone and evaluate its tail inside the CUDA kernels (see prepare_frame);
         # False = call net.encoder as a black box (any encoder with the reference's four outputs)
         self.use_latents = True
+        # 8f-3: the ViT's attention through th_vit_attention (flash-style); False = net.ViT as a black box
+        self.use_flash_vit = True
         # set `profile = True` to have every prologue stage bracketed by CUDA events; `last_prologue_ms` then
         # holds {stage: milliseconds} of the last prepare_frame (bench.py's `plugin` record)
         self.profile = False
@@ -148,6 +150,31 @@ class Renderer:
         if [l.shape[1] for l in latents] != [64, 64, 128]:
             return None
         return ops.EncoderTail(latents, images, enc.upsample_color.weight, enc.upsample_color.bias)
+
+    def _vit_forward(self, tokens, pe):
+        """``net.ViT(tokens, pe, mask=None)`` (vision_transformer.py:371-383) with the attention of every block
+        through ``th_vit_attention`` (8f-3: no (V,3,N,N) attention matrix); LayerNorms, Linear layers and the MLP
+        stay the reference's modules.  Anything that is not the reference's VisionTransformer at inference
+        (dropout / stochastic depth active, other head sizes) is called whole."""
+        vit = self.net.ViT
+        blocks = getattr(vit, 'blocks', None)
+        ok = self.use_flash_vit and blocks is not None and hasattr(vit, 'prepare_tokens') and hasattr(vit, 'norm')
+        if ok:
+            for blk in blocks:
+                a = getattr(blk, 'attn', None)
+                ok = ok and a is not None and all(hasattr(a, n) for n in ('qkv', 'proj', 'num_heads', 'scale')) \
+                    and a.qkv.out_features == 3 * a.num_heads * 64 \
+                    and all(hasattr(blk, n) for n in ('norm1', 'norm2', 'mlp')) \
+                    and (not vit.training or (a.attn_drop.p == 0 and a.proj_drop.p == 0
+                                              and isinstance(blk.drop_path, torch.nn.Identity)))
+        if not ok:
+            return vit(tokens, pe, mask=None)
+        x = vit.prepare_tokens(tokens, pe, None)
+        for blk in blocks:
+            a = blk.attn
+            x = x + a.proj(ops.vit_attention(a.qkv(blk.norm1(x)), a.num_heads, a.scale))
+            x = x + blk.mlp(blk.norm2(x))
+        return vit.norm(x)
 
     def refresh_weights(self):
         """Call after loading a new checkpoint into ``net``."""
@@ -212,7 +239,7 @@ class Renderer:
         tok_rot = ops.group_mean(blend.contiguous(), self.clusters)[:, :3, :3].float() if blend.dtype == torch.float64 \
             else ops.group_mean(blend.float().contiguous(), self.clusters, outer_order=False)[:, :3, :3]
         self._stage("vit")
-        holder = self.net.ViT(grouped.contiguous(), self.normalize_PE(pe), mask=None)
+        holder = self._vit_forward(grouped.contiguous(), self.normalize_PE(pe))
         fs = np.asarray(pixel_scale, dtype=np.float64)
         sc = fs / np.array(image_shape)
         # pre-mapped maps (alpha_res_0 / rgb_res_0 / rgb_res_1 applied to the maps once per frame, tcgen05 GEMM over
