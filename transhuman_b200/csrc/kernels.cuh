@@ -41,8 +41,9 @@ struct CullGrid {
   float ox, oy, oz, inv_h;
   int nx, ny, nz, ncell;
   int* cell_start;   // (ncell + 1)
-  int* cursor;       // (ncell) build scratch
+  int* cursor;       // (ncell) build scratch; after the build: 1 where the 3 x 3 x 3 block around the cell holds a vertex
   float4* sorted;    // (n_verts) vertices grouped by cell
+  int covers;        // the grid box spans every vertex + one cell (no dimension was clamped to MAX_DIM)
 };
 inline size_t cull_grid_bytes(int n_verts) {
   size_t cells = (size_t)CullGrid::MAX_DIM * CullGrid::MAX_DIM * CullGrid::MAX_DIM;

@@ -101,12 +101,16 @@ class Renderer:
         self.voxel_PE_can = torch.stack([self.vertex_can[mem[st[c]:st[c + 1]]].mean(0) for c in range(num_voxel)])
         self._weights = None
         self._weights_key = None
+        self._mlp_params = None
         self.last_counters = None
         # 8f-2: run only the encoder's backbone and evaluate its tail inside the CUDA kernels (see prepare_frame);
         # False = call net.encoder as a black box (any encoder with the reference's four outputs)
         self.use_latents = True
         # 8f-3: the ViT's attention through th_vit_attention (flash-style); False = net.ViT as a black box
         self.use_flash_vit = True
+        # replay the ViT's blocks as one CUDA graph per token shape (inference only)
+        self.use_vit_graph = True
+        self._vit_graphs = {}
         # set `profile = True` to have every prologue stage bracketed by CUDA events; `last_prologue_ms` then
         # holds {stage: milliseconds} of the last prepare_frame (bench.py's `plugin` record)
         self.profile = False
@@ -119,8 +123,16 @@ class Renderer:
         lo, hi = self.CR[:3][None, None].to(PE.device), self.CR[3:][None, None].to(PE.device)
         return ((((PE - lo) / (hi - lo)) - 0.5) * 2).type(torch.float32)
 
+    def _weights_fingerprint(self):
+        """(data_ptr, in-place version) of every per-point-network parameter: changes when a checkpoint is loaded
+        (load_state_dict copies in place -> version bump) or a parameter is replaced.  32 small tensors."""
+        if self._mlp_params is None:
+            self._mlp_params = [prm for name, prm in self.net.named_parameters()
+                                if not name.startswith(('encoder.', 'ViT.'))]
+        return tuple((prm.data_ptr(), prm._version) for prm in self._mlp_params)
+
     def _packed_weights(self, V, device):
-        key = (V, str(device))
+        key = (V, str(device), self._weights_fingerprint() if hasattr(self.net, 'named_parameters') else None)
         if self._weights is None or self._weights_key != key:
             self._weights = ops.PackedWeights(self.net.state_dict(), V, device=device)
             self._weights_key = key
@@ -169,16 +181,47 @@ class Renderer:
                                               and isinstance(blk.drop_path, torch.nn.Identity)))
         if not ok:
             return vit(tokens, pe, mask=None)
+        if not self.use_vit_graph or torch.is_grad_enabled():
+            return self._vit_blocks(tokens, pe)
+        # The ~130 small launches of the 12 blocks replayed as ONE CUDA graph per (shape, device): at 300 tokens
+        # the ViT is launch-bound (2.5 ms of Python + launch latency for ~0.4 ms of kernels).  Static input / output
+        # buffers; the parameters are read through their own storage, so in-place weight updates are seen.
+        key = (tuple(tokens.shape), str(tokens.device), tuple((p.data_ptr(), p.dtype) for p in vit.parameters()))
+        ent = self._vit_graphs.get(key)
+        if ent is None:
+            st_tok, st_pe = tokens.clone(), pe.clone()
+            side = torch.cuda.Stream(device=tokens.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up off the capture (cuBLAS workspaces, autotune)
+                for _ in range(2):
+                    self._vit_blocks(st_tok, st_pe)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st_out = self._vit_blocks(st_tok, st_pe)
+            ent = self._vit_graphs[key] = (graph, st_tok, st_pe, st_out)
+            if len(self._vit_graphs) > 8:          # shapes rarely change; do not hoard graphs
+                self._vit_graphs.pop(next(iter(self._vit_graphs)))
+        graph, st_tok, st_pe, st_out = ent
+        st_tok.copy_(tokens)
+        st_pe.copy_(pe)
+        graph.replay()
+        return st_out.clone()
+
+    def _vit_blocks(self, tokens, pe):
+        vit = self.net.ViT
         x = vit.prepare_tokens(tokens, pe, None)
-        for blk in blocks:
+        for blk in vit.blocks:
             a = blk.attn
             x = x + a.proj(ops.vit_attention(a.qkv(blk.norm1(x)), a.num_heads, a.scale))
             x = x + blk.mlp(blk.norm2(x))
         return vit.norm(x)
 
     def refresh_weights(self):
-        """Call after loading a new checkpoint into ``net``."""
+        """Forces a re-pack (only needed after REPLACING parameter tensors of ``net``; in-place updates such as
+        ``load_state_dict`` are detected through the tensors' version counters)."""
         self._weights = None
+        self._mlp_params = None
 
     def _stage(self, name):
         """Marks the start of a prologue stage (CUDA event on the current stream when profiling)."""
