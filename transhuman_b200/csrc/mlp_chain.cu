@@ -1254,7 +1254,42 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     TH_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)num_sms * STATS_PER_CTA * 8, st));
     pg.stats = d_stats;
   }
-  k_chain<<<2 * nclusters, NUM_THREADS, SMEM_BYTES, st>>>(pg);
+  // TH_CHAIN_L2WIN=1 (experiment, profiles/README.md): an access-policy window over the per-CTA scratch asks L2 to
+  // keep those lines (persisting) while the chunk inputs stream past them.
+  static const int l2win = getenv("TH_CHAIN_L2WIN") ? atoi(getenv("TH_CHAIN_L2WIN")) : 0;
+  if (l2win) {
+    int dev = 0, max_persist = 0, max_win = 0;
+    TH_CUDA(cudaGetDevice(&dev));
+    TH_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    TH_CUDA(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    const size_t scr = (size_t)(2 * nclusters) * scratch_stride(V);
+    const size_t persist = scr < (size_t)max_persist ? scr : (size_t)max_persist;
+    static bool limit_set[64] = {false};
+    if (!limit_set[dev & 63]) {
+      TH_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
+      limit_set[dev & 63] = true;
+      fprintf(stderr, "[chain] L2 window: scratch %zu MB, persisting limit %zu MB (max %d MB), window max %d MB\n",
+              scr >> 20, persist >> 20, max_persist >> 20, max_win >> 20);
+    }
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeAccessPolicyWindow;
+    attr.val.accessPolicyWindow.base_ptr = scratch;
+    attr.val.accessPolicyWindow.num_bytes = scr < (size_t)max_win ? scr : (size_t)max_win;
+    attr.val.accessPolicyWindow.hitRatio = (float)((double)persist / (double)attr.val.accessPolicyWindow.num_bytes);
+    if (attr.val.accessPolicyWindow.hitRatio > 1.f) attr.val.accessPolicyWindow.hitRatio = 1.f;
+    attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * nclusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    TH_CUDA(cudaLaunchKernelEx(&cfg, k_chain, pg));
+  } else {
+    k_chain<<<2 * nclusters, NUM_THREADS, SMEM_BYTES, st>>>(pg);
+  }
   TH_LAUNCHED();
   if (want_stats) {
     static int printed = 0;
