@@ -18,7 +18,9 @@ def _ref_attention(qkv, H, scale, dtype):
     return (attn @ v).transpose(1, 2).reshape(B, N, C)
 
 
-@pytest.mark.parametrize("B,N", [(3, 300), (1, 1), (2, 129), (3, 1500), (1, 64), (2, 193)])
+# (3, 6000) and (3, 4321) fill the machine with pairs of query tiles (k_attn_tc<2>); the others run k_attn_tc<1>
+@pytest.mark.parametrize("B,N", [(3, 300), (1, 1), (2, 129), (3, 1500), (1, 64), (2, 193), (1, 128), (1, 65),
+                                 (3, 6000), (3, 4321)])
 def test_vit_attention_matches_float64(B, N):
     H, D = 3, 64
     g = torch.Generator("cpu").manual_seed(N)
