@@ -65,6 +65,20 @@ class _Cfg:
     time_steps = 1
 
 
+def make(n_tok: int, device, size: int = 512):
+    """(Renderer, batch) of one synthetic frame with the genuine Network (tools/profile_plugin_frame.py)."""
+    from transhuman_b200 import synth
+    from transhuman_b200.renderer import Renderer
+    g = torch.Generator().manual_seed(7)
+    imgs = torch.rand((1, 3, 3, size, size), generator=g)
+    fr = synth.make_frame(H=size, W=size, n_class=n_tok, V=3, feat_hw=size, seed=0, with_feature_maps=False)
+    net, _ = _network(fr, device)
+    cfg = _Cfg()
+    cfg.num_class = n_tok
+    r = Renderer(net, cfg=cfg, pc2voxel_ind=fr["pc2voxel_ind"], vertex_can=synth.make_body(0))
+    return r, _batch(fr, imgs, device)
+
+
 def run(device, size: int = 512, tokens=(300, 1500, 6000)) -> dict:
     from transhuman_b200 import synth
     from transhuman_b200.renderer import Renderer

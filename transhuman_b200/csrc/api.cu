@@ -628,7 +628,10 @@ int th_render_rays(const ThFrame* f, const ThRays* r, ThOut* o, int32_t culled, 
     TH_CUDA(cudaMemsetAsync(ws.counters, 0, 64, st));
     TH_CUDA(cudaMemsetAsync(ws.ray_any, 0, (size_t)N, st));
     if ((rc = launch_grid_build(f->verts, f->n_verts, f->cull_radius, ws.grid, st))) return rc;
-    if ((rc = launch_cull_grid(src, NP, ws.grid, f->cull_radius, m, ws.ids, ws.ray_any, ws.counters, st))) return rc;
+    // candidate list of the two-pass cull: the workspace's raw block is idle until the network runs
+    if ((rc = launch_cull_grid(src, NP, ws.grid, f->cull_radius, m, ws.ids, ws.ray_any, ws.counters, st,
+                               reinterpret_cast<int32_t*>(ws.raw))))
+      return rc;
     if ((rc = launch_count_nonzero(ws.ray_any, N, ws.counters + 1, st))) return rc;
     unsigned long long cnt[3] = {0, 0, 0};
     TH_CUDA(cudaMemcpyAsync(cnt, ws.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
@@ -683,7 +686,9 @@ int th_query_density(const ThFrame* f, const float* pts, int64_t n_points, float
   TH_CUDA(cudaMemsetAsync(ws.counters, 0, 64, st));
   TH_CUDA(cudaMemsetAsync(alpha_raw, 0, (size_t)n_points * 4, st));
   if ((rc = launch_grid_build(f->verts, f->n_verts, f->cull_radius, ws.grid, st))) return rc;
-  if ((rc = launch_cull_grid(src, n_points, ws.grid, f->cull_radius, m, ws.ids, nullptr, ws.counters, st))) return rc;
+  if ((rc = launch_cull_grid(src, n_points, ws.grid, f->cull_radius, m, ws.ids, nullptr, ws.counters, st,
+                             reinterpret_cast<int32_t*>(ws.raw))))
+    return rc;
   unsigned long long cnt = 0;
   TH_CUDA(cudaMemcpyAsync(&cnt, ws.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
   TH_CUDA(cudaStreamSynchronize(st));

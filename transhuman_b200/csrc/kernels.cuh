@@ -44,6 +44,9 @@ struct CullGrid {
   int* cursor;       // (ncell) build scratch; after the build: 1 where the 3 x 3 x 3 block around the cell holds a vertex
   float4* sorted;    // (n_verts) vertices grouped by cell
   int covers;        // the grid box spans every vertex + one cell (no dimension was clamped to MAX_DIM)
+  float d2_max;      // largest float d2 with sqrt_rn(d2) < radius: `sqrt(d2) < radius` <=> `d2 <= d2_max` (sqrt_rn is monotonic)
+  float prune2;      // (radius + 1e-4)^2: a cell row farther than this from the point cannot hold a vertex within radius
+  float h;           // cell size
 };
 inline size_t cull_grid_bytes(int n_verts) {
   size_t cells = (size_t)CullGrid::MAX_DIM * CullGrid::MAX_DIM * CullGrid::MAX_DIM;
@@ -56,8 +59,11 @@ int launch_sample_points(const PointSource& src, int64_t n_points, float* pts, f
 int launch_cull_brute(const PointSource& src, int64_t n_points, const float* verts, int n_verts, float radius,
                       float* d2, int64_t* idx, uint8_t* mask, cudaStream_t st);
 int launch_grid_build(const float* verts, int n_verts, float radius, void* grid_mem, cudaStream_t st);
+// cand (optional, >= n_points int32 of scratch; needs counters): two-pass form -- classify, then scan the candidates
+// with full warps; counters[3] = candidate count
 int launch_cull_grid(const PointSource& src, int64_t n_points, const void* grid_mem, float radius, uint8_t* mask,
-                     int32_t* ids, uint8_t* ray_any, unsigned long long* counters, cudaStream_t st);
+                     int32_t* ids, uint8_t* ray_any, unsigned long long* counters, cudaStream_t st,
+                     int32_t* cand = nullptr);
 int launch_count_nonzero(const uint8_t* flags, int64_t n, unsigned long long* out, cudaStream_t st);
 int launch_expand_rays(const uint8_t* ray_any, int64_t n_points, int S, uint8_t* mask, int32_t* ids,
                        unsigned long long* counter, cudaStream_t st);
