@@ -47,11 +47,13 @@ struct CullGrid {
   float d2_max;      // largest float d2 with sqrt_rn(d2) < radius: `sqrt(d2) < radius` <=> `d2 <= d2_max` (sqrt_rn is monotonic)
   float prune2;      // (radius + 1e-4)^2: a cell row farther than this from the point cannot hold a vertex within radius
   float h;           // cell size
+  float4* rowbox;    // (ncell, 2): bounding box (min, max) of the vertices in cells x-1 .. x+1 of the cell's row --
+                     // the range one step of the 27-cell scan reads; an empty range has min = +inf, max = -inf
 };
 inline size_t cull_grid_bytes(int n_verts) {
   size_t cells = (size_t)CullGrid::MAX_DIM * CullGrid::MAX_DIM * CullGrid::MAX_DIM;
   return align_up(sizeof(CullGrid), 256) + align_up((cells + 1) * 4, 256) + align_up(cells * 4, 256) +
-         align_up((size_t)n_verts * 16, 256);
+         align_up((size_t)n_verts * 16, 256) + align_up(cells * 32, 256);
 }
 
 // ---- geometry.cu -------------------------------------------------------------
