@@ -547,9 +547,10 @@ def main():
                 "l2_bytes_per_launch": l2_bytes,
                 "l2_tbs_live": (l2_bytes * (gemm_launches // args.steps) / (gemm_ms_step * 1e-3) / 1e12
                                 if l2_bytes and gemm_ms_step > 0 else None),
-                "binding": ("chip-level L2 throughput (operand stream ~85 % of the ~6300 B/clk cap) together with the "
-                            "job pipeline's attention-mix bubble; tensor pipe ~60 % active" if chain
-                            else "HBM (K=256 layers) / tensor (K>=512)"),
+                "binding": ("latency of the job pipeline (layer -> epilogue -> store -> fence -> TMA -> next layer at a "
+                            "dependency distance of three jobs, plus the attention-mix window): MMA issuer busy ~47 % of a "
+                            "unit, tensor pipe ~60 % active; neither HBM (2.6 TB/s of 6.55) nor L2 bound (DESIGN 4-5)"
+                            if chain else "HBM (K=256 layers) / tensor (K>=512)"),
                 "hbm_algorithmic_gbs": BYTES_PER_RAY * N_rays / (ms_step * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
     breakdown = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
