@@ -262,3 +262,31 @@ def test_synth_frame_is_deterministic():
     assert sorted(np.unique(a["pc2voxel_ind"])) == list(range(100))
     v = a["tar_smpl_vertice"]
     assert v.shape == (6890, 3) and abs(v[:, 0]).max() < 0.95 and v[:, 1].min() > -1.25
+
+
+def test_prologue_entry_points_validate_their_arguments(lib):
+    """Argument errors of the SURVEY 8f entry points come back as TH_EINVAL (-1) with a message -- no device needed,
+    nothing is launched -- and the workspace queries are pure host arithmetic."""
+    enc = _lib.ThEncoderTail()
+    dummy = np.zeros(64, dtype=np.float32)
+    p = C.c_void_p(dummy.ctypes.data)
+    assert lib.th_premap_from_latents(C.byref(enc), p, p, p, 1 << 20, None) == -1        # null latents
+    assert b"th_premap_from_latents" in lib.th_last_error() or b"enc_views" in lib.th_last_error()
+    for i in range(3):
+        enc.latent[i], enc.lat_h[i], enc.lat_w[i] = dummy.ctypes.data, 4, 4
+    enc.images, enc.color_w, enc.color_b = dummy.ctypes.data, dummy.ctypes.data, dummy.ctypes.data
+    enc.n_views, enc.h, enc.w = 9, 8, 8                                                   # more than TH_MAX_VIEWS
+    assert lib.th_premap_from_latents(C.byref(enc), p, p, p, 1 << 20, None) == -1
+    enc.n_views = 3
+    need = lib.th_premap_from_latents_workspace_bytes(C.byref(enc))
+    assert need >= 3 * 16 * 512 * 4 and need % 256 == 0                                   # three 4 x 4 levels of 512 floats
+    assert lib.th_premap_from_latents(C.byref(enc), p, p, p, need - 256, None) == -1      # workspace too small
+    assert lib.th_paint_group_latents_workspace_bytes(3, 6890, 300) >= 3 * 6890 * 384 * 4
+    assert lib.th_paint_group_latents(C.byref(enc), p, p, 1.0, 1.0, p, 6890, p, p, p, None, p, p, 300, p, p, 16, None) == -1
+    # attention: vit_tiny's head size only; workspace = the operand images (query tiles in pairs of 128, key tiles of 64)
+    assert lib.th_vit_attention(p, 1, 8, 3, 32, 1.0, p, p, 1 << 20, None) == -1
+    assert b"head_dim" in lib.th_last_error()
+    assert lib.th_vit_attention(p, 1, 0, 3, 64, 1.0, p, p, 1 << 20, None) == -1
+    ws = lib.th_vit_attention_workspace_bytes(3, 6000, 3)
+    assert ws == 9 * (24 * 2 * 32768 + 94 * 32768)
+    assert lib.th_vit_attention(p, 3, 6000, 3, 64, 0.125, p, C.c_void_p(256), ws - 256, None) == -1
