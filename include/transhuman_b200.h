@@ -279,6 +279,24 @@ int th_paint_group_latents(const ThEncoderTail* enc, const float* reduction_w, c
                            const float* cam_T, const float* cam_K, const uint8_t* vizmap, const int32_t* cluster_start,
                            const int32_t* cluster_members, int32_t n_tok, float* tokens, void* workspace,
                            size_t workspace_bytes, void* stream);
+/* ---- mesh extraction ---------------------------------------------------------- */
+/* The step after the density-grid query: if_mesh_renderer.py:98-104 pads the cube by 10 voxels on the CPU and calls
+ * the third-party `mcubes.marching_cubes(cube, cfg.mesh_th)`.  th_marching_cubes runs marching cubes on a DEVICE
+ * volume (nx,ny,nz) fp32 (dim 0 = x slowest ... dim 2 = z fastest, like the numpy cube): a corner is inside when its
+ * value is > iso; one vertex per cut lattice edge at a + (iso - v_a) / (v_b - v_a) in index coordinates (fp32; the
+ * caller applies voxel_size and the lower bound as lines 106-109 do); triangles (vertex ids) from a 256-case table.
+ * PyMCubes is not available to this repository (absent from the reference tree and unpinned), so its table is not
+ * reproduced: the table is derived (tools/gen_mc_table.py) -- surfaces differ from mcubes' only in how ambiguous
+ * faces are joined and polygons fanned.  Indexed, duplicate-free, deterministic order (vertices by lattice edge,
+ * triangles by cube).  counts_host[0..1] (HOST) receive the vertex and triangle counts -- the call synchronises the
+ * stream for that; vertices / triangles may be NULL (count only) and are filled up to max_vertices / max_triangles
+ * (TH_EWORKSPACE if a non-NULL buffer was too small).  workspace (DEVICE, 256-byte aligned) >=
+ * th_marching_cubes_workspace_bytes(nx, ny, nz) (12 bytes per voxel). */
+size_t th_marching_cubes_workspace_bytes(int32_t nx, int32_t ny, int32_t nz);
+int th_marching_cubes(const float* volume, int32_t nx, int32_t ny, int32_t nz, float iso, float* vertices,
+                      int64_t max_vertices, int32_t* triangles, int64_t max_triangles, int64_t* counts_host,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- token transformer attention ---------------------------------------------- */
 /* Attention.forward between its two Linear layers (vision_transformer.py:267-275) for vit_tiny (3 heads of 64):
  * qkv (B,N,3,H,64) fp32 = the output of `self.qkv` viewed as in line 269; out (B,N,H*64) fp32 = the input of

@@ -164,6 +164,15 @@ def test_mesh_renderer_cube():
     mb["can_bounds"] = torch.tensor([[grid.reshape(-1, 3).min(0), grid.reshape(-1, 3).max(0)]])
     ret = mr.render(mb)
     assert ret["cube"].shape == (60, 60, 60) and np.all(ret["cube"][:10] == 0)
+    # the mesh step (if_mesh_renderer.py:98-109) through th_marching_cubes -- mcubes is not installed here -- against
+    # the numpy oracle on the same cube, with the reference's index -> world transform
+    from oracle import marching_cubes as omc
+    cfg = _Cfg()
+    v, f = ret["mesh"].vertices, ret["mesh"].faces
+    wv, wf = omc.marching_cubes(ret["cube"], cfg.mesh_th)
+    assert len(f) > 50 and np.array_equal(f, wf)
+    lb = grid.reshape(-1, 3).min(0) - 10 * np.array(cfg.voxel_size)
+    assert np.allclose(v, wv.astype(np.float64) * np.array(cfg.voxel_size) + lb, atol=1e-12)
     tf, tokens = _oracle_frame(fr, mr, mb)
     walpha, wmask = orc.query_density(tf, torch.from_numpy(grid.reshape(-1, 3)), tokens=tokens)
     got = torch.from_numpy(ret["cube"][10:-10, 10:-10, 10:-10]).reshape(-1)

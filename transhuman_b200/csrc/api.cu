@@ -937,6 +937,41 @@ int th_paint_group_latents(const ThEncoderTail* enc, const float* reduction_w, c
                                     cluster_members, n_tok, scratch, tokens, st);
 }
 
+size_t th_marching_cubes_workspace_bytes(int32_t nx, int32_t ny, int32_t nz) {
+  if (nx < 1 || ny < 1 || nz < 1) return 256;
+  return marching_cubes_workspace_bytes(nx, ny, nz);
+}
+
+int th_marching_cubes(const float* volume, int32_t nx, int32_t ny, int32_t nz, float iso, float* vertices,
+                      int64_t max_vertices, int32_t* triangles, int64_t max_triangles, int64_t* counts_host,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TH_CHECK_ARG(volume && counts_host && workspace, "null pointer");
+  TH_CHECK_ARG(nx >= 1 && ny >= 1 && nz >= 1 && (int64_t)nx * ny * nz < (1LL << 31) / 3, "bad volume size");
+  TH_CHECK_ARG(max_vertices >= 0 && max_triangles >= 0, "bad capacity");
+  TH_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  if (workspace_bytes < th_marching_cubes_workspace_bytes(nx, ny, nz)) {
+    set_error("th_marching_cubes: workspace %zu < %zu bytes", workspace_bytes, th_marching_cubes_workspace_bytes(nx, ny, nz));
+    return TH_EWORKSPACE;
+  }
+  unsigned long long* counts_dev =
+      reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + workspace_bytes - 256);
+  int rc = launch_marching_cubes(volume, nx, ny, nz, iso, vertices, vertices ? max_vertices : 0, triangles,
+                                 triangles ? max_triangles : 0, counts_dev, workspace, st);
+  if (rc) return rc;
+  unsigned long long cnt[2] = {0, 0};
+  TH_CUDA(cudaMemcpyAsync(cnt, counts_dev, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  TH_CUDA(cudaStreamSynchronize(st));
+  counts_host[0] = (int64_t)cnt[0];
+  counts_host[1] = (int64_t)cnt[1];
+  if ((vertices && (int64_t)cnt[0] > max_vertices) || (triangles && (int64_t)cnt[1] > max_triangles)) {
+    set_error("th_marching_cubes: %llu vertices / %llu triangles exceed the buffers (%lld / %lld)", cnt[0], cnt[1],
+              (long long)max_vertices, (long long)max_triangles);
+    return TH_EWORKSPACE;
+  }
+  return TH_OK;
+}
+
 size_t th_vit_attention_workspace_bytes(int32_t batch, int32_t n_tokens, int32_t n_heads) {
   if (batch < 1 || n_tokens < 1 || n_heads < 1) return 256;
   return vit_attention_workspace_bytes(batch, n_tokens, n_heads);

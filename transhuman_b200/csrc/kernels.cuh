@@ -66,6 +66,12 @@ int launch_grid_build(const float* verts, int n_verts, float radius, void* grid_
 int launch_cull_grid(const PointSource& src, int64_t n_points, const void* grid_mem, float radius, uint8_t* mask,
                      int32_t* ids, uint8_t* ray_any, unsigned long long* counters, cudaStream_t st,
                      int32_t* cand = nullptr);
+int launch_scan_counts(int32_t* counts, int n, unsigned long long* total, cudaStream_t st);
+// mesh.cu: marching cubes on a device volume (th_marching_cubes)
+size_t marching_cubes_workspace_bytes(int nx, int ny, int nz);
+int launch_marching_cubes(const float* vol, int nx, int ny, int nz, float iso, float* verts, int64_t max_verts,
+                          int32_t* tris, int64_t max_tris, unsigned long long* counts_dev, void* workspace,
+                          cudaStream_t st);
 int launch_count_nonzero(const uint8_t* flags, int64_t n, unsigned long long* out, cudaStream_t st);
 int launch_expand_rays(const uint8_t* ray_any, int64_t n_points, int S, uint8_t* mask, int32_t* ids,
                        unsigned long long* counter, cudaStream_t st);

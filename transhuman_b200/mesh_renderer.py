@@ -2,9 +2,9 @@
 reconstruction.yaml selects it through ``renderer_module``/``renderer_path``).
 
 ``render(batch)`` runs the density-grid query (if_mesh_renderer.py:46-96) on the
-GPU and returns ``{'cube': np.ndarray (X+20,Y+20,Z+20), 'mesh': trimesh or None}``
-(111).  Marching cubes and the mesh object (98-109) come after the path and
-stay on the CPU third-party packages when those are installed.
+GPU and returns ``{'cube': np.ndarray (X+20,Y+20,Z+20), 'mesh': ...}`` (111).  Marching cubes
+(98-109) uses the reference's CPU packages ``mcubes`` / ``trimesh`` when they are installed and
+``th_marching_cubes`` on the device otherwise.
 """
 from __future__ import annotations
 
@@ -27,19 +27,39 @@ class Renderer(_BaseRenderer):
         return alpha.view(*sh[1:4])
 
     def render(self, batch):
-        cube = self.query_cube(batch).detach().cpu().numpy()
-        cube = np.pad(cube, 10, mode='constant')
+        """if_mesh_renderer.py:98-111.  The cube is queried on the GPU; the mesh comes from ``mcubes`` when that
+        package is installed (the reference's own step), else from ``th_marching_cubes`` on the device (SURVEY 8f-4:
+        same vertices-on-edges and world transform, case table derived in tools/gen_mc_table.py); ``mesh`` is a
+        ``trimesh.Trimesh`` if trimesh exists, else a small object with ``.vertices`` / ``.faces``."""
+        cube_dev = torch.nn.functional.pad(self.query_cube(batch).detach(), (10,) * 6)      # np.pad(cube, 10), line 102
+        cube = cube_dev.cpu().numpy()
         mesh = None
-        try:  # if_mesh_renderer.py:98-109 (CPU, third party; out of scope of the CUDA path)
-            import mcubes
-            import trimesh
-            if not (getattr(mcubes, "__file__", None) and getattr(trimesh, "__file__", None)):
-                raise ImportError("mcubes / trimesh are placeholders")      # e.g. the test shim's stub modules
+        if hasattr(self.cfg, 'voxel_size') and hasattr(self.cfg, 'mesh_th'):
+            mcubes, trimesh = _optional('mcubes'), _optional('trimesh')
+            if mcubes is not None:
+                vertices, triangles = mcubes.marching_cubes(cube, self.cfg.mesh_th)
+            else:
+                v, t = ops.marching_cubes(cube_dev, float(self.cfg.mesh_th))
+                vertices, triangles = v.double().cpu().numpy(), t.cpu().numpy()
             voxel_size = np.array(self.cfg.voxel_size)
-            vertices, triangles = mcubes.marching_cubes(cube, self.cfg.mesh_th)
             can_bounds = batch['can_bounds'][0].cpu().numpy()
             LB = (can_bounds[0] - 10 * voxel_size)[None, ...]
-            mesh = trimesh.Trimesh(vertices * voxel_size[None, ...] + LB, triangles)
-        except ImportError:
-            pass
+            vertices_world = vertices * voxel_size[None, ...] + LB                          # lines 106-109
+            mesh = trimesh.Trimesh(vertices_world, triangles) if trimesh is not None else SimpleMesh(vertices_world, triangles)
         return {'cube': cube, 'mesh': mesh}
+
+
+def _optional(name):
+    """The real third-party module, or None (absent, or a placeholder such as the test shim's stub modules)."""
+    try:
+        mod = __import__(name)
+    except ImportError:
+        return None
+    return mod if getattr(mod, "__file__", None) else None
+
+
+class SimpleMesh:
+    """Stand-in for ``trimesh.Trimesh(vertices, faces)`` when trimesh is not installed."""
+
+    def __init__(self, vertices, faces):
+        self.vertices, self.faces = np.asarray(vertices), np.asarray(faces)

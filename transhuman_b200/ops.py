@@ -18,7 +18,7 @@ from ._lib import (TH_FLAG_LAYERWISE, TH_FLAG_PREMAPPED, TH_FLAG_SIMT_MLP, TH_FL
 
 __all__ = ["PackedWeights", "Frame", "render_rays", "query_density", "sample_points", "cull_knn1", "cull_grid",
            "world2smpl", "view_embed", "pixel_gather", "knn_dparf", "mlp_raw", "integrate", "nchw_to_nhwc",
-           "premap_features", "vit_attention", "EncoderTail", "premap_from_latents", "paint_group_latents", "ClusterIndex", "paint_group",
+           "premap_features", "vit_attention", "marching_cubes", "EncoderTail", "premap_from_latents", "paint_group_latents", "ClusterIndex", "paint_group",
            "group_mean", "generate_rays", "near_far",
            "launch_count", "TH_RENDER_DENSE", "TH_RENDER_MASKED", "TH_RENDER_FAST"]
 
@@ -473,6 +473,27 @@ def paint_group_latents(enc: EncoderTail, reduction_w, reduction_b, uv_scale, ve
                                           _ptr(clusters.members), clusters.n_tok, _ptr(out), _ptr(ws), nbytes,
                                           _stream()), "th_paint_group_latents")
     return out
+
+
+def marching_cubes(volume, iso: float):
+    """8f-4: marching cubes on a device volume (X,Y,Z) fp32 (``th_marching_cubes``) -> (vertices (n,3) fp32 in index
+    coordinates, triangles (m,3) int32), both on the device.  One counting call, one emitting call."""
+    lib = _lib.load()
+    vol = _f32(volume, "volume")
+    assert vol.dim() == 3
+    nx, ny, nz = vol.shape
+    nbytes = lib.th_marching_cubes_workspace_bytes(nx, ny, nz)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=vol.device)
+    counts = (C.c_int64 * 2)()
+    _lib.check(lib.th_marching_cubes(_ptr(vol), nx, ny, nz, float(iso), None, 0, None, 0, counts, _ptr(ws), nbytes,
+                                     _stream()), "th_marching_cubes")
+    nv, nt = int(counts[0]), int(counts[1])
+    verts = torch.empty((nv, 3), device=vol.device)
+    tris = torch.empty((nt, 3), dtype=torch.int32, device=vol.device)
+    if nv:
+        _lib.check(lib.th_marching_cubes(_ptr(vol), nx, ny, nz, float(iso), _ptr(verts), nv, _ptr(tris) if nt else None,
+                                         nt, counts, _ptr(ws), nbytes, _stream()), "th_marching_cubes")
+    return verts, tris
 
 
 def vit_attention(qkv, n_heads: int, scale: float):
