@@ -342,9 +342,20 @@ def other_configs(args, device):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 2
+    # the mesh step behind it (if_mesh_renderer.py:98-104): pad 10, marching cubes at the median density
+    cube = torch.nn.functional.pad(alpha.view(256, 256, 256), (10,) * 6)
+    iso = float(alpha[mask.bool()].median()) if int(mask.sum()) else 0.0
+    ops.marching_cubes(cube, iso)
+    torch.cuda.synchronize()
+    e0.record()
+    mv, mt = ops.marching_cubes(cube, iso)
+    e1.record()
+    torch.cuda.synchronize()
     out["c5_grid256_6000tok"] = {"points": pts.shape[0], "inside_radius": int(mask.sum().item()), "ms": ms,
                                  "grid_points_per_s": pts.shape[0] / (ms * 1e-3),
-                                 "evaluated_points_per_s": int(mask.sum().item()) / (ms * 1e-3)}
+                                 "evaluated_points_per_s": int(mask.sum().item()) / (ms * 1e-3),
+                                 "marching_cubes": {"ms": e0.elapsed_time(e1), "grid": list(cube.shape), "iso": iso,
+                                                    "vertices": int(mv.shape[0]), "triangles": int(mt.shape[0])}}
     return out
 
 
