@@ -204,9 +204,14 @@ int th_pixel_gather(const ThFrame* frame, const float* pts, int64_t n_points, fl
                     void* stream);
 /* a8: get_human_representation (cross_transformer.py:158-205): pts (P,3) SMPL
  * coordinates -> knn_idx (P,K) int64, knn_d2 (P,K) squared, human_rep (V,255,P).
- * Outputs may be NULL. */
+ * Outputs may be NULL.  workspace (DEVICE, 256-byte aligned, >= th_knn_workspace_bytes(n_tok)) is optional: with it
+ * the K nearest tokens are searched through a uniform grid over the tokens (shells of cells until the K-th distance
+ * is covered; exactly the same (d2, index)-ordered result as the scan over all tokens, which remains the fall-back
+ * for points far from every token) -- what the fused path does for culled rays and grid points from 1024 tokens on;
+ * NULL = scan all tokens. */
+size_t th_knn_workspace_bytes(int32_t n_tok);
 int th_knn_dparf(const ThFrame* frame, const float* pts_smpl, int64_t n_points, int64_t* knn_idx,
-                 float* knn_d2, float* human_rep, void* stream);
+                 float* knn_d2, float* human_rep, void* workspace, size_t workspace_bytes, void* stream);
 /* a9+a10: the per-point network from its reference inputs
  * (cross_transformer.py:273-353): human_rep (V,255,P), pixel_feat (V,384,P),
  * viewdir (P,27), pts_mask (P) or NULL -> raw (P,4).  With a mask, masked-out

@@ -154,6 +154,34 @@ def test_knn_exact_with_many_tokens():
         g = torch.Generator().manual_seed(n_class)
         body = tf["tar_smpl_vertice_smplcoord"]
         ps = body[torch.randint(0, body.shape[0], (6000,), generator=g)] + torch.randn((6000, 3), generator=g) * 0.03
-        idx, d2, rep = ops.knn_dparf(frame, ps.to(DEV))
         wd2, widx, _ = orc.knn_points(ps[None], tokens[0][None], K=7)
-        assert torch.equal(idx.cpu(), widx[0]) and torch.equal(d2.cpu(), wd2[0])
+        # through the token grid (what the fused path uses at these token counts) and by the scan over all tokens
+        for grid in (True, False):
+            idx, d2, rep = ops.knn_dparf(frame, ps.to(DEV), token_grid=grid)
+            assert torch.equal(idx.cpu(), widx[0]) and torch.equal(d2.cpu(), wd2[0]), (n_class, grid)
+
+
+@pytest.mark.parametrize("n_class,K", [(300, 7), (300, 12), (1500, 1), (6000, 3)])
+def test_token_grid_knn_is_exact_everywhere(n_class, K):
+    """The grid search must return the scan's (d2, index)-ordered result for EVERY point: near the body (one or two
+    shells), in sparse neighbourhoods (three shells, then the fall-back scan), far outside the grid box (fall-back),
+    exactly on tokens (d2 = 0) and with duplicated tokens (equal distances: the lower index first)."""
+    fr = synth.make_frame(H=8, W=8, n_class=n_class, V=1, feat_hw=8, seed=8)
+    tf = orc.to_torch_frame(fr)
+    tok_xyz, tok_blend = orc.build_tokens(tf)
+    tok_xyz = tok_xyz.clone()
+    tok_xyz[5] = tok_xyz[200]                       # duplicates: ties between indices 5 and 200, 17 and 18
+    tok_xyz[18] = tok_xyz[17]
+    frame, _ = frame_to_device(fr, (tok_xyz, tok_blend), DEV)
+    frame.c.knn = K
+    g = torch.Generator().manual_seed(K)
+    body = tf["tar_smpl_vertice_smplcoord"]
+    near = body[torch.randint(0, body.shape[0], (3000,), generator=g)] + torch.randn((3000, 3), generator=g) * 0.02
+    shell = body[torch.randint(0, body.shape[0], (1500,), generator=g)] + torch.randn((1500, 3), generator=g) * 0.15
+    far = torch.randn((500, 3), generator=g) * 3.0
+    on = tok_xyz[torch.randint(0, n_class, (200,), generator=g)].float()
+    ps = torch.cat([near, shell, far, on, tok_xyz[[5, 17, 18, 200]].float()])
+    wd2, widx, _ = orc.knn_points(ps[None], tok_xyz.float()[None], K=K)
+    idx, d2, _ = ops.knn_dparf(frame, ps.to(DEV), token_grid=True)
+    assert torch.equal(d2.cpu(), wd2[0])
+    assert torch.equal(idx.cpu(), widx[0])

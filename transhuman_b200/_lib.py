@@ -91,7 +91,8 @@ SIGNATURES = {
     "th_world2smpl": (C.c_int, [_fp, C.c_int64, _fp, _fp, _fp, _fp]),
     "th_view_embed": (C.c_int, [_fp, C.c_int64, _fp, _fp]),
     "th_pixel_gather": (C.c_int, [C.POINTER(ThFrame), _fp, C.c_int64, _fp, _fp]),
-    "th_knn_dparf": (C.c_int, [C.POINTER(ThFrame), _fp, C.c_int64, _fp, _fp, _fp, _fp]),
+    "th_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "th_knn_dparf": (C.c_int, [C.POINTER(ThFrame), _fp, C.c_int64, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "th_mlp_raw": (C.c_int, [C.POINTER(ThFrame), _fp, _fp, _fp, _fp, C.c_int64, _fp, _fp, C.c_size_t, _fp]),
     "th_integrate": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp]),
     "th_nchw_to_nhwc": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp]),

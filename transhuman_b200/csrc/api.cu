@@ -396,8 +396,15 @@ struct Workspace {
   float* raw;
   float* chunk;
   int64_t chunk_pts;
+  unsigned char* tok_grid;  // token grid of the K-NN (culled rays / density grid with >= TOKEN_GRID_MIN tokens)
 };
 
+constexpr int TOKEN_GRID_MAX = 65536;  // tokens the reserved grid block can hold (th_workspace_bytes has no token count)
+// TH_TOKEN_GRID=<n>: use the token grid from n tokens on (default TOKEN_GRID_MIN; a huge n = never) -- measurement knob
+static int token_grid_min() {
+  static const int v = getenv("TH_TOKEN_GRID") ? atoi(getenv("TH_TOKEN_GRID")) : TOKEN_GRID_MIN;
+  return v;
+}
 static size_t ws_plan(int64_t n_points, int V, int n_verts, unsigned char* base, Workspace* ws) {
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -414,7 +421,9 @@ static size_t ws_plan(int64_t n_points, int V, int n_verts, unsigned char* base,
   unsigned char* raw = take((size_t)np * 16);
   int64_t cp = np < chunk_pts() ? np : chunk_pts();
   unsigned char* chunk = take((size_t)pad_points(cp) * mlp_buffer_floats_per_point(V) * 4 + 1024);
+  unsigned char* tok_grid = take(n_verts > 0 ? cull_grid_bytes(TOKEN_GRID_MAX) : 0);
   if (ws) {
+    ws->tok_grid = n_verts > 0 ? tok_grid : nullptr;
     ws->grid = grid;
     ws->counters = reinterpret_cast<unsigned long long*>(counters);
     ws->ray_any = ray_any;
@@ -461,6 +470,7 @@ static int frame_dev(const ThFrame* f, FrameDev* d, bool need_tokens, bool need_
   d->sx = f->uv_scale_x;
   d->sy = f->uv_scale_y;
   d->knn_alpha = f->knn_dist_alpha;
+  d->tok_grid = nullptr;
   return TH_OK;
 }
 
@@ -654,6 +664,11 @@ int th_render_rays(const ThFrame* f, const ThRays* r, ThOut* o, int32_t culled, 
       o->counters_host[2] = n_eval;
     }
     if (o->raw) TH_CUDA(cudaMemsetAsync(o->raw, 0, (size_t)NP * 16, st));
+    // every evaluated point lies within the cull radius of the body: its K nearest tokens come from the token grid
+    if (ws.tok_grid && fr.n_tok >= token_grid_min() && fr.n_tok <= TOKEN_GRID_MAX && n_eval > 0) {
+      if ((rc = launch_token_grid(fr.tok_xyz, fr.n_tok, ws.tok_grid, st))) return rc;
+      fr.tok_grid = reinterpret_cast<const CullGrid*>(ws.tok_grid);
+    }
     if ((rc = run_points(f, fr, hdr, src, ws.ids, n_eval, ws, raw, nullptr, 0, zero_rgb, st))) return rc;
     mask = integ_mask;
   }
@@ -692,6 +707,10 @@ int th_query_density(const ThFrame* f, const float* pts, int64_t n_points, float
   unsigned long long cnt = 0;
   TH_CUDA(cudaMemcpyAsync(&cnt, ws.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
   TH_CUDA(cudaStreamSynchronize(st));
+  if (ws.tok_grid && fr.n_tok >= token_grid_min() && fr.n_tok <= TOKEN_GRID_MAX && cnt > 0) {
+    if ((rc = launch_token_grid(fr.tok_xyz, fr.n_tok, ws.tok_grid, st))) return rc;
+    fr.tok_grid = reinterpret_cast<const CullGrid*>(ws.tok_grid);
+  }
   return run_points(f, fr, hdr, src, ws.ids, (int64_t)cnt, ws, nullptr, alpha_raw, 1, 0, st);
 }
 
@@ -766,12 +785,21 @@ int th_pixel_gather(const ThFrame* f, const float* pts, int64_t n_points, float*
   return launch_features(fr, src, n_points, fo, static_cast<cudaStream_t>(stream));
 }
 
+size_t th_knn_workspace_bytes(int32_t n_tok) { return cull_grid_bytes(n_tok > 0 ? n_tok : 1); }
+
 int th_knn_dparf(const ThFrame* f, const float* pts_smpl, int64_t n_points, int64_t* knn_idx, float* knn_d2,
-                 float* human_rep, void* stream) {
+                 float* human_rep, void* workspace, size_t workspace_bytes, void* stream) {
   TH_CHECK_ARG(pts_smpl, "null pointer");
   FrameDev fr;
   int rc = frame_dev(f, &fr, true, false);
   if (rc) return rc;
+  // with a workspace the K-NN goes through the token grid (what the fused path does for culled rays / grid points)
+  if (workspace && fr.n_tok <= TOKEN_GRID_MAX) {
+    TH_CHECK_ARG(workspace_bytes >= cull_grid_bytes(fr.n_tok) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                 "token-grid workspace too small or misaligned");
+    if ((rc = launch_token_grid(fr.tok_xyz, fr.n_tok, workspace, static_cast<cudaStream_t>(stream)))) return rc;
+    fr.tok_grid = static_cast<const CullGrid*>(workspace);
+  }
   PointSource src{};
   src.pts = pts_smpl;
   src.n_samples = 1;

@@ -6,11 +6,15 @@
 
 namespace th {
 
+struct CullGrid;
 // Frame parameters as the kernels see them (by value).
 struct FrameDev {
   const float *tok_feat, *tok_xyz, *tok_rot, *feat, *cam_R, *cam_T, *cam_K, *Rh, *Th;
   int V, n_tok, H, W, K;
   float sx, sy, knn_alpha;
+  // uniform grid over the token positions (launch_token_grid) for the exact K-NN of points near the body; nullptr =
+  // scan all tokens from shared memory
+  const CullGrid* tok_grid;
 };
 
 // Output description of k_features.  Element (v, p, c) of the DPaRF
@@ -61,6 +65,10 @@ int launch_sample_points(const PointSource& src, int64_t n_points, float* pts, f
 int launch_cull_brute(const PointSource& src, int64_t n_points, const float* verts, int n_verts, float radius,
                       float* d2, int64_t* idx, uint8_t* mask, cudaStream_t st);
 int launch_grid_build(const float* verts, int n_verts, float radius, void* grid_mem, cudaStream_t st);
+// token grid for the K-NN (geometry.cu: knn_grid): the same structure over tok_xyz, cell size from the token density;
+// grid_mem >= cull_grid_bytes(n_tok).  Worth it from TOKEN_GRID_MIN tokens on (1500- and 6000-token configs).
+constexpr int TOKEN_GRID_MIN = 1024;
+int launch_token_grid(const float* tok_xyz, int n_tok, void* grid_mem, cudaStream_t st);
 // cand (optional, >= n_points int32 of scratch; needs counters): two-pass form -- classify, then scan the candidates
 // with full warps; counters[3] = candidate count
 int launch_cull_grid(const PointSource& src, int64_t n_points, const void* grid_mem, float radius, uint8_t* mask,

@@ -285,15 +285,23 @@ def pixel_gather(frame: Frame, pts_world):
     return out
 
 
-def knn_dparf(frame: Frame, pts_smpl):
+def knn_dparf(frame: Frame, pts_smpl, token_grid=None):
+    """a8 staged.  ``token_grid``: search the K nearest tokens through the token grid (True), by the scan over all
+    tokens (False), or like the fused path does for culled rays / grid points (None: grid from 1024 tokens on)."""
     lib = _lib.load()
     pts = _f32(pts_smpl, "pts").view(-1, 3)
     P, K = pts.shape[0], frame.c.knn
     idx = torch.empty((P, K), dtype=torch.int64, device=pts.device)
     d2 = torch.empty((P, K), device=pts.device)
     rep = torch.empty((frame.V, 255, P), device=pts.device)
-    _lib.check(lib.th_knn_dparf(C.byref(frame.c), _ptr(pts), P, _ptr(idx), _ptr(d2), _ptr(rep), _stream()),
-               "th_knn_dparf")
+    if token_grid is None:
+        token_grid = frame.c.n_tok >= 1024
+    ws, nbytes = None, 0
+    if token_grid:
+        nbytes = lib.th_knn_workspace_bytes(frame.c.n_tok)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=pts.device)
+    _lib.check(lib.th_knn_dparf(C.byref(frame.c), _ptr(pts), P, _ptr(idx), _ptr(d2), _ptr(rep), _ptr(ws), nbytes,
+                                _stream()), "th_knn_dparf")
     return idx, d2, rep
 
 
