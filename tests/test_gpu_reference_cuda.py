@@ -201,7 +201,7 @@ def test_plugin_vit_forward_matches_reference_vit(n_tok):
     fr = synth.make_frame(H=8, W=8, n_class=300, V=3, feat_hw=16, seed=3, with_feature_maps=False)
     ns, net, renderer, batch = build_reference(fr, 8, device="cuda", knn=_knn_cuda, fake_prologue=False)
     ours = Renderer.__new__(Renderer)
-    ours.net, ours.use_flash_vit, ours.use_vit_graph, ours._vit_graphs = net, True, True, {}
+    ours.net, ours.use_flash_vit, ours.use_cuda_graphs, ours._graphs = net, True, True, {}
     g = torch.Generator("cpu").manual_seed(n_tok)
     tokens = torch.randn((3, n_tok, 192), generator=g).to(DEV)
     pe = (torch.rand((3, n_tok, 3), generator=g) * 2 - 1).to(DEV)
@@ -210,10 +210,10 @@ def test_plugin_vit_forward_matches_reference_vit(n_tok):
         got = ours._vit_forward(tokens.clone(), pe)            # captures the CUDA graph
         again = ours._vit_forward(tokens.clone(), pe)          # replays it
         other = ours._vit_forward(tokens.clone() * 0.5, pe)    # new inputs through the same graph
-        ours.use_vit_graph = False
+        ours.use_cuda_graphs = False
         eager = ours._vit_forward(tokens.clone(), pe)
         other_eager = ours._vit_forward(tokens.clone() * 0.5, pe)
-        assert len(ours._vit_graphs) == 1
+        assert len(ours._graphs) == 1
         assert torch.equal(got, again)
         # replayed vs eager launches of the same kernels (cuBLAS may pick another algorithm under capture)
         assert float((got - eager).abs().max()) <= 2e-6 and float((other - other_eager).abs().max()) <= 2e-6

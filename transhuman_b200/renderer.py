@@ -108,9 +108,9 @@ class Renderer:
         self.use_latents = True
         # 8f-3: the ViT's attention through th_vit_attention (flash-style); False = net.ViT as a black box
         self.use_flash_vit = True
-        # replay the ViT's blocks as one CUDA graph per token shape (inference only)
-        self.use_vit_graph = True
-        self._vit_graphs = {}
+        # replay the chains of small torch launches (encoder backbone, ViT blocks) as CUDA graphs (inference only)
+        self.use_cuda_graphs = True
+        self._graphs = {}
         # set `profile = True` to have every prologue stage bracketed by CUDA events; `last_prologue_ms` then
         # holds {stage: milliseconds} of the last prepare_frame (bench.py's `plugin` record)
         self.profile = False
@@ -150,18 +150,52 @@ class Renderer:
               and tuple(enc.reduction_layer.weight.shape[:2]) == (192, 384))
         if not ok:
             return None
-        # channels_last memory format: cuDNN's native layout, and the latents come out channel-last in place -- the
-        # layout th_premap_from_latents / th_paint_group_latents read (same values; only the strides differ)
-        x = m.relu(m.bn1(m.conv1(images.contiguous(memory_format=torch.channels_last))))
-        latents = [x]
-        if enc.use_first_pool:
-            x = m.maxpool(x)
-        x = m.layer1(x)
-        latents.append(x)
-        latents.append(m.layer2(x))
+        def backbone(img):
+            # channels_last memory format: cuDNN's native layout, and the latents come out channel-last in place -- the
+            # layout th_premap_from_latents / th_paint_group_latents read (same values; only the strides differ)
+            x = m.relu(m.bn1(m.conv1(img.contiguous(memory_format=torch.channels_last))))
+            lat = [x]
+            if enc.use_first_pool:
+                x = m.maxpool(x)
+            x = m.layer1(x)
+            lat.append(x)
+            lat.append(m.layer2(x))
+            return tuple(lat)
+
+        latents = self._graphed(("encoder", tuple(images.shape), str(images.device),
+                                 tuple((p.data_ptr(), p.dtype) for p in m.parameters())), backbone, images)
         if [l.shape[1] for l in latents] != [64, 64, 128]:
             return None
-        return ops.EncoderTail(latents, images, enc.upsample_color.weight, enc.upsample_color.bias)
+        return ops.EncoderTail(list(latents), images, enc.upsample_color.weight, enc.upsample_color.bias)
+
+    def _graphed(self, key, fn, *inputs):
+        """``fn(*inputs)`` (a tuple of tensors, or one tensor) replayed as ONE CUDA graph per key -- the chains of
+        small launches of the reference's torch modules are bound by Python + launch latency, not by the GPU.  Static
+        input / output buffers; parameters are read through their own storage, so in-place weight updates are seen.
+        Inference only (no grad); ``use_cuda_graphs = False`` runs eagerly."""
+        if not self.use_cuda_graphs or torch.is_grad_enabled():
+            return fn(*inputs)
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_in = [x.clone() for x in inputs]
+            side = torch.cuda.Stream(device=inputs[0].device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up off the capture (cuDNN / cuBLAS workspaces, autotune)
+                for _ in range(2):
+                    fn(*static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = fn(*static_in)
+            ent = self._graphs[key] = (graph, static_in, static_out)
+            if len(self._graphs) > 16:             # shapes rarely change; do not hoard graphs
+                self._graphs.pop(next(iter(self._graphs)))
+        graph, static_in, static_out = ent
+        for dst, src in zip(static_in, inputs):
+            dst.copy_(src)
+        graph.replay()
+        # the static outputs are overwritten by the next replay: hand out copies
+        return tuple(o.clone() for o in static_out) if isinstance(static_out, tuple) else static_out.clone()
 
     def _vit_forward(self, tokens, pe):
         """``net.ViT(tokens, pe, mask=None)`` (vision_transformer.py:371-383) with the attention of every block
@@ -181,32 +215,8 @@ class Renderer:
                                               and isinstance(blk.drop_path, torch.nn.Identity)))
         if not ok:
             return vit(tokens, pe, mask=None)
-        if not self.use_vit_graph or torch.is_grad_enabled():
-            return self._vit_blocks(tokens, pe)
-        # The ~130 small launches of the 12 blocks replayed as ONE CUDA graph per (shape, device): at 300 tokens
-        # the ViT is launch-bound (2.5 ms of Python + launch latency for ~0.4 ms of kernels).  Static input / output
-        # buffers; the parameters are read through their own storage, so in-place weight updates are seen.
-        key = (tuple(tokens.shape), str(tokens.device), tuple((p.data_ptr(), p.dtype) for p in vit.parameters()))
-        ent = self._vit_graphs.get(key)
-        if ent is None:
-            st_tok, st_pe = tokens.clone(), pe.clone()
-            side = torch.cuda.Stream(device=tokens.device)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):          # warm-up off the capture (cuBLAS workspaces, autotune)
-                for _ in range(2):
-                    self._vit_blocks(st_tok, st_pe)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                st_out = self._vit_blocks(st_tok, st_pe)
-            ent = self._vit_graphs[key] = (graph, st_tok, st_pe, st_out)
-            if len(self._vit_graphs) > 8:          # shapes rarely change; do not hoard graphs
-                self._vit_graphs.pop(next(iter(self._vit_graphs)))
-        graph, st_tok, st_pe, st_out = ent
-        st_tok.copy_(tokens)
-        st_pe.copy_(pe)
-        graph.replay()
-        return st_out.clone()
+        return self._graphed(("vit", tuple(tokens.shape), str(tokens.device),
+                              tuple((p.data_ptr(), p.dtype) for p in vit.parameters())), self._vit_blocks, tokens, pe)
 
     def _vit_blocks(self, tokens, pe):
         vit = self.net.ViT
