@@ -284,6 +284,20 @@ int th_paint_group_latents(const ThEncoderTail* enc, const float* reduction_w, c
                            const float* cam_T, const float* cam_K, const uint8_t* vizmap, const int32_t* cluster_start,
                            const int32_t* cluster_members, int32_t n_tok, float* tokens, void* workspace,
                            size_t workspace_bytes, void* stream);
+/* ---- linear layers of the token transformer on the tensor cores ---------------- */
+/* y = x W^T + b for an nn.Linear (vision_transformer.py: qkv 269, proj 276, Mlp.fc1 / fc2 246-250) with the same
+ * fp16 hi/lo three-product scheme as the per-point network (fp32-equivalent: ~1e-6 relative), through the tcgen05
+ * GEMM: th_linear_pack (HOST) turns weight (n_out, n_in) + bias (n_out, or NULL) into the operand images the kernel
+ * copies into shared memory (n_in a multiple of 64; n_out any multiple of 4 -- it is cut into chunks of 256 / 128
+ * output columns, the last one zero padded); th_linear runs on the DEVICE copy of that blob: x (m, n_in) fp32 rows with
+ * leading dimension ldx, y (m, n_out) with ldy (both multiples of 4, pointers 16-byte aligned).  No workspace, no
+ * synchronisation: capturable in a CUDA graph. */
+size_t th_linear_packed_bytes(int32_t n_out, int32_t n_in);
+int th_linear_pack(const float* weight_host, const float* bias_host, int32_t n_out, int32_t n_in, void* packed_host,
+                   size_t bytes);
+int th_linear(const float* x, int64_t m, int32_t ldx, const void* packed_dev, int32_t n_out, int32_t n_in, float* y,
+              int32_t ldy, int32_t relu, void* stream);
+
 /* ---- mesh extraction ---------------------------------------------------------- */
 /* The step after the density-grid query: if_mesh_renderer.py:98-104 pads the cube by 10 voxels on the CPU and calls
  * the third-party `mcubes.marching_cubes(cube, cfg.mesh_th)`.  th_marching_cubes runs marching cubes on a DEVICE

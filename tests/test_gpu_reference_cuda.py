@@ -192,7 +192,7 @@ def test_plugin_through_make_renderer_matches_reference_renderer():
     assert float(ref_d["acc_map"].max()) > 0.2 and float(ref_f["acc_map"].max()) > 0.2
 
 
-@pytest.mark.parametrize("n_tok", [300, 1500])
+@pytest.mark.parametrize("n_tok", [300, 1500, 6000])
 def test_plugin_vit_forward_matches_reference_vit(n_tok):
     """the genuine vit_tiny (depth 12) run whole against the plugin's forward of the same module with
     every block's attention through th_vit_attention."""
@@ -202,6 +202,7 @@ def test_plugin_vit_forward_matches_reference_vit(n_tok):
     ns, net, renderer, batch = build_reference(fr, 8, device="cuda", knn=_knn_cuda, fake_prologue=False)
     ours = Renderer.__new__(Renderer)
     ours.net, ours.use_flash_vit, ours.use_cuda_graphs, ours._graphs = net, True, True, {}
+    ours.use_tc_linear, ours.tc_linear_min_rows, ours._linears = True, 4096, {}     # 1500 x 3 and 6000 x 3 rows: th_linear
     g = torch.Generator("cpu").manual_seed(n_tok)
     tokens = torch.randn((3, n_tok, 192), generator=g).to(DEV)
     pe = (torch.rand((3, n_tok, 3), generator=g) * 2 - 1).to(DEV)

@@ -64,3 +64,26 @@ def test_vit_attention_rejects_other_head_dims():
     qkv = torch.zeros((1, 8, 3 * 3 * 32), device=DEV)
     with pytest.raises(Exception):
         ops.vit_attention(qkv, 3, 1.0)
+
+
+@pytest.mark.parametrize("n_out,n_in", [(576, 192), (192, 192), (768, 192), (192, 768), (64, 64), (260, 128)])
+@pytest.mark.parametrize("rows", [1, 300, 5000])
+def test_tc_linear_matches_float64(n_out, n_in, rows):
+    """th_linear (the ViT's Linear layers on the tcgen05 GEMM, fp16 hi/lo three-product scheme) against float64:
+    chunking of n_out into 256 / 128 columns with a zero-padded, column-guarded last chunk; bias; row guard."""
+    g = torch.Generator("cpu").manual_seed(n_out * 7 + rows)
+    w = torch.randn((n_out, n_in), generator=g) * 0.05
+    b = torch.randn((n_out,), generator=g) * 0.1
+    x = torch.randn((rows, n_in), generator=g).to(DEV)
+    lin = ops.PackedLinear(w, b, device=DEV)
+    guard = torch.full((rows + 1, n_out), 7.0, device=DEV)          # nothing may be written past the last row
+    y = lin(x)
+    want = x.double() @ w.double().t().to(DEV) + b.double().to(DEV)
+    err = (y.double() - want).abs().max().item()
+    tol = 1e-5 * max(1.0, want.abs().max().item())   # 22-bit operands, fp32 accumulation over up to 768 terms
+    assert y.shape == (rows, n_out) and err <= tol, err
+    y3 = lin(x.reshape(1, rows, n_in), relu=True)
+    assert y3.shape == (1, rows, n_out) and (y3.double() - want.clamp(min=0)[None]).abs().max().item() <= tol
+    nob = ops.PackedLinear(w, None, device=DEV)(x)
+    assert (nob.double() - (want - b.double().to(DEV))).abs().max().item() <= tol
+    assert bool((guard == 7.0).all())

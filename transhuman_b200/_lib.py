@@ -104,6 +104,9 @@ SIGNATURES = {
     "th_paint_group_latents_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "th_paint_group_latents": (C.c_int, [C.POINTER(ThEncoderTail), _fp, _fp, C.c_float, C.c_float, _fp, C.c_int32, _fp,
                                          _fp, _fp, _fp, _fp, _fp, C.c_int32, _fp, _fp, C.c_size_t, _fp]),
+    "th_linear_packed_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "th_linear_pack": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, _fp, C.c_size_t]),
+    "th_linear": (C.c_int, [_fp, C.c_int64, C.c_int32, _fp, C.c_int32, C.c_int32, _fp, C.c_int32, C.c_int32, _fp]),
     "th_marching_cubes_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "th_marching_cubes": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, _fp, C.c_int64, _fp, C.c_int64,
                                     C.POINTER(C.c_int64), _fp, C.c_size_t, _fp]),

@@ -85,6 +85,38 @@ static int64_t chunk_pts() {
   return v;
 }
 
+// fp16 hi/lo tile image of an (n_rows, K) fp32 matrix (rows beyond n_rows up to N are zero) scaled by `up`, in the
+// layout k_gemm_tc2 / k_chain copy into shared memory: per 64-wide k-block and per half of the N rows (one half per
+// CTA of a cta_group::2 pair) [hi | lo], each N/2 rows of 128 bytes, K-major, 16-byte chunk ^= row & 7.
+static void pack_weight_image(const float* src, int N, int K, int n_rows, float up, unsigned char* img) {
+  auto sat = [](float f) { return f > 65504.f ? 65504.f : (f < -65504.f ? -65504.f : f); };  // like the device split
+  for (int kb = 0; kb < K / 64; ++kb)
+    for (int n = 0; n < N; ++n)
+      for (int kk = 0; kk < 64; ++kk) {
+        const float x = n < n_rows ? src[(size_t)n * K + kb * 64 + kk] * up : 0.f;
+        const __half a = __float2half_rn(sat(x));
+        const __half b = __float2half_rn(sat(x - __half2float(a)));
+        const size_t off = (size_t)n * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+        const int half_rows = N / 2, r = n / half_rows;
+        unsigned char* tile = img + (size_t)kb * (2 * N * 128) + (size_t)r * (N * 128);  // this half: [hi | lo]
+        memcpy(tile + off - (size_t)r * half_rows * 128, &a, 2);
+        memcpy(tile + (size_t)half_rows * 128 + off - (size_t)r * half_rows * 128, &b, 2);
+      }
+}
+static int weight_scale_exp(const float* src, size_t n) {  // max|w| 2^e in (2^13, 2^14]
+  float wmax = 0.f;
+  for (size_t i = 0; i < n; ++i) wmax = fmaxf(wmax, fabsf(src[i]));
+  int e = 0;
+  if (wmax > 0.f && isfinite(wmax)) {
+    int ex = 0;
+    frexpf(wmax, &ex);  // wmax = f * 2^ex, f in [0.5, 1)
+    e = 14 - ex;
+    if (e > 60) e = 60;
+    if (e < -60) e = -60;
+  }
+  return e;
+}
+
 // ---------------------------------------------------------------------------
 // weight packing (host)
 // ---------------------------------------------------------------------------
@@ -349,16 +381,7 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
     const float* src = W(h.*(m.w));
     unsigned char* img = blob + h.*(m.h);
     // power-of-two scale (PackedHeader::img_inv_scale): max|w| 2^e in (2^13, 2^14]
-    float wmax = 0.f;
-    for (size_t i = 0; i < (size_t)m.N * m.K; ++i) wmax = fmaxf(wmax, fabsf(src[i]));
-    int e = 0;
-    if (wmax > 0.f && isfinite(wmax)) {
-      int ex = 0;
-      frexpf(wmax, &ex);  // wmax = f * 2^ex, f in [0.5, 1)
-      e = 14 - ex;
-      if (e > 60) e = 60;
-      if (e < -60) e = -60;
-    }
+    const int e = weight_scale_exp(src, (size_t)m.N * m.K);
     const float up = ldexpf(1.0f, e);
     PackedHeader* hb = reinterpret_cast<PackedHeader*>(blob);
     if (hb->n_img < 24) {
@@ -366,20 +389,7 @@ int th_pack_weights(const ThWeightsF32* w, int32_t V, void* packed_host, size_t 
       hb->img_inv_scale[hb->n_img] = ldexpf(1.0f, -e);
       ++hb->n_img;
     }
-    for (int kb = 0; kb < m.K / 64; ++kb)
-      for (int n = 0; n < m.N; ++n)
-        for (int kk = 0; kk < 64; ++kk) {
-          const float x = src[(size_t)n * m.K + kb * 64 + kk] * up;
-          // saturating like the device-side split (common.cuh): no inf planes from a huge weight
-          auto sat = [](float f) { return f > 65504.f ? 65504.f : (f < -65504.f ? -65504.f : f); };
-          const __half a = __float2half_rn(sat(x));
-          const __half b = __float2half_rn(sat(x - __half2float(a)));
-          const size_t off = (size_t)n * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
-          const int half_rows = m.N / 2, r = n / half_rows;
-          unsigned char* tile = img + (size_t)kb * (2 * m.N * 128) + (size_t)r * (m.N * 128);  // this half: [hi | lo]
-          memcpy(tile + off - (size_t)r * half_rows * 128, &a, 2);
-          memcpy(tile + (size_t)half_rows * 128 + off - (size_t)r * half_rows * 128, &b, 2);
-        }
+    pack_weight_image(src, m.N, m.K, m.N, up, img);
   }
   return TH_OK;
 }
@@ -963,6 +973,90 @@ int th_paint_group_latents(const ThEncoderTail* enc, const float* reduction_w, c
   return launch_paint_group_latents(static_cast<const EncTail*>(workspace), enc->n_views, reduction_w, reduction_b,
                                     uv_scale_x, uv_scale_y, verts, cam_R, cam_T, cam_K, vizmap, n_verts, cluster_start,
                                     cluster_members, n_tok, scratch, tokens, st);
+}
+
+// ---- generic linear layer through the tcgen05 GEMM --------------------------------------------
+struct LinearPlan {
+  int n_chunks;
+  int chunk_n[16], chunk_valid[16], col0[16];
+  size_t img_off[16], bias_off, scale_off, total;
+};
+static bool linear_plan(int n_out, int n_in, LinearPlan* p) {
+  if (n_out < 4 || n_out % 4 || n_in < 64 || n_in % 64 || n_out > 16 * 256) return false;
+  p->n_chunks = 0;
+  size_t off = 256;  // [0]: magic, [16]: inv_scale
+  p->scale_off = 16;
+  for (int c = 0; c < n_out;) {
+    const int rem = n_out - c;
+    const int n = rem > 128 ? 256 : 128, valid = rem < n ? rem : n;
+    const int i = p->n_chunks++;
+    p->chunk_n[i] = n, p->chunk_valid[i] = valid, p->col0[i] = c;
+    p->img_off[i] = off;
+    off += align_up((size_t)n * n_in * 2 * 2, 1024);
+    c += valid;
+  }
+  p->bias_off = off;
+  off += align_up((size_t)p->n_chunks * 256 * 4, 256);
+  p->total = off;
+  return true;
+}
+constexpr uint32_t LINEAR_MAGIC = 0x314E4C54u;  // 'TLN1'
+
+size_t th_linear_packed_bytes(int32_t n_out, int32_t n_in) {
+  LinearPlan p;
+  return linear_plan(n_out, n_in, &p) ? p.total : 0;
+}
+
+int th_linear_pack(const float* weight_host, const float* bias_host, int32_t n_out, int32_t n_in, void* packed_host,
+                   size_t bytes) {
+  TH_CHECK_ARG(weight_host && packed_host, "null pointer");
+  LinearPlan p;
+  TH_CHECK_ARG(linear_plan(n_out, n_in, &p), "n_in must be a multiple of 64, n_out a multiple of 4 (<= 4096)");
+  TH_CHECK_ARG(bytes >= p.total, "buffer too small");
+  unsigned char* blob = static_cast<unsigned char*>(packed_host);
+  memset(blob, 0, p.total);
+  const int e = weight_scale_exp(weight_host, (size_t)n_out * n_in);
+  const float up = ldexpf(1.0f, e), inv = ldexpf(1.0f, -e);
+  memcpy(blob, &LINEAR_MAGIC, 4);
+  memcpy(blob + p.scale_off, &inv, 4);
+  for (int i = 0; i < p.n_chunks; ++i) {
+    pack_weight_image(weight_host + (size_t)p.col0[i] * n_in, p.chunk_n[i], n_in, p.chunk_valid[i], up,
+                      blob + p.img_off[i]);
+    if (bias_host) memcpy(blob + p.bias_off + (size_t)i * 256 * 4, bias_host + p.col0[i], (size_t)p.chunk_valid[i] * 4);
+  }
+  return TH_OK;
+}
+
+int th_linear(const float* x, int64_t m, int32_t ldx, const void* packed_dev, int32_t n_out, int32_t n_in, float* y,
+              int32_t ldy, int32_t relu, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TH_CHECK_ARG(x && packed_dev && y, "null pointer");
+  LinearPlan p;
+  TH_CHECK_ARG(linear_plan(n_out, n_in, &p), "n_in must be a multiple of 64, n_out a multiple of 4 (<= 4096)");
+  TH_CHECK_ARG(m >= 0 && ldx >= n_in && ldx % 4 == 0 && ldy >= n_out && ldy % 4 == 0, "bad leading dimension");
+  TH_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(packed_dev) & 1023) == 0,
+               "misaligned pointer (x, y: 16 bytes; packed blob: 1024 bytes)");
+  if (m == 0) return TH_OK;
+  const unsigned char* blob = static_cast<const unsigned char*>(packed_dev);
+  for (int i = 0; i < p.n_chunks; ++i) {
+    GemmArgs g{};
+    g.nseg = 1;
+    g.seg[0].ptr = x;
+    g.seg[0].K = n_in;
+    g.seg[0].ld = ldx;
+    g.bias = reinterpret_cast<const float*>(blob + p.bias_off + (size_t)i * 256 * 4);
+    g.C = y + p.col0[i];
+    g.ldc = ldy;
+    g.M = m;
+    g.N = p.chunk_n[i];
+    g.n_store = p.chunk_valid[i];
+    g.relu = relu ? 1 : 0;
+    g.acc_scale = reinterpret_cast<const float*>(blob + p.scale_off);
+    int rc = launch_gemm_tc(g, blob + p.img_off[i], st, PROF_PROLOGUE);
+    if (rc) return rc;
+  }
+  return TH_OK;
 }
 
 size_t th_marching_cubes_workspace_bytes(int32_t nx, int32_t ny, int32_t nz) {

@@ -318,6 +318,8 @@ struct GemmArgs {
   int64_t M;
   int N;  // multiple of 128
   int relu;
+  int n_store;             // fp32 C output: only columns < n_store are written (0 = all N): the padded last chunk of a
+                           // linear layer whose width is not a multiple of 128
   const float* acc_scale;  // tensor-core path: DEVICE pointer to the 2^-e of the weight image (img_inv_scale_ptr);
                            // the accumulator is multiplied by it before the bias; nullptr = 1
 };

@@ -112,6 +112,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
   }
   for (int i = tid; i < N; i += NUM_THREADS) s_bias[i] = a.g.bias ? a.g.bias[i] : 0.f;
   const float acc_scale = a.g.acc_scale ? __ldg(a.g.acc_scale) : 1.0f;  // 2^-e of the weight image (read from the blob)
+  const int n_store = a.g.n_store > 0 ? a.g.n_store : N;
   if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)TMEM_COLS)
@@ -388,7 +389,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ge
             const int row = rr + (lane >> 3);
             const int64_t m = mbase + row;
             const float4 o = *reinterpret_cast<const float4*>(stage + row * EPI_LD + (lane & 7) * 4);
-            if (m < M) *reinterpret_cast<float4*>(a.g.C + m * a.g.ldc + c0 + (lane & 7) * 4) = o;
+            if (m < M && c0 + (lane & 7) * 4 < n_store)
+              *reinterpret_cast<float4*>(a.g.C + m * a.g.ldc + c0 + (lane & 7) * 4) = o;
           }
           __syncwarp();
         }

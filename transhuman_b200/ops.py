@@ -18,7 +18,7 @@ from ._lib import (TH_FLAG_LAYERWISE, TH_FLAG_PREMAPPED, TH_FLAG_SIMT_MLP, TH_FL
 
 __all__ = ["PackedWeights", "Frame", "render_rays", "query_density", "sample_points", "cull_knn1", "cull_grid",
            "world2smpl", "view_embed", "pixel_gather", "knn_dparf", "mlp_raw", "integrate", "nchw_to_nhwc",
-           "premap_features", "vit_attention", "marching_cubes", "EncoderTail", "premap_from_latents", "paint_group_latents", "ClusterIndex", "paint_group",
+           "premap_features", "vit_attention", "PackedLinear", "marching_cubes", "EncoderTail", "premap_from_latents", "paint_group_latents", "ClusterIndex", "paint_group",
            "group_mean", "generate_rays", "near_far",
            "launch_count", "TH_RENDER_DENSE", "TH_RENDER_MASKED", "TH_RENDER_FAST"]
 
@@ -481,6 +481,39 @@ def paint_group_latents(enc: EncoderTail, reduction_w, reduction_b, uv_scale, ve
                                           _ptr(clusters.members), clusters.n_tok, _ptr(out), _ptr(ws), nbytes,
                                           _stream()), "th_paint_group_latents")
     return out
+
+
+class PackedLinear:
+    """An ``nn.Linear`` packed for ``th_linear`` (fp16 hi/lo operand images of the weight, host-side; the blob is
+    1 KB-aligned on the device).  Re-pack when the parameters change (``key``: data pointers + versions)."""
+
+    def __init__(self, weight, bias, device="cuda"):
+        lib = _lib.load()
+        w = weight.detach().to(torch.float32).cpu().contiguous()
+        b = None if bias is None else bias.detach().to(torch.float32).cpu().contiguous()
+        self.n_out, self.n_in = w.shape
+        nbytes = lib.th_linear_packed_bytes(self.n_out, self.n_in)
+        if nbytes == 0:
+            raise ValueError(f"th_linear: unsupported shape ({self.n_out}, {self.n_in}): n_in % 64, n_out % 4")
+        host = np.zeros(nbytes, dtype=np.uint8)
+        _lib.check(lib.th_linear_pack(C.c_void_p(w.data_ptr()), None if b is None else C.c_void_p(b.data_ptr()),
+                                      self.n_out, self.n_in, C.c_void_p(host.ctypes.data), nbytes), "th_linear_pack")
+        buf = torch.empty((nbytes + 1024,), dtype=torch.uint8, device=device)
+        shift = (-buf.data_ptr()) % 1024
+        self._buf = buf
+        self.blob = buf[shift:shift + nbytes]
+        self.blob.copy_(torch.from_numpy(host))
+
+    def __call__(self, x, relu: bool = False):
+        lib = _lib.load()
+        x = _f32(x, "x")
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        assert x2.shape[1] == self.n_in
+        y = torch.empty((x2.shape[0], self.n_out), device=x.device)
+        _lib.check(lib.th_linear(_ptr(x2), x2.shape[0], x2.stride(0), self.blob.data_ptr(), self.n_out, self.n_in, _ptr(y),
+                                 self.n_out, 1 if relu else 0, _stream()), "th_linear")
+        return y.reshape(*shape[:-1], self.n_out)
 
 
 def marching_cubes(volume, iso: float):

@@ -111,6 +111,10 @@ class Renderer:
         # replay the chains of small torch launches (encoder backbone, ViT blocks) as CUDA graphs (inference only)
         self.use_cuda_graphs = True
         self._graphs = {}
+        # the ViT's Linear layers through th_linear from this many token rows (views x tokens) on
+        self.use_tc_linear = True
+        self.tc_linear_min_rows = 4096
+        self._linears = {}
         # set `profile = True` to have every prologue stage bracketed by CUDA events; `last_prologue_ms` then
         # holds {stage: milliseconds} of the last prepare_frame (bench.py's `plugin` record)
         self.profile = False
@@ -211,6 +215,8 @@ class Renderer:
                 ok = ok and a is not None and all(hasattr(a, n) for n in ('qkv', 'proj', 'num_heads', 'scale')) \
                     and a.qkv.out_features == 3 * a.num_heads * 64 \
                     and all(hasattr(blk, n) for n in ('norm1', 'norm2', 'mlp')) \
+                    and all(hasattr(blk.mlp, n) for n in ('fc1', 'fc2', 'act')) \
+                    and (not vit.training or getattr(getattr(blk.mlp, 'drop', None), 'p', 0) == 0) \
                     and (not vit.training or (a.attn_drop.p == 0 and a.proj_drop.p == 0
                                               and isinstance(blk.drop_path, torch.nn.Identity)))
         if not ok:
@@ -221,11 +227,24 @@ class Renderer:
     def _vit_blocks(self, tokens, pe):
         vit = self.net.ViT
         x = vit.prepare_tokens(tokens, pe, None)
+        # from a few thousand rows on, the four Linear layers of a block also go through the tensor cores
+        # (th_linear: fp16 hi/lo three-product tcgen05 GEMM); below that cuBLAS' fp32 kernels are launch-bound anyway
+        tc = self.use_tc_linear and x.shape[0] * x.shape[1] >= self.tc_linear_min_rows
+        lin = self._packed_linear if tc else (lambda m: m)
         for blk in vit.blocks:
             a = blk.attn
-            x = x + a.proj(ops.vit_attention(a.qkv(blk.norm1(x)), a.num_heads, a.scale))
-            x = x + blk.mlp(blk.norm2(x))
+            x = x + lin(a.proj)(ops.vit_attention(lin(a.qkv)(blk.norm1(x)), a.num_heads, a.scale))
+            h = blk.mlp.act(lin(blk.mlp.fc1)(blk.norm2(x)))
+            x = x + lin(blk.mlp.fc2)(h)
         return vit.norm(x)
+
+    def _packed_linear(self, mod):
+        """``ops.PackedLinear`` of an ``nn.Linear``, re-packed when its parameters change."""
+        fp = tuple((p.data_ptr(), p._version) for p in (mod.weight, mod.bias) if p is not None)
+        ent = self._linears.get(id(mod))
+        if ent is None or ent[0] != fp:
+            ent = self._linears[id(mod)] = (fp, ops.PackedLinear(mod.weight, mod.bias, device=mod.weight.device))
+        return ent[1]
 
     def refresh_weights(self):
         """Forces a re-pack (only needed after REPLACING parameter tensors of ``net``; in-place updates such as
