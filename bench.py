@@ -359,6 +359,16 @@ def other_configs(args, device):
     return out
 
 
+def _claim_stdout():
+    """stdout carries exactly ONE line, the JSON record: file descriptor 1 is pointed at stderr for the whole run
+    (the reference's modules and torchvision print from Python and from C), and the record goes to the saved
+    descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -381,6 +391,7 @@ def main():
                     help="one untimed dense step and exit (for ncu; prints nothing)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    record_out = _claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -392,7 +403,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        print(json.dumps(reference_arm(args)), flush=True)
+        print(json.dumps(reference_arm(args)), file=record_out, flush=True)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -648,7 +659,7 @@ def main():
                                            "after the timed region (the timed region runs without them)",
                                     "ms_per_step_profiled_pass": ms_step_profiled},
                 **extra}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=record_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
