@@ -161,6 +161,13 @@ int th_pack_weights(const ThWeightsF32* w_host, int32_t n_views, void* packed_ho
 /* Workspace needed by th_render_rays / th_query_density for up to `n_points`
  * sample points in flight (n_rays * n_samples for rays). */
 size_t th_workspace_bytes(int64_t n_points, int32_t n_views, int32_t n_verts);
+/* The same for the schedule `frame->flags` select (th_render_rays / th_query_density accept either size): with
+ * TH_FLAG_PREMAPPED -- the layer-chained kernel, the default path -- the chunk block holds only the feature
+ * kernel's operand images (8.25 KB per point of a 284,160-point chunk) and the kernel's fixed per-CTA scratch
+ * (138 MB on 148 SMs): 2.6 GB per stream at configs[1] instead of the 7.8 GB th_workspace_bytes reserves for the
+ * layer-at-a-time schedule.  with_cull = 0 leaves the cull grid of frame->n_verts vertices out (dense rays).
+ * Sized for the current device's SM count (148 when no device is present). */
+size_t th_frame_workspace_bytes(const ThFrame* frame, int64_t n_points, int32_t with_cull);
 
 /* Renderer.render (dense: every sample evaluated, pts_mask=None;
  * if_clight_renderer.py:486-498 -> 500-605) when culled == 0, and

@@ -229,6 +229,30 @@ def test_workspace_bytes(lib):
     assert 0 < a < b < c < 8 << 30
 
 
+def test_frame_workspace_bytes_follows_the_schedule(lib):
+    """The layer-chained schedule on pre-mapped maps keeps no per-point activation buffers: 8.25 KB per point of a
+    chunk + the fixed per-CTA scratch instead of 26.9 KB per point; every other flag
+    combination gets th_workspace_bytes' figure."""
+    NP = 262144 * 64
+    f = _lib.ThFrame()
+    f.n_views, f.n_verts = 3, 6890
+    full = lib.th_workspace_bytes(NP, 3, 6890)
+    for flags in (0, ops.TH_FLAG_SIMT_MLP, ops.TH_FLAG_LAYERWISE, ops.TH_FLAG_PREMAPPED | ops.TH_FLAG_SIMT_MLP):
+        f.flags = flags
+        assert lib.th_frame_workspace_bytes(C.byref(f), NP, 1) == full
+    f.flags = ops.TH_FLAG_PREMAPPED
+    compact = lib.th_frame_workspace_bytes(C.byref(f), NP, 1)
+    chunk = 284160
+    per_point = (3 * (256 + 384) + 128 + 64) * 4            # rep, [X | P2] per view; R and the view direction per point
+    scratch = 148 * (2 * 3 + 3 // 2 + 0.5) * 128 * 1024       # 148 CTAs x (2 V + V / 2) activation tiles of 128 KB
+    fixed = NP * (1 + 1 + 4 + 16)                             # ray flags, mask, id list, raw
+    assert 0 <= compact - (chunk * per_point + scratch + fixed) < 32 << 20, compact   # + the cull / token grids
+    assert compact < 0.4 * full
+    assert lib.th_frame_workspace_bytes(C.byref(f), NP, 0) < compact   # without the cull / token grids
+    f.n_views = 4                                              # V = 4: no chain schedule -> the full carve
+    assert lib.th_frame_workspace_bytes(C.byref(f), NP, 1) == lib.th_workspace_bytes(NP, 4, 6890)
+
+
 def test_no_cpu_fallback():
     """CPU tensors are rejected; nothing in the package imports the oracle."""
     with pytest.raises(ValueError, match="CUDA"):

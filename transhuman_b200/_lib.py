@@ -82,6 +82,7 @@ SIGNATURES = {
     "th_packed_weights_bytes": (C.c_size_t, [C.c_int32]),
     "th_pack_weights": (C.c_int, [C.POINTER(ThWeightsF32), C.c_int32, _fp, C.c_size_t]),
     "th_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "th_frame_workspace_bytes": (C.c_size_t, [C.POINTER(ThFrame), C.c_int64, C.c_int32]),
     "th_render_rays": (C.c_int, [C.POINTER(ThFrame), C.POINTER(ThRays), C.POINTER(ThOut), C.c_int32, _fp,
                                  C.c_size_t, _fp]),
     "th_query_density": (C.c_int, [C.POINTER(ThFrame), _fp, C.c_int64, _fp, _fp, _fp, C.c_size_t, _fp]),

@@ -407,7 +407,24 @@ struct Workspace {
   float* chunk;
   int64_t chunk_pts;
   unsigned char* tok_grid;  // token grid of the K-NN (culled rays / density grid with >= TOKEN_GRID_MIN tokens)
+  int compact_sms;          // > 0: compact chunk block of the layer-chained schedule on pre-mapped maps (mlp_carve), scratch sized for this SM count
 };
+
+// The schedule a frame's flags select keeps either the per-point activation buffers of the layer-at-a-time
+// schedule (26.9 KB per point of the chunk) or -- pre-mapped maps, hence the layer-chained kernel: the default
+// path -- only the feature kernel's operand images and a fixed per-CTA scratch (8.25 KB per point + 138 MB).
+static int compact_sms_for(const ThFrame* f) {
+  if (!f || !(f->flags & TH_FLAG_PREMAPPED) || (f->flags & (TH_FLAG_SIMT_MLP | TH_FLAG_LAYERWISE)) ||
+      !chain_supported(f->n_views))
+    return 0;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      n < 2) {
+    cudaGetLastError();  // no device (host-side sizing): size for a B200
+    n = 148;
+  }
+  return n;
+}
 
 constexpr int TOKEN_GRID_MAX = 65536;  // tokens the reserved grid block can hold (th_workspace_bytes has no token count)
 // TH_TOKEN_GRID=<n>: use the token grid from n tokens on (default TOKEN_GRID_MIN; a huge n = never) -- measurement knob
@@ -415,7 +432,7 @@ static int token_grid_min() {
   static const int v = getenv("TH_TOKEN_GRID") ? atoi(getenv("TH_TOKEN_GRID")) : TOKEN_GRID_MIN;
   return v;
 }
-static size_t ws_plan(int64_t n_points, int V, int n_verts, unsigned char* base, Workspace* ws) {
+static size_t ws_plan(int64_t n_points, int V, int n_verts, unsigned char* base, Workspace* ws, int compact_sms = 0) {
   size_t off = 0;
   auto take = [&](size_t bytes) {
     unsigned char* p = base ? base + off : nullptr;
@@ -430,7 +447,8 @@ static size_t ws_plan(int64_t n_points, int V, int n_verts, unsigned char* base,
   unsigned char* ids = take((size_t)np * 4);
   unsigned char* raw = take((size_t)np * 16);
   int64_t cp = np < chunk_pts() ? np : chunk_pts();
-  unsigned char* chunk = take((size_t)pad_points(cp) * mlp_buffer_floats_per_point(V) * 4 + 1024);
+  unsigned char* chunk = take((compact_sms > 0 ? mlp_compact_bytes(cp, V, chain_scratch_bytes(cp, V, compact_sms))
+                                               : (size_t)pad_points(cp) * mlp_buffer_floats_per_point(V) * 4) + 1024);
   unsigned char* tok_grid = take(n_verts > 0 ? cull_grid_bytes(TOKEN_GRID_MAX) : 0);
   if (ws) {
     ws->tok_grid = n_verts > 0 ? tok_grid : nullptr;
@@ -442,6 +460,7 @@ static size_t ws_plan(int64_t n_points, int V, int n_verts, unsigned char* base,
     ws->raw = reinterpret_cast<float*>(raw);
     ws->chunk = reinterpret_cast<float*>(chunk);
     ws->chunk_pts = cp;
+    ws->compact_sms = compact_sms;
   }
   return off;
 }
@@ -449,6 +468,11 @@ static size_t ws_plan(int64_t n_points, int V, int n_verts, unsigned char* base,
 size_t th_workspace_bytes(int64_t n_points, int32_t n_views, int32_t n_verts) {
   if (n_views < 1) n_views = 1;
   return ws_plan(n_points, n_views, n_verts, nullptr, nullptr);
+}
+size_t th_frame_workspace_bytes(const ThFrame* f, int64_t n_points, int32_t with_cull) {
+  if (!f) return 0;
+  const int V = f->n_views < 1 ? 1 : f->n_views;
+  return ws_plan(n_points, V, with_cull ? f->n_verts : 0, nullptr, nullptr, compact_sms_for(f));
 }
 
 static int frame_dev(const ThFrame* f, FrameDev* d, bool need_tokens, bool need_feat) {
@@ -520,7 +544,7 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
   for (int64_t first = 0; first < n_list; first += ws.chunk_pts) {
     int64_t P = n_list - first < ws.chunk_pts ? n_list - first : ws.chunk_pts;
     MlpBuffers b;
-    mlp_carve(ws.chunk, P, V, &b);
+    mlp_carve(ws.chunk, P, V, &b, ws.compact_sms > 0 ? chain_scratch_bytes(P, V, ws.compact_sms) : 0);
     const int64_t Pp = pad_points(P);
     FeatOut fo{};
     fo.rep = b.rep;
@@ -578,7 +602,8 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
     }();
     int num_sms = 0;
     if (device_sm_count(&num_sms)) return TH_ECUDA;
-    const size_t scratch_room = (size_t)Pp * V * (256 * 4 + 128 * 2) * 4;  // b.s ... b.ks are contiguous
+    const size_t scratch_room = ws.compact_sms > 0 ? chain_scratch_bytes(P, V, ws.compact_sms)  // sized for it
+                                                   : (size_t)Pp * V * (256 * 4 + 128 * 2) * 4;  // b.s ... b.ks are contiguous
     if (use_tc && (use_chain || premapped) && !(f->flags & TH_FLAG_LAYERWISE) && chain_supported(V) &&
         chain_scratch_bytes(P, V, num_sms) <= scratch_room) {
       rc = mlp_forward_chain(run, b, hdr, reinterpret_cast<unsigned char*>(b.s), nullptr, st);
@@ -617,7 +642,7 @@ int th_render_rays(const ThFrame* f, const ThRays* r, ThOut* o, int32_t culled, 
   TH_CHECK_ARG(f->Rh && f->Th, "null Rh/Th");
   if (culled) TH_CHECK_ARG(f->verts && f->n_verts > 0, "culled mode needs the cull vertices");
   Workspace ws;
-  size_t need = ws_plan(NP, fr.V, culled ? f->n_verts : 0, static_cast<unsigned char*>(workspace), &ws);
+  size_t need = ws_plan(NP, fr.V, culled ? f->n_verts : 0, static_cast<unsigned char*>(workspace), &ws, compact_sms_for(f));
   if (!workspace || workspace_bytes < need) {
     set_error("th_render_rays: workspace %zu < %zu bytes", workspace_bytes, need);
     return TH_EWORKSPACE;
@@ -697,7 +722,7 @@ int th_query_density(const ThFrame* f, const float* pts, int64_t n_points, float
   if (rc) return rc;
   TH_CHECK_ARG(f->Rh && f->Th && f->verts && f->n_verts > 0, "null Rh/Th/verts");
   Workspace ws;
-  size_t need = ws_plan(n_points, fr.V, f->n_verts, static_cast<unsigned char*>(workspace), &ws);
+  size_t need = ws_plan(n_points, fr.V, f->n_verts, static_cast<unsigned char*>(workspace), &ws, compact_sms_for(f));
   if (!workspace || workspace_bytes < need) {
     set_error("th_query_density: workspace %zu < %zu bytes", workspace_bytes, need);
     return TH_EWORKSPACE;

@@ -212,7 +212,9 @@ struct MlpBuffers {
   float *net;      // (V*P, 256)
 };
 size_t mlp_buffer_floats_per_point(int V);
-void mlp_carve(float* base, int64_t P, int V, MlpBuffers* b);
+// chain_scratch > 0: compact carve for the layer-chained schedule on pre-mapped maps (mlp_simt.cu)
+void mlp_carve(float* base, int64_t P, int V, MlpBuffers* b, size_t chain_scratch = 0);
+size_t mlp_compact_bytes(int64_t P, int V, size_t chain_scratch);
 
 // Runs fc_0 ... rgb_fc for P points whose inputs sit in `b`; writes raw rows
 // (rgb x3, alpha) to raw[dst_ids ? dst_ids[first + i] : first + i].  alpha_only

@@ -353,7 +353,14 @@ size_t mlp_buffer_floats_per_point(int V) {
 }
 
 // All buffers are sized and strided for Pp = pad_points(P) rows per view.
-void mlp_carve(float* base, int64_t P, int V, MlpBuffers* b) {
+// chain_scratch > 0 = COMPACT carve for the layer-chained schedule on pre-mapped maps (the default path): that
+// schedule reads rep, the pix block [X | P2], R (128 wide, in pix_mean) and vd, and keeps everything between its
+// layers in a per-CTA scratch of a FIXED size (chain_scratch_bytes) -- none of the per-point activation buffers of
+// the layer-at-a-time schedule (s .. ks, 15 KB per point) exist.  8.25 KB per point + the scratch.
+size_t mlp_compact_bytes(int64_t P, int V, size_t chain_scratch) {
+  return (size_t)pad_points(P) * ((size_t)V * (REP_LD + PIX_LD) + 128 + 2 * VD_LD) * 4 + ((chain_scratch + 1023) & ~size_t(1023));
+}
+void mlp_carve(float* base, int64_t P, int V, MlpBuffers* b, size_t chain_scratch) {
   const int64_t Pp = pad_points(P);
   // tile images need 1 KB alignment; every buffer size below is a multiple of 1 KB because Pp % 256 == 0
   float* p = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(base) + 1023) & ~uintptr_t(1023));
@@ -364,6 +371,14 @@ void mlp_carve(float* base, int64_t P, int V, MlpBuffers* b) {
   };
   b->rep = take((size_t)V * REP_LD);
   b->pix = take((size_t)V * PIX_LD);
+  if (chain_scratch) {
+    b->s = p;  // the chain kernel's scratch (1 KB aligned: everything before it is a multiple of 1 KB)
+    p += ((chain_scratch + 1023) & ~size_t(1023)) / 4;
+    b->x = b->xt = b->net = b->kp = b->ks = nullptr;
+    b->pix_mean = take(128);
+    b->vd = take(2 * VD_LD);
+    return;
+  }
   b->s = take((size_t)V * 256);
   b->x = take((size_t)V * 256);
   b->xt = take((size_t)V * 256);

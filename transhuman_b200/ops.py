@@ -203,7 +203,7 @@ def render_rays(frame: Frame, ray_o, ray_d, near, far, S: int, mode: int = TH_RE
         o.pts_mask = out["pts_mask"].data_ptr()
     counters = (C.c_int64 * 3)()
     o.counters_host = counters
-    nbytes = lib.th_workspace_bytes(N * S, frame.V, frame.verts.shape[0])
+    nbytes = lib.th_frame_workspace_bytes(C.byref(frame.c), N * S, 1)   # sized for the schedule the frame selects
     ws = _workspace(nbytes, dev)
     _lib.check(lib.th_render_rays(C.byref(frame.c), C.byref(r), C.byref(o), mode, _ptr(ws), ws.numel(), _stream()),
                "th_render_rays")
@@ -218,7 +218,7 @@ def query_density(frame: Frame, pts):
     P = pts.shape[0]
     alpha = torch.empty((P,), device=pts.device)
     mask = torch.empty((P,), dtype=torch.uint8, device=pts.device)
-    nbytes = lib.th_workspace_bytes(P, frame.V, frame.verts.shape[0])
+    nbytes = lib.th_frame_workspace_bytes(C.byref(frame.c), P, 1)
     ws = _workspace(nbytes, pts.device)
     _lib.check(lib.th_query_density(C.byref(frame.c), _ptr(pts), P, _ptr(alpha), _ptr(mask), _ptr(ws), ws.numel(),
                                     _stream()), "th_query_density")
