@@ -105,3 +105,23 @@ def test_tmem_side_mix_matches_in_place_mix_and_oracle(mode, monkeypatch):
         assert (got["rgb_map"].cpu() - want["rgb_map"][0]).abs().max().item() <= 1e-4, name
     assert torch.equal(b["raw"], c["raw"])
     assert (a["raw"] - b["raw"]).abs().max().item() <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("mode", ["dense", "culled"])
+def test_pipelined_feature_kernel_is_bit_identical(mode, monkeypatch):
+    """k_features<7, IMG, PRE, PIPE> (csrc/geometry.cu: phase 2 as a rolling software pipeline, the default for the
+    id-list launches of culled rays) issues the same arithmetic per channel as the plain form: the rendered frame
+    must be bit-identical whichever form a launch uses."""
+    fr, tf, tokens = _frame()
+    S = 16
+    m = ops.TH_RENDER_DENSE if mode == "dense" else ops.TH_RENDER_MASKED
+    f1, rays = frame_to_device(fr, tokens, DEV, premapped=True)
+    out = {}
+    for form in ("0", "1"):
+        monkeypatch.setenv("TH_FEAT_PIPE", form)
+        out[form] = ops.render_rays(f1, *rays, S, mode=m, want_raw=True)
+    monkeypatch.delenv("TH_FEAT_PIPE")
+    torch.cuda.synchronize()
+    for k in ("raw", "rgb_map", "acc_map", "depth_map"):
+        assert torch.equal(out["0"][k], out["1"][k]), k
+    assert out["0"]["raw"].abs().max().item() > 0
