@@ -125,3 +125,33 @@ def test_pipelined_feature_kernel_is_bit_identical(mode, monkeypatch):
     for k in ("raw", "rgb_map", "acc_map", "depth_map"):
         assert torch.equal(out["0"][k], out["1"][k]), k
     assert out["0"]["raw"].abs().max().item() > 0
+
+
+@pytest.mark.parametrize("premapped", [True, False])
+@pytest.mark.parametrize("white", [False, True])
+@pytest.mark.parametrize("S", [16, 64, 128, 24])
+def test_fused_compositing_equals_integrate_kernel(S, white, premapped, monkeypatch):
+    """Dense rays on the chain schedule with S | 128: raw2outputs runs inside the chain kernel's fc_4' epilogue
+    (CompositeArgs, csrc/mlp_chain.cu) -- no raw tensor, no k_integrate.  It must give the bits of the two-kernel
+    form (TH_FUSE_INTEGRATE=0), with and without the raw output requested; S = 24 (not a divisor of 128) takes the
+    two-kernel form either way.  400 rays x S is not a multiple of the 256-point unit: the ragged last tile."""
+    fr, tf, tokens = _frame()
+    f1, rays = frame_to_device(fr, tokens, DEV, premapped=premapped, white_bkgd=white)
+    a = ops.render_rays(f1, *rays, S, mode=ops.TH_RENDER_DENSE)
+    b = ops.render_rays(f1, *rays, S, mode=ops.TH_RENDER_DENSE, want_raw=True)
+    n_fused = ops.launch_count(reset=True)
+    ops.render_rays(f1, *rays, S, mode=ops.TH_RENDER_DENSE)
+    n_fused = ops.launch_count(reset=True)
+    monkeypatch.setenv("TH_FUSE_INTEGRATE", "0")
+    c = ops.render_rays(f1, *rays, S, mode=ops.TH_RENDER_DENSE, want_raw=True)
+    n_plain = ops.launch_count(reset=True)
+    monkeypatch.delenv("TH_FUSE_INTEGRATE")
+    torch.cuda.synchronize()
+    for k in ("rgb_map", "acc_map", "depth_map"):
+        assert torch.equal(a[k], c[k]), k
+        assert torch.equal(b[k], c[k]), k
+    assert torch.equal(b["raw"], c["raw"])
+    assert n_plain - n_fused == (1 if 128 % S == 0 else 0)   # k_integrate is gone from the fused form
+    want = orc.render(tf, S, tokens=tokens, white_bkgd=white) if S == 16 else None
+    if want is not None:
+        assert (a["rgb_map"].cpu() - want["rgb_map"][0]).abs().max().item() <= 1e-4

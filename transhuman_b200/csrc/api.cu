@@ -537,9 +537,17 @@ static int cached_header(const ThFrame* f, PackedHeader* h, cudaStream_t st) {
 }
 
 // feature kernel + MLP over a list of points, in chunks
+// the layer-chained kernel runs this frame's network (mlp_chain.cu) -- otherwise the layer-at-a-time schedules
+static bool uses_chain(const ThFrame* f) {
+  const char* e = getenv("TH_CHAIN");
+  const int use_chain = e ? atoi(e) : 1;
+  const bool premapped = (f->flags & TH_FLAG_PREMAPPED) != 0;
+  return !(f->flags & (TH_FLAG_SIMT_MLP | TH_FLAG_LAYERWISE)) && (use_chain || premapped) && chain_supported(f->n_views);
+}
+
 static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& hdr, PointSource src,
                       const int32_t* ids, int64_t n_list, const Workspace& ws, float* raw, float* alpha_out,
-                      int alpha_only, int zero_rgb, cudaStream_t st) {
+                      int alpha_only, int zero_rgb, cudaStream_t st, const CompositeArgs* cmp = nullptr) {
   const int V = fr.V;
   for (int64_t first = 0; first < n_list; first += ws.chunk_pts) {
     int64_t P = n_list - first < ws.chunk_pts ? n_list - first : ws.chunk_pts;
@@ -594,19 +602,18 @@ static int run_points(const ThFrame* f, const FrameDev& fr, const PackedHeader& 
     run.use_tensor_cores = use_tc;
     run.inputs_are_images = use_tc;
     run.premapped = premapped ? 1 : 0;
+    if (cmp) run.cmp = *cmp;
     // one layer-chained launch per chunk (mlp_chain.cu) unless TH_CHAIN=0 asks for the
     // layer-at-a-time schedule; its scratch is the (otherwise unused) S/X/XT/NET/KP/KS block
-    static const int use_chain = [] {
-      const char* e = getenv("TH_CHAIN");
-      return e ? atoi(e) : 1;
-    }();
     int num_sms = 0;
     if (device_sm_count(&num_sms)) return TH_ECUDA;
     const size_t scratch_room = ws.compact_sms > 0 ? chain_scratch_bytes(P, V, ws.compact_sms)  // sized for it
                                                    : (size_t)Pp * V * (256 * 4 + 128 * 2) * 4;  // b.s ... b.ks are contiguous
-    if (use_tc && (use_chain || premapped) && !(f->flags & TH_FLAG_LAYERWISE) && chain_supported(V) &&
-        chain_scratch_bytes(P, V, num_sms) <= scratch_room) {
+    if (uses_chain(f) && chain_scratch_bytes(P, V, num_sms) <= scratch_room) {
       rc = mlp_forward_chain(run, b, hdr, reinterpret_cast<unsigned char*>(b.s), nullptr, st);
+    } else if (cmp) {
+      set_error("fused compositing needs the layer-chained schedule");
+      rc = TH_EUNSUPPORTED;
     } else if (premapped) {
       set_error("TH_FLAG_PREMAPPED: the layer-chained schedule is not available for this chunk");
       rc = TH_EUNSUPPORTED;
@@ -662,12 +669,31 @@ int th_render_rays(const ThFrame* f, const ThRays* r, ThOut* o, int32_t culled, 
   const int white = (f->flags & TH_FLAG_WHITE_BKGD) ? 1 : 0;
 
   if (!culled) {
-    if ((rc = run_points(f, fr, hdr, src, nullptr, NP, ws, raw, nullptr, 0, 0, st))) return rc;
+    // Dense rays on the chain schedule with S | 128: the rows of a 128-point tile are whole rays, so the chain kernel
+    // composites them in its fc_4' epilogue (CompositeArgs) -- no raw tensor unless the caller asks for it, no
+    // k_integrate.  TH_FUSE_INTEGRATE=0 keeps the two-kernel form (tests compare the two bit for bit).
+    const char* fuse_env = getenv("TH_FUSE_INTEGRATE");
+    const bool fuse = uses_chain(f) && S <= 128 && 128 % S == 0 && ws.chunk_pts % S == 0 && !(fuse_env && !atoi(fuse_env));
+    CompositeArgs cmp{};
+    if (fuse) {
+      cmp.rgb_map = o->rgb_map;
+      cmp.acc_map = o->acc_map;
+      cmp.depth_map = o->depth_map;
+      cmp.near_ = r->near_;
+      cmp.far_ = r->far_;
+      cmp.t_vals = r->t_vals;
+      cmp.ray_d = r->ray_d;
+      cmp.S = S;
+      cmp.white_bkgd = white;
+    }
+    if ((rc = run_points(f, fr, hdr, src, nullptr, NP, ws, fuse ? o->raw : raw, nullptr, 0, 0, st, fuse ? &cmp : nullptr)))
+      return rc;
     if (o->counters_host) {
       o->counters_host[0] = NP;
       o->counters_host[1] = N;
       o->counters_host[2] = NP;
     }
+    if (fuse) return TH_OK;
   } else {
     uint8_t* m = o->pts_mask ? o->pts_mask : ws.mask;
     TH_CUDA(cudaMemsetAsync(ws.counters, 0, 64, st));

@@ -134,6 +134,36 @@ __device__ __forceinline__ void split_hl2(float x, float y, uint32_t& hi, uint32
   lo = cvt_f16x2_sat(x - hf.x, y - hf.y);
 }
 
+// ---- raw2outputs (nerf_net_utils.py:14-59) in two parts, shared by k_integrate and by the chain kernel's fused
+// compositing so that both produce the same bits: the per-sample terms (independent of the other samples) and the
+// sequential step along the ray (transmittance as a running product, sums in sample order).
+struct SampleTerm {
+  float alpha, r, g, b;
+};
+// dist = (z_{s+1} - z_s) or 1e10 for the last sample, already multiplied by |ray_d|
+__device__ __forceinline__ SampleTerm composite_sample(float4 raw, float dist) {
+  SampleTerm t;
+  const float sigma = fmaxf(raw.w, 0.f);
+  t.alpha = __fsub_rn(1.0f, expf(-__fmul_rn(sigma, dist)));
+  t.r = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-raw.x)));
+  t.g = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-raw.y)));
+  t.b = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-raw.z)));
+  return t;
+}
+struct RayAcc {
+  float T, r, g, b, acc, depth;
+};
+__device__ __forceinline__ RayAcc ray_acc_init() { return RayAcc{1.0f, 0.f, 0.f, 0.f, 0.f, 0.f}; }
+__device__ __forceinline__ void composite_step(RayAcc& a, const SampleTerm& t, float z) {
+  const float w = __fmul_rn(t.alpha, a.T);
+  a.r = __fmaf_rn(w, t.r, a.r);
+  a.g = __fmaf_rn(w, t.g, a.g);
+  a.b = __fmaf_rn(w, t.b, a.b);
+  a.depth = __fmaf_rn(w, z, a.depth);
+  a.acc = __fadd_rn(a.acc, w);
+  a.T = __fmul_rn(a.T, __fadd_rn(__fsub_rn(1.0f, t.alpha), 1e-10f));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -220,6 +220,14 @@ size_t mlp_compact_bytes(int64_t P, int V, size_t chain_scratch);
 // (rgb x3, alpha) to raw[dst_ids ? dst_ids[first + i] : first + i].  alpha_only
 // skips the colour branch (a12).  zero_rgb_if_transparent reproduces the
 // progressive variant's output (rgb = 0 where alpha_raw <= 0).
+// Fused compositing (chain schedule, dense rays): raw2outputs (nerf_net_utils.py:14-59) inside the fc_4' epilogue.
+// A 128-row tile of the chain kernel holds whole rays when the sample count divides 128 and the chunk starts on a ray
+// boundary, so a ray's alpha, transmittance and weighted sums never leave the CTA: no raw tensor, no k_integrate.
+struct CompositeArgs {
+  float *rgb_map, *acc_map, *depth_map;  // rgb_map == nullptr: off (raw is written, k_integrate composites)
+  const float *near_, *far_, *t_vals, *ray_d;
+  int32_t S, white_bkgd;
+};
 struct MlpRun {
   const unsigned char* weights;  // device blob
   int64_t P;
@@ -235,6 +243,7 @@ struct MlpRun {
   // experimental (TH_FLAG_PREMAPPED, chain schedule only): the pix block holds the images
   // [X (V*Pp,256) | P2 (V*Pp,128)] and pix_mean the image R (Pp,128) -- see k_features PRE
   int premapped;
+  CompositeArgs cmp;  // chain schedule only; requires dst_ids == nullptr, first % S == 0, P % S == 0, 128 % S == 0
   // test hook (th_debug_chain_program): mlp_forward_chain copies its job program here and returns
   // before touching the device
   void* program_dump;

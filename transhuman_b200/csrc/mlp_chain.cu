@@ -109,6 +109,7 @@ struct Program {
   int32_t njobs, num_units, V, has_mix, zero_rgb, alpha_only, kp_col;
   int32_t deferred_tail;  // 1 = the program has shift -1 jobs (and two alternating A slot sets)
   int32_t ks_col[TH_MAX_VIEWS];
+  CompositeArgs cmp;  // fused compositing in the EPI_RGB epilogue (rgb_map == nullptr: off)
   int32_t dbg;  // TH_CHAIN_DBG: timing experiments only, 1 = skip the mix, 2 = skip the store fences (results wrong); 16/32/64/128 = random delays in the loader / MMA / epilogue / mix role, 512 = writer-side fences as well (results valid)
   unsigned long long* stats;  // TH_CHAIN_STATS=1: per-CTA wait-time counters (cycles), else nullptr
 };
@@ -240,7 +241,9 @@ constexpr int STATS_PER_CTA = 32 + 3 * MAX_JOBS;  // role totals + per-job MMA w
 constexpr int ATAB_LD = 9;  // attention table row stride (floats): V x V <= 9 entries per point
 // stages | bias (2 x 256) | attention table | partial scores | control (256 B) | mix staging (96 B per mix thread)
 constexpr uint32_t MIX_RING_OFF = NSTAGE * STAGE_BYTES + 2 * 256 * 4 + 128 * ATAB_LD * 4 + 128 * 4 * 4 + 256;
-constexpr size_t SMEM_BYTES = (size_t)MIX_RING_OFF + (size_t)MIX_THREADS * 96;
+// ... | per-sample compositing terms (alpha, r, g, b, z per row of the tile)
+constexpr uint32_t COMP_OFF = MIX_RING_OFF + MIX_THREADS * 96;
+constexpr size_t SMEM_BYTES = (size_t)COMP_OFF + 128 * 5 * 4;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     k_chain(const __grid_constant__ Program pg) {
@@ -799,13 +802,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
               o2 = fmaf(t, __ldg(pg.rgb_w + 256 + c0 + e), o2);
             }
           }
-          if (pt < pg.P) {
+          const bool live = pt < pg.P;
+          if (live) {
             o0 += __ldg(pg.rgb_b);
             o1 += __ldg(pg.rgb_b + 1);
             o2 += __ldg(pg.rgb_b + 2);
             if (pg.zero_rgb && !(alpha_reg > 0.f)) o0 = o1 = o2 = 0.f;
             const int64_t dst = pg.dst_ids ? (int64_t)pg.dst_ids[pg.first + pt] : pg.first + pt;
-            reinterpret_cast<float4*>(pg.raw)[dst] = make_float4(o0, o1, o2, alpha_reg);
+            if (pg.raw) reinterpret_cast<float4*>(pg.raw)[dst] = make_float4(o0, o1, o2, alpha_reg);
+          }
+          if (pg.cmp.rgb_map) {
+            // Fused compositing (raw2outputs, nerf_net_utils.py:14-59): the rows of this tile are whole rays
+            // (S | 128, the chunk starts on a ray boundary).  Every thread forms the terms of its own sample --
+            // alpha from sigma and the interval, the sigmoids -- and the thread that owns a ray's first sample walks
+            // the ray in sample order with the transmittance in a register: the same two functions, in the same
+            // order, as k_integrate.
+            const int S = pg.cmp.S;
+            const int s = et % S;
+            const int64_t ray = (pg.first + pt - s) / S;
+            float* sc = reinterpret_cast<float*>(smem_raw + COMP_OFF) + et * 5;
+            if (live) {
+              const float nrm = norm3(__ldg(pg.cmp.ray_d + ray * 3), __ldg(pg.cmp.ray_d + ray * 3 + 1),
+                                      __ldg(pg.cmp.ray_d + ray * 3 + 2));
+              const float near_ = __ldg(pg.cmp.near_ + ray), far_ = __ldg(pg.cmp.far_ + ray);
+              const float z = sample_z(near_, far_, __ldg(pg.cmp.t_vals + s));
+              float dist = s + 1 < S ? __fsub_rn(sample_z(near_, far_, __ldg(pg.cmp.t_vals + s + 1)), z) : 1e10f;
+              dist = __fmul_rn(dist, nrm);
+              const SampleTerm t = composite_sample(make_float4(o0, o1, o2, alpha_reg), dist);
+              sc[0] = t.alpha;
+              sc[1] = t.r;
+              sc[2] = t.g;
+              sc[3] = t.b;
+              sc[4] = z;
+            }
+            asm volatile("bar.sync 3, 128;" ::: "memory");  // the four group-0 warps
+            if (live && s == 0) {
+              RayAcc a = ray_acc_init();
+              for (int i = 0; i < S; ++i) {
+                const float* q5 = sc + i * 5;
+                composite_step(a, SampleTerm{q5[0], q5[1], q5[2], q5[3]}, q5[4]);
+              }
+              const float bg = pg.cmp.white_bkgd ? 1.0f - a.acc : 0.f;
+              pg.cmp.rgb_map[ray * 3] = pg.cmp.white_bkgd ? a.r + bg : a.r;
+              pg.cmp.rgb_map[ray * 3 + 1] = pg.cmp.white_bkgd ? a.g + bg : a.g;
+              pg.cmp.rgb_map[ray * 3 + 2] = pg.cmp.white_bkgd ? a.b + bg : a.b;
+              pg.cmp.acc_map[ray] = a.acc;
+              pg.cmp.depth_map[ray] = a.depth;
+            }
+            // (the terms are overwritten by the next unit's fc_4' epilogue, ~20 named barriers of all epilogue
+            // warps later: the walking threads' warps take part in every one of them)
           }
         }
         // this warp is done with the accumulator of job G
@@ -1234,6 +1279,13 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
   pg.zero_rgb = run.zero_rgb_if_transparent;
   pg.alpha_only = run.alpha_only;
   pg.num_units = (int)(Pp / 256);
+  pg.cmp = run.cmp;
+  if (pg.cmp.rgb_map && (run.alpha_only || run.dst_ids || pg.cmp.S < 1 || 128 % pg.cmp.S || run.first % pg.cmp.S ||
+                         P % pg.cmp.S)) {
+    set_error("mlp_forward_chain: fused compositing needs dense rays, S | 128 and chunks of whole rays (S %d, first %lld, P %lld)",
+              pg.cmp.S, (long long)run.first, (long long)P);
+    return TH_EINVAL;
+  }
 
   int num_sms = 0;
   if (device_sm_count(&num_sms)) return TH_ECUDA;
