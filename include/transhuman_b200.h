@@ -176,7 +176,14 @@ size_t th_frame_workspace_bytes(const ThFrame* frame, int64_t n_points, int32_t 
  * 607-656, Network.forward cross_transformer.py:207-271 and raw2outputs
  * nerf_net_utils.py:14-59) when culled != 0 (TH_RENDER_*).  Rows a1-a11 of
  * SURVEY 8(a).  Synchronises the stream once when culled != 0 (to read the
- * survivor count). */
+ * survivor count, which sizes the launches over the compacted point list and
+ * decides the reference's <= 2400-ray branch; measured cost: the launches of
+ * a culled 512x512x64 frame add up to within 85 us = 1 % of the frame time).
+ * Dense rays whose sample count divides 128 are composited inside the chain
+ * kernel's last epilogue (raw2outputs fused: `out->raw` is written only when
+ * it is not NULL and no separate integration kernel runs); other sample
+ * counts and the culled modes write raw to the workspace and composite with
+ * th_integrate's kernel -- the same two device functions, the same bits. */
 int th_render_rays(const ThFrame* frame, const ThRays* rays, ThOut* out, int32_t culled,
                    void* workspace, size_t workspace_bytes, void* stream);
 
