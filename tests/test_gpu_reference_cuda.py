@@ -69,9 +69,19 @@ def _capture_raw(ns):
 
 def test_full_frame_c2_dense_matches_reference_cuda():
     """BASELINE configs[1] in full: every one of the 262,144 rays against the reference's Renderer.render."""
+    _full_frame_dense(64, 300)
+
+
+def test_full_frame_c3_dense_matches_reference_cuda():
+    """BASELINE configs[2] in full (512x512 rays x 128 samples, 1500 tokens: 33.5 M sample points, S = 128 = one ray per
+    128-row tile of the fused compositing)."""
+    _full_frame_dense(128, 1500)
+
+
+def _full_frame_dense(S, n_class):
     from oracle.make_golden import build_reference
-    S, H = 64, 512
-    fr = synth.make_frame(H=H, W=H, n_class=300, V=3, feat_hw=256, seed=0, alpha_bias_shift=-15.0)
+    H = 512
+    fr = synth.make_frame(H=H, W=H, n_class=n_class, V=3, feat_hw=256, seed=0, alpha_bias_shift=-15.0)
     ns, net, renderer, batch = build_reference(fr, S, device="cuda", knn=_knn_cuda)
     box, restore = _capture_raw(ns)
     try:
@@ -96,7 +106,7 @@ def test_full_frame_c2_dense_matches_reference_cuda():
               f"(ours {got['raw'][r, s_].cpu().tolist()} ref {raw_ref[r, s_].tolist()}), rgb diff {float(e_rgb[r]):.3e}")
     n_edge = assert_maps_close(got, {k: ref[k].cpu() for k in ("rgb_map", "acc_map", "depth_map")}, raw_ref,
                                box["z_vals"].reshape(-1, S).cpu(), tf["ray_d"], S, float(fr["far"].max()),
-                               "full C2 frame vs reference torch-CUDA (TF32 off)")
+                               f"full 512x512x{S} frame, {n_class} tokens, vs reference torch-CUDA (TF32 off)")
     assert n_edge < 0.001 * H * H
     scale = max(1.0, float(raw_ref.abs().max()))
     raw_err = (got["raw"].cpu() - raw_ref).abs().max().item()
@@ -111,9 +121,18 @@ def test_full_frame_c2_dense_matches_reference_cuda():
 
 def test_full_frame_c2_culled_matches_reference_cuda():
     """The same frame through render_fast (what run.py executes): exact survivor set, culled rays exactly 0."""
+    _full_frame_culled(64, 300)
+
+
+def test_full_frame_c3_culled_matches_reference_cuda():
+    """configs[2] through render_fast: 1500 tokens, so the K-NN of the surviving points runs through the token grid."""
+    _full_frame_culled(128, 1500)
+
+
+def _full_frame_culled(S, n_class):
     from oracle.make_golden import build_reference
-    S, H = 64, 512
-    fr = synth.make_frame(H=H, W=H, n_class=300, V=3, feat_hw=256, seed=0, alpha_bias_shift=-15.0)
+    H = 512
+    fr = synth.make_frame(H=H, W=H, n_class=n_class, V=3, feat_hw=256, seed=0, alpha_bias_shift=-15.0)
     ns, net, renderer, batch = build_reference(fr, S, device="cuda", knn=_knn_cuda)
     box, restore = _capture_raw(ns)
     try:
@@ -136,7 +155,8 @@ def test_full_frame_c2_culled_matches_reference_cuda():
     raw_full[pm.cpu()] = box["raw"].reshape(-1, S, 4).cpu()
     _, z = orc.get_sampling_points(tf["ray_o"][None], tf["ray_d"][None], tf["near"][None], tf["far"][None], S)
     assert_maps_close(got, {k: ref[k].cpu() for k in ("rgb_map", "acc_map", "depth_map")}, raw_full, z[0],
-                      tf["ray_d"], S, float(fr["far"].max()), "full C2 frame, render_fast vs reference torch-CUDA")
+                      tf["ray_d"], S, float(fr["far"].max()),
+                      f"full 512x512x{S} frame, {n_class} tokens, render_fast vs reference torch-CUDA")
 
 
 def test_plugin_through_make_renderer_matches_reference_renderer():
