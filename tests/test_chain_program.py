@@ -243,9 +243,10 @@ def _interpret(blob, head, jobs, data):
 
 @pytest.mark.parametrize("V", [1, 2, 3])
 @pytest.mark.parametrize("variant", ["default", "alpha_only", "premapped", "premapped_alpha_only", "premapped_tmem",
-                                     "premapped_tmem_alpha_only", "premapped_defer", "premapped_defer_alpha_only"])
+                                     "premapped_tmem_alpha_only", "premapped_defer", "premapped_defer_alpha_only",
+                                     "premapped_deep", "premapped_deep_alpha_only"])
 def test_chain_program(lib, V, variant, monkeypatch):
-    monkeypatch.setenv("TH_CHAIN_DEFER", "1" if "defer" in variant else "0")
+    monkeypatch.setenv("TH_CHAIN_DEFER", "1" if "defer" in variant else "2" if "deep" in variant else "0")
     from oracle import transhuman_oracle as orc
     w = synth.make_weights(seed=9)
     blob = _pack(lib, w, V)
@@ -260,7 +261,10 @@ def test_chain_program(lib, V, variant, monkeypatch):
         assert head["has_mix"] == 1 and not any(jb["epi"] == EPI_MIX for jb in jobs)
     _check_tmem(head, jobs)
     _check_scratch(head, jobs)
-    if "defer" not in variant:
+    if "deep" in variant:                                     # everything behind the scores runs one unit late
+        assert head["deferred"] == 1
+        assert [jb["shift"] for jb in jobs] == [0] * (3 * V) + [-1] * (2 * V + 1 if alpha_only else 3 * V + 2)
+    elif "defer" not in variant:
         assert head["deferred"] == 0 and all(jb["shift"] == 0 for jb in jobs)
     else:                                                     # opt-in: the tail of the network deferred by one unit
         assert head["deferred"] == 1 and sum(jb["shift"] == -1 for jb in jobs) == (1 if alpha_only else V + 2)

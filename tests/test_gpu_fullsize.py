@@ -108,11 +108,14 @@ def test_chain_kernel_is_insensitive_to_role_timing(monkeypatch):
         assert torch.equal(a["raw"], b["raw"]) and torch.equal(a["rgb_map"], b["rgb_map"])
     # the opt-in schedule that issues the tail of the network one unit late (software pipelining across units,
     # alternating scratch slot sets): same arithmetic in a different order of jobs -> bit-identical, also under jitter
-    monkeypatch.setenv("TH_CHAIN_DEFER", "1")
-    for bits in ("0", "240"):
-        monkeypatch.setenv("TH_CHAIN_DBG", bits)
-        c = ops.render_rays(frame, *(r[sel] for r in rays), S, mode=ops.TH_RENDER_DENSE, want_raw=True)
-        assert torch.equal(a["raw"], c["raw"]) and torch.equal(a["rgb_map"], c["rgb_map"])
+    # ("2" = deep deferral: everything behind the scores -- fc_1' ... fc_4' -- one unit late, so that the tensor pipe
+    # never waits for the in-place mix; the attention table alternates with the unit's parity)
+    for mode in ("1", "2"):
+        monkeypatch.setenv("TH_CHAIN_DEFER", mode)
+        for bits in ("0", "240", "128"):
+            monkeypatch.setenv("TH_CHAIN_DBG", bits)
+            c = ops.render_rays(frame, *(r[sel] for r in rays), S, mode=ops.TH_RENDER_DENSE, want_raw=True)
+            assert torch.equal(a["raw"], c["raw"]) and torch.equal(a["rgb_map"], c["rgb_map"]), (mode, bits)
     monkeypatch.delenv("TH_CHAIN_DBG")
     monkeypatch.delenv("TH_CHAIN_DEFER")
 

@@ -257,7 +257,10 @@ constexpr int ATAB_LD = 9;  // attention table row stride (floats): V x V <= 9 e
 constexpr uint32_t MIX_RING_OFF = NSTAGE * STAGE_BYTES + 2 * 256 * 4 + 128 * ATAB_LD * 4 + 128 * 4 * 4 + 256;
 // ... | per-sample compositing terms (alpha, r, g, b, z per row of the tile)
 constexpr uint32_t COMP_OFF = MIX_RING_OFF + MIX_THREADS * 96;
-constexpr size_t SMEM_BYTES = (size_t)COMP_OFF + 128 * 5 * 4;
+// ... | second attention table: the table alternates with the unit's parity, so that the score epilogues of unit u + 1
+// may run while the mix warps still read the table of unit u (deep deferral, TH_CHAIN_DEFER=2)
+constexpr uint32_t ATAB1_OFF = COMP_OFF + 128 * 5 * 4;
+constexpr size_t SMEM_BYTES = (size_t)ATAB1_OFF + 128 * ATAB_LD * 4;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     k_chain(const __grid_constant__ Program pg) {
@@ -266,6 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   float* s_bias = reinterpret_cast<float*>(smem_raw + NSTAGE * STAGE_BYTES);  // 2 x 256
   float* s_atab = s_bias + 512;                                               // 128 x ATAB_LD
   float* s_part = s_atab + 128 * ATAB_LD;                                     // 128 x 4 partial scores
+  float* s_atab1 = reinterpret_cast<float*>(smem_raw + ATAB1_OFF);            // the table of odd units
   unsigned char* ctrl_ptr = reinterpret_cast<unsigned char*>(s_part + 128 * 4);
   const uint32_t ctrl = base + NSTAGE * STAGE_BYTES + 2048 + 128 * ATAB_LD * 4 + 128 * 4 * 4;
   const uint32_t bar_full = ctrl, bar_empty = ctrl + 24, bar_pfull = ctrl + 48, bar_tfull = ctrl + 72;
@@ -403,7 +407,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
               x[i][2] = join2(ch[i].z, cl[i].z);
               x[i][3] = join2(ch[i].w, cl[i].w);
             }
-          const float* A = s_atab + row * ATAB_LD;
+          const float* A = ((it & 1) ? s_atab1 : s_atab) + row * ATAB_LD;
 #pragma unroll
           for (int j = 0; j < CHAIN_MAX_V; ++j)
             if (j < V) {
@@ -451,7 +455,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     if (lane == 0) {
       uint32_t s = 0, ph = 0;  // stage index and its phase bit
       for (int it = 0; it < n_iter; ++it) {
-        const uint32_t mix_target = (uint32_t)(MIX_THREADS / 32) * (uint32_t)(it + 1);
         // What this thread's fences already cover in this iteration: bit j = the tile job j stored, bit kb = the
         // mix of k-block kb.  A fence executed after a counter was seen complete orders those stores before
         // every later copy, so each dependency costs one wait + fence per unit, not one per reader -- a
@@ -467,6 +470,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           // iteration work on; a consumer needs its producers' outputs for ITS unit: it + shift + 1 executions
           // (a deferred consumer of a shift-0 producer needs one execution less than the producer's own class)
           const uint32_t done_target = (uint32_t)EPI_WARPS * (uint32_t)(it + jb.shift + 1);
+          const uint32_t mix_target = (uint32_t)(MIX_THREADS / 32) * (uint32_t)(it + jb.shift + 1);  // the mix of ITS unit
           const uint32_t aset_off = (ui & 1) ? aset_bytes : 0u;
           const uint32_t b_bytes = (uint32_t)jb.N * 128u;  // N/2 rows x 128 B x (hi, lo)
           const unsigned char* w = jb.wimg + (size_t)rank * b_bytes;
@@ -582,7 +586,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     const int q = warp & 3;          // TMEM lane quadrant
     const int grp = (warp - EPI_WARP0) >> 2;
     const int et = q * 32 + lane;    // row inside the 128-row tile
-    float* atab = s_atab + et * ATAB_LD;
     float alpha_reg = 0.f;
     uint32_t G = 0;
     for (int it = 0; it < n_iter; ++it) {
@@ -594,6 +597,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         const int64_t ptile = 2 * (int64_t)(cluster_id + ui * nclusters) + rank;
         const int64_t pt = ptile * BM + et;  // chunk-local point of this thread (per-point jobs)
         const uint32_t out_aset_off = (jb.out_aset && (ui & 1)) ? aset_bytes : 0u;
+        float* atab = ((ui & 1) ? s_atab1 : s_atab) + et * ATAB_LD;  // this unit's attention table
         const int N = jb.N, epi = jb.epi;
         float* bias_s = s_bias + (G & 1) * 256;
         // this job's bias -> shared memory (double buffered by job parity; the named barrier of EVERY
@@ -1098,8 +1102,15 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
   // faster: the kernel moves ~68 KB per point through L2 at ~85 % of the chip's L2 throughput cap, so the tail's
   // operand stream and the mix now contend (mix 50 -> 68 kcycles per unit, fc_3 waits 20 kcycles for operands), and the
   // larger scratch costs L2 hits (71 % -> 59 %, DRAM 6.8 -> 9.3 GB per launch).  Measured in profiles/README.md (r2h-r2j).
+  // TH_CHAIN_DEFER=2, "deep" deferral: EVERYTHING behind the scores -- fc_1', fc_2 and the tail -- runs one iteration
+  // late, i.e. iteration `it` issues the front of unit `it` (fc_0, key embeds, scores) and then fc_1' ... fc_4' of unit
+  // `it - 1`, whose in-place mix has had the whole previous back half to finish: the tensor pipe never waits for the
+  // mix warps.  Same job order as the plain program, only the unit the back half works on changes; the attention
+  // table alternates with the unit's parity (the scores of unit `it` are written while the mix of unit `it - 1` may
+  // still read its own).
   const char* defer_env = getenv("TH_CHAIN_DEFER");
-  const bool defer = x_in_chunk && !tmix && defer_env && atoi(defer_env);
+  const int defer_mode = (x_in_chunk && !tmix && defer_env) ? atoi(defer_env) : 0;
+  const bool defer = defer_mode == 1, deep = defer_mode == 2;
   auto add_fc3 = [&]() {
     const int j = B.pg.njobs++;
     Job& jb = B.pg.job[j];
@@ -1188,7 +1199,8 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
     }
   }
   if (!defer) add_tail();
-  if (defer) {
+  if (defer || deep) {
+    if (deep) n_tail = B.pg.njobs - first_tail;  // fc_1' ... fc_4': every job behind the front
     B.pg.deferred_tail = 1;
     const uint32_t a_end = (uint32_t)V * SCR_ACT, b_end = 2u * a_end;
     auto remap = [&](uint32_t off, int32_t* aset) {   // slot A -> parity-alternating set; slot B -> behind both A sets
