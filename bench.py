@@ -589,7 +589,9 @@ def main():
                 "binding": ("latency of the job pipeline (layer -> epilogue -> store -> fence -> TMA -> next layer at a "
                             "dependency distance of three jobs, plus the attention-mix window): MMA issuer busy ~47 % of a "
                             "unit, tensor pipe 51 % active under ncu (profiles/r2_chain_details.txt); not HBM bound "
-                            "(2.6 TB/s of 6.55); the fp16x3 split caps roofline.frac at 0.54 (DESIGN 4-5)"
+                            "(2.6 TB/s of 6.55); the fp16x3 split caps roofline.frac at 0.54; the board sits at its 1 kW power cap "
+                            "(SM clock 1.5-1.6 of 1.965 GHz): a schedule with 6.5 % fewer chain cycles runs at a 5 % lower "
+                            "clock (DESIGN 4-5, profiles/README.md)"
                             if chain else "HBM (K=256 layers) / tensor (K>=512)"),
                 "hbm_algorithmic_gbs": BYTES_PER_RAY * N_rays / (ms_step * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
