@@ -78,7 +78,17 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def wait_first(self, timeout_s: float = 20.0):
+        """Block until nvidia-smi has delivered its first sample (its start-up is over)."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout_s and self.proc.poll() is None:
+            time.sleep(0.05)
+
+    def mark(self):
+        """The timed region starts here: earlier samples (warm-up) are not reported."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -99,11 +109,12 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = self.rows[self.first:]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
-        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        reasons = sorted({n for r in rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        pw = [float(r[3]) for r in rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
@@ -476,18 +487,35 @@ def main():
         step(dev_rays)
     barrier()
     ops.profile_stop()
-    for _ in range(warm_steps - max(args.warmup, args.steps)):
-        step(dev_rays)
-    barrier()
+    # nvidia-smi is started, and its first sample awaited, BEFORE the last warm-up steps: its start-up (NVML
+    # initialisation over every GPU of the box; seconds on a fresh box) otherwise falls into the timed region and
+    # stalls the device once for 0.1-0.4 s -- seen as a first timed region 10-20 % slower than the profiled pass right
+    # behind it in the first bench process on a fresh box.  Only the samples taken from the start of the timed region
+    # on are reported (`mark`).
     clocks = ClockSampler(local_rank)
     clocks.start()
+    clocks.wait_first()      # (on a fresh box the first nvidia-smi takes seconds to come up)
+    for _ in range(max(warm_steps - max(args.warmup, args.steps), 6)):
+        step(dev_rays)
+    barrier()
+    clocks.mark()
     ops.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_marks = []  # TH_BENCH_STEP_TIMES=1: one event per step, per-step times to stderr (diagnosis of transients)
     e0.record()
     for _ in range(args.steps):
         img, last = step(dev_rays)
+        if os.environ.get("TH_BENCH_STEP_TIMES"):
+            step_marks.append(torch.cuda.Event(enable_timing=True))
+            step_marks[-1].record()
     e1.record()
     barrier()
+    if step_marks:
+        prev, per = e0, []
+        for m in step_marks:
+            per.append(round(prev.elapsed_time(m), 1))
+            prev = m
+        print(f"[bench] rank {rank} timed region, ms per step: {per}", file=sys.stderr)
     launches = ops.launch_count()
     ops.profile_start()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtranshuman_b200.so")
+LIB_PATH = os.environ.get("TH_LIB_PATH") or os.path.join(HERE, "libtranshuman_b200.so")  # TH_LIB_PATH: A/B builds
 
 TH_MAX_VIEWS = 4
 TH_MAX_KNN = 16
