@@ -478,10 +478,12 @@ def main():
     # pool exists; the timed region itself runs WITHOUT it (an event pair around each of the ~120 launches of a step
     # costs 1-12 ms per step depending on the box's host), and the per-kernel-category times come from a second pass
     # of the same K steps, profiler on, right behind it (`category_timing` in the line says so).
-    # W is a minimum: the load is kept on for at least 12 steps (~2.7 s) before the timed region so that the
-    # power-capped clocks have settled -- the first step after a cold start runs boosted and some boxes then dip below
-    # their steady state (tools/transient_probe.py).  A fixed count, so that every rank runs the same collectives.
-    warm_steps = max(args.warmup, args.steps, 12)
+    # W is a minimum: the load is kept on for at least 36 steps (~8 s) before the timed region so that the
+    # power-capped clocks have settled -- the first step after a cold start runs boosted, and in the first process on
+    # a fresh box the power controller then holds the clock below its steady state for several seconds (a timed
+    # region at 4.5-9 s after the start read 3.4 % slower than the same steps at 9-13 s; tools/transient_probe.py).
+    # A fixed count, so that every rank runs the same collectives.
+    warm_steps = max(args.warmup, args.steps, 36)
     ops.profile_start()                      # the first steps with the profiler on: its CUDA-event pool exists afterwards
     for _ in range(max(args.warmup, args.steps)):
         step(dev_rays)
