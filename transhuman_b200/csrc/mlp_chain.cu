@@ -1056,7 +1056,10 @@ int mlp_forward_chain(const MlpRun& run, const MlpBuffers& b, const PackedHeader
                     B.pg.ks_col[v], 2);
   for (int v = 0; v < V; ++v) {
     Seg x = x_in_chunk ? B.in_view(b.pix, 256, v) : Builder::scr(B.slotB(v), 256, j_x[v]);
-    x.keep = tmix ? 1 : 0;  // X is read again by the Y jobs
+    // X is read again: by the Y jobs (TMEM-side mix), or -- in-place mix -- by the mix warps ~50 kcycles later, which
+    // otherwise find it evicted (the loader's default for chunk inputs is evict-first).  TH_CHAIN_XKEEP=0: A/B knob.
+    static const bool xkeep = !(getenv("TH_CHAIN_XKEEP") && atoi(getenv("TH_CHAIN_XKEEP")) == 0);
+    x.keep = (tmix || (x_in_chunk && xkeep)) ? 1 : 0;
     const int j = B.add({x}, wimg(h.h_k0), wf(h.k0_b), 128, 0, EPI_SCORES, 0, v, B.pg.kp_col, v == 0 ? 2 : 1);
     B.pg.job[j].bias2 = wf(h.k1_b);
     if (v == V - 1)
